@@ -1,0 +1,120 @@
+/*
+ * t2h.h -- C ABI of the B200 (sm_100a) hot path of TomoSAR2Height.
+ *
+ * Every entry point replaces one third-party operator call of the reference
+ * (paths relative to the reference repository).  The reference is pure Python, so the
+ * "FFI" a maintainer binds is ctypes; there are no torch types in
+ * any signature: raw device pointers, sizes and a CUDA stream.
+ *
+ * Conventions
+ *   - return value: 0 = ok, otherwise a T2H_ERR_* code (t2h_status_string() names it).
+ *     Nothing throws across the boundary, nothing is allocated, freed or retained:
+ *     the caller owns every buffer (inputs, outputs, workspaces).
+ *   - all functions are re-entrant and hold no global or thread-local state (forward runs on
+ *     the caller's thread, backward on the autograd thread); work is enqueued on `stream`.
+ *   - "rows": per-point feature matrices are row-major (n_rows, C) fp32, one row per point.
+ *   - "plane": feature planes are channels-last, (B, r, r, C) fp32, i.e. the memory layout of
+ *     a torch (B, C, r, r) tensor with torch.channels_last strides.
+ *   - "topology": points sorted by cell key.  key = b * R*R + code(ix, iy) with code = Morton
+ *     (Z-order) interleave when `morton` != 0, else ix + R*iy.  With Morton keys the segments
+ *     of every coarser power-of-two level r = R >> k are the key ranges
+ *     [cell_start[s << 2k], cell_start[(s + 1) << 2k]), so ONE sort serves every level
+ *     (`shift` = 2k below).  `perm[i]` is the row of the point at sorted position i; a NULL
+ *     `perm` means rows are already stored in sorted order (the fused model path).
+ *   - supported channel counts C: 4,8,16,32,64,128 and multiples of 128 up to 1024.
+ */
+#ifndef T2H_H_
+#define T2H_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* t2h_stream_t; /* cudaStream_t */
+
+enum {
+  T2H_OK = 0,
+  T2H_ERR_INVALID_ARGUMENT = 1,
+  T2H_ERR_UNSUPPORTED_SHAPE = 2,
+  T2H_ERR_CUDA = 3,
+  T2H_ERR_WORKSPACE_TOO_SMALL = 4
+};
+
+int t2h_abi_version(void);
+const char* t2h_status_string(int status);
+
+/* ---- a1: utils/coordinate.py:12-28 coordinate2index --------------------------------------
+ * out_index[i] = trunc(x*reso) + reso * trunc(y*reso), int64, no clamp (bit-exact). */
+int t2h_cell_index(const float* xy, int64_t n_points, int64_t point_stride, int reso,
+                   int64_t* out_index, t2h_stream_t stream);
+
+/* ---- topology (replaces the 10-12 index recomputations per forward: pointnet.py:70,
+ *      alto.py:80,190) ------------------------------------------------------------------- */
+/* keys[i] = b*reso^2 + code(ix,iy), cell coordinates clamped to [0, reso-1]; b = i / n_per_batch */
+int t2h_xy_keys(const float* xyz, int64_t n_points, int64_t point_stride, int64_t n_per_batch,
+                int reso, int morton, int32_t* keys, t2h_stream_t stream);
+/* keys[i] = b*dim_size + index[i]; *flag set non-zero if an index is outside [0, dim_size) */
+int t2h_index_keys(const int64_t* index, int64_t n_points, int64_t n_per_batch, int64_t dim_size,
+                   int32_t* keys, int32_t* flag, t2h_stream_t stream);
+size_t t2h_sort_workspace_bytes(int64_t n_points);
+/* stable sort by key; writes keys_sorted[n], perm[n] (sorted position -> input position) and
+ * cell_start[n_keys + 1] (first sorted position of every key; cell_start[n_keys] = n) */
+int t2h_sort_by_cell(const int32_t* keys, int64_t n_points, int64_t n_keys, void* workspace,
+                     size_t workspace_bytes, int32_t* keys_sorted, int32_t* perm,
+                     int32_t* cell_start, t2h_stream_t stream);
+/* dst[i, :] = src[perm[i], :]  (rows of `width` floats; used for xyz and for re-ordering rows) */
+int t2h_gather_rows(const float* src, const int32_t* perm, int64_t n_rows, int width, float* dst,
+                    t2h_stream_t stream);
+/* dst[perm[i], :] = src[i, :] */
+int t2h_scatter_rows(const float* src, const int32_t* perm, int64_t n_rows, int width, float* dst,
+                     t2h_stream_t stream);
+
+/* ---- a2: pointnet.py:92-99 pool_local = torch_scatter.scatter_max + gather ------------------
+ * Per segment and channel: max over the segment's rows, ties -> first row in sorted order
+ * (= smallest point index, the torch_scatter CPU rule), empty -> 0 / arg -1.
+ *   pooled (n_rows, C), nullable: the max broadcast back to every row of the segment
+ *   plane  (n_seg, C),  nullable: the per-cell max, rows in row-major (b, y, x) cell order
+ *   arg    (n_seg, C)  int32   : winning ROW index (same row order as plane), -1 if empty     */
+int t2h_seg_max_fwd(const float* rows, const int32_t* perm, const int32_t* cell_start,
+                    int64_t n_seg, int shift, int C, int morton, int reso, float* pooled,
+                    float* plane, int32_t* arg, t2h_stream_t stream);
+/* grad_rows[row, c] = (row == arg[seg, c]) ? sum_{rows of seg} grad_pooled[., c] + grad_plane[seg, c] : 0 */
+int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane, const int32_t* perm,
+                    const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton,
+                    int reso, const int32_t* arg, float* grad_rows, t2h_stream_t stream);
+
+/* ---- a3: pointnet.py:101-111, alto.py:76-88,187-197 torch_scatter.scatter_mean ---------------
+ * plane[cell, :] = sum of the segment's rows (/ count when mean != 0); empty cell -> 0.        */
+int t2h_seg_reduce_fwd(const float* rows, const int32_t* perm, const int32_t* cell_start,
+                       int64_t n_seg, int shift, int C, int morton, int reso, int mean,
+                       float* plane, t2h_stream_t stream);
+/* rows[row, :] = plane[cell(row), :] (/ count when mean != 0): backward of the mean, and the
+ * gather-back of pool_local when scatter_type == 'mean'                                        */
+int t2h_seg_broadcast(const float* plane, const int32_t* perm, const int32_t* cell_start,
+                      int64_t n_seg, int shift, int C, int morton, int reso, int mean,
+                      float* rows, t2h_stream_t stream);
+
+/* ---- a4: alto.py:90-95,199-205 F.grid_sample(bilinear, border, align_corners=True) -----------
+ * out_rows[row, :] = 4-tap bilinear sample of plane[b] at (x, y) = xyz_sorted[i, 0:2]          */
+int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, const float* xyz_sorted,
+                            int64_t point_stride, const int32_t* perm, int64_t n_points,
+                            int64_t n_per_batch, float* out_rows, t2h_stream_t stream);
+/* grad_plane (B, r, r, C): atomic-free gather over the 3x3 neighbour cells of every plane cell */
+int t2h_bilinear_sample_bwd(const float* grad_rows, int reso, int C, const float* xyz_sorted,
+                            int64_t point_stride, const int32_t* perm, const int32_t* cell_start,
+                            int64_t n_seg, int shift, int morton, float* grad_plane,
+                            t2h_stream_t stream);
+
+/* ---- a5: pixel.py:105-111 F.interpolate(bilinear, align_corners=True) ----------------------- */
+int t2h_upsample_bilinear_fwd(const float* in, int B, int h, int w, int C, int out_h, int out_w,
+                              float* out, t2h_stream_t stream);
+int t2h_upsample_bilinear_bwd(const float* grad_out, int B, int h, int w, int C, int out_h,
+                              int out_w, float* grad_in, t2h_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2H_H_ */

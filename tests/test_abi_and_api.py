@@ -1,0 +1,126 @@
+"""CPU-side checks: the C-ABI library exports what include/t2h.h declares, the Python mirror keeps
+the reference's API surface / state_dict layout, and the product path refuses to run without CUDA."""
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import tomosar2height_b200 as t2h
+from tomosar2height_b200 import _lib
+from cases import CASES, make_cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build_library()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    header = open(os.path.join(ROOT, "include", "t2h.h")).read()
+    declared = set(re.findall(r"\b(t2h_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.t2h_abi_version() == 1
+    assert lib.t2h_status_string(0) == b"ok"
+    assert lib.t2h_status_string(2) == b"unsupported shape"
+    assert lib.t2h_sort_workspace_bytes(1 << 20) > (1 << 22)
+
+
+def test_header_cites_reference():
+    header = open(os.path.join(ROOT, "include", "t2h.h")).read()
+    for cite in ("utils/coordinate.py:12-28", "pointnet.py:92-99", "alto.py:90-95", "pixel.py:105-111"):
+        assert cite in header
+
+
+def test_argument_validation_without_gpu(lib):
+    # invalid arguments are rejected before any launch, so this is safe on a CPU box
+    assert lib.t2h_cell_index(None, 10, 2, 256, None, None) == 1
+    assert lib.t2h_seg_reduce_fwd(None, None, None, 8, 0, 32, 0, 4, 1, None, None) == 1
+    assert lib.t2h_xy_keys(None, 0, 3, 1, 100, 1, None, None) == 1
+
+
+@pytest.mark.parametrize("name", list(CASES) + ["berlin_full", "berlin_image_full", "munich_full", "munich_image_full"])
+def test_state_dict_matches_reference(golden_dir, name):
+    with open(os.path.join(golden_dir, f"state_dict_{name}.json")) as fh:
+        ref = {k: tuple(v) for k, v in json.load(fh).items()}
+    if name in CASES:
+        cfg = make_cfg(**CASES[name]["cfg"])
+    else:
+        cfg = (t2h.berlin_config if name.startswith("berlin") else t2h.munich_config)(use_image="image" in name)
+    model = t2h.TomoSAR2Height(cfg)
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == ref
+    assert list(got) == list(ref) or sorted(got) == sorted(ref)
+
+
+def test_registries_and_errors():
+    assert set(t2h.encoder_dict) == {"pointnet_local_pool", "pointnet_plus_plus", "hourglass", "unet"}
+    assert set(t2h.decoder_dict) == {"pixel"}
+    from tomosar2height_b200.encoder.pointnet import LocalPoolPointnet
+    from tomosar2height_b200.decoder.pixel import PixelwiseDecoder
+    from tomosar2height_b200.encoder.alto import UNet as Alto
+    with pytest.raises(ValueError):
+        LocalPoolPointnet(unet_type="nope", unet_kwargs={})
+    with pytest.raises(ValueError):
+        LocalPoolPointnet(scatter_type="nope", unet_kwargs={"depth": 2, "start_filts": 8}, feature_dim=8, hidden_dim=8)
+    with pytest.raises(ValueError):
+        PixelwiseDecoder(mode="nope")
+    with pytest.raises(ValueError):
+        Alto(8, in_channels=8, depth=2, start_filts=8, up_mode="nope")
+    with pytest.raises(ValueError):
+        Alto(8, in_channels=8, depth=2, start_filts=8, up_mode="upsample", merge_mode="add")
+    with pytest.raises(NotImplementedError):
+        t2h.encoder_dict["hourglass"]()
+    blk = t2h.ResnetBlockFC(64, 32)
+    assert blk.shortcut is not None and blk.shortcut.bias is None and t2h.ResnetBlockFC(32).shortcut is None
+    assert float(blk.fc_1.weight.abs().max()) == 0.0
+
+
+def test_init_rule_matches_reference():
+    torch.manual_seed(0)
+    model = t2h.TomoSAR2Height(make_cfg(**CASES["berlin_small"]["cfg"]))
+    for m in model.modules():
+        if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)) and m.bias is not None:
+            assert float(m.bias.abs().max()) == 0.0
+    # z_scale, threshold
+    assert abs(model.z_scale - 190.2) < 1e-9 and model.threshold == 0.5
+
+
+def test_no_cpu_fallback():
+    model = t2h.TomoSAR2Height(make_cfg(**CASES["berlin_small"]["cfg"]))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(input_cloud=torch.rand(1, 100, 3))
+    from tomosar2height_b200.utils import coordinate2index
+    with pytest.raises(RuntimeError, match="CUDA"):
+        coordinate2index(torch.rand(1, 10, 2), 4)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tomosar2height_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_install_as_reference_alias():
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == "tomosar2height" or k.startswith("tomosar2height.")}
+    try:
+        t2h.install_as_reference()
+        from tomosar2height import TomoSAR2Height
+        from tomosar2height.encoder import encoder_dict  # noqa: F401
+        assert TomoSAR2Height is t2h.TomoSAR2Height
+    finally:
+        for k in [k for k in sys.modules if k == "tomosar2height" or k.startswith("tomosar2height.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -1,0 +1,147 @@
+"""Whole-path GPU parity: TomoSAR2Height forward + backward on the B200 path vs
+(a) fixtures produced by the real reference (tests/golden/*.npz) and (b) the CPU oracle in fp64."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from cases import CASES, make_cfg, grad_probe_positions, synthetic_cloud, synthetic_targets
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def strict_fp32():
+    """Parity is defined against the CPU fp32 reference: keep the retained cuDNN convs out of TF32."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _build(name):
+    import tomosar2height_b200 as t2h
+    spec = CASES[name]
+    cfg = make_cfg(**spec["cfg"])
+    shapes = oracle.reference_param_shapes(cfg)
+    params = oracle.synth_state_dict(shapes, seed=spec["seed"])
+    model = t2h.TomoSAR2Height(cfg)
+    model.load_state_dict(params)
+    return cfg, params, model.cuda()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_model_matches_reference_fixture(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg, params, model = _build(name)
+    cloud = torch.from_numpy(g["cloud"]).cuda()
+    image = torch.from_numpy(g["image"]).cuda() if "image" in g.files else None
+    dsm = torch.from_numpy(g["dsm"]).cuda()
+    pa, pb = model(input_cloud=cloud, input_image=image)
+    assert pa.shape == g["pa_f32"].shape
+    scale = np.abs(g["pa_f32"]).max()
+    err = np.abs(pa.detach().cpu().numpy() - g["pa_f32"]).max()
+    assert err <= REL * scale, f"heights: {err:.3e} vs {scale:.3e}"
+    if pb is not None:
+        errb = np.abs(pb.detach().cpu().numpy() - g["pb_f32"]).max()
+        assert errb <= REL * np.abs(g["pb_f32"]).max()
+    # trainer.py:63-69
+    loss = torch.nn.functional.l1_loss(pa.squeeze(), dsm.squeeze())
+    if cfg.use_footprint:
+        loss = loss + 10.0 * torch.nn.functional.binary_cross_entropy_with_logits(
+            pb.squeeze(), (dsm.squeeze() > 0.0001).float())
+    assert abs(loss.item() - float(g["loss_f32"])) <= REL * abs(float(g["loss_f32"]))
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k, pname in enumerate(str(n) for n in g["param_names"]):
+        ref_norm = float(g["grad_norm_f32"][k])
+        grad = named[pname].grad
+        if ref_norm < 0:
+            assert grad is None or float(grad.abs().max()) == 0.0, pname
+            continue
+        flat = grad.double().flatten().cpu()
+        assert abs(flat.norm().item() - ref_norm) <= 5 * REL * max(ref_norm, 1e-6), (pname, flat.norm().item(), ref_norm)
+        pos = grad_probe_positions(flat.numel())
+        got = np.asarray([flat[i].item() for i in pos])
+        ref = g["grad_probe_f32"][k][: len(pos)]
+        tol = 5 * REL * max(float(flat.abs().max()), 1e-12)
+        assert np.abs(got - ref).max() <= tol, (pname, got, ref)
+
+
+@pytest.mark.parametrize("name", ["berlin_small", "munich_small"])
+def test_model_matches_fp64_oracle(name):
+    """Error of the fp32 B200 path measured against an fp64 evaluation of the same network."""
+    cfg, params, model = _build(name)
+    spec = CASES[name]
+    B, N = spec["B"], 2 * spec["N"]
+    size = cfg.model.decoder_pixel_kwargs.output_size
+    cloud = synthetic_cloud(B, N, seed=spec["seed"] + 50)
+    dsm, image = synthetic_targets(B, size, spec["seed"] + 50, with_image=cfg.use_image)
+    P64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    pa64, pb64 = oracle.oracle_forward(P64, cfg, cloud.double(), None if image is None else image.double(), aten=False)
+    oracle.oracle_loss(pa64, pb64, dsm, cfg.use_footprint).backward()
+    pa, pb = model(input_cloud=cloud.cuda(), input_image=None if image is None else image.cuda())
+    loss = torch.nn.functional.l1_loss(pa.squeeze(), dsm.cuda().squeeze())
+    if cfg.use_footprint:
+        loss = loss + 10.0 * torch.nn.functional.binary_cross_entropy_with_logits(
+            pb.squeeze(), (dsm.cuda().squeeze() > 0.0001).float())
+    loss.backward()
+    scale = pa64.abs().max().item()
+    assert (pa.detach().cpu().double() - pa64.detach()).abs().max().item() <= REL * scale
+    worst = 0.0
+    for pname, p in model.named_parameters():
+        g64 = P64[pname].grad
+        if g64 is None or p.grad is None:
+            continue
+        denom = max(g64.abs().max().item(), 1e-12)
+        worst = max(worst, (p.grad.cpu().double() - g64).abs().max().item() / denom)
+    assert worst <= 10 * REL, f"worst relative gradient error {worst:.3e}"
+
+
+def test_alto_unet_accepts_reference_arguments():
+    """UNet.forward(p, x, c) with the reference's tensor arguments (alto.py:368) == topology path."""
+    cfg, params, model = _build("berlin_small")
+    enc = model.point_encoder
+    cloud = synthetic_cloud(1, 2000, seed=4).cuda()
+    from tomosar2height_b200.topology import Topology
+    import tomosar2height_b200.functional as T
+    R, C = enc.reso_plane, enc.c_dim
+    g = torch.Generator().manual_seed(0)
+    c = torch.randn(1, 2000, C, generator=g).cuda()
+    topo = Topology(cloud, R)
+    plane = T.plane_to_nchw(T.seg_mean(topo.sort_rows(c.view(-1, C)), topo.level(R)), 1, R)
+    with torch.no_grad():
+        a = enc.unet(cloud, {'xy': plane}, c)
+        b = enc.unet(topo, {'xy': plane}, topo.sort_rows(c.view(-1, C)))
+    assert torch.equal(a, b)
+    # pool_local / generate_plane_features with reference-style arguments
+    from tomosar2height_b200.utils import coordinate2index
+    idx = coordinate2index(cloud[..., :2].contiguous(), R)
+    net = torch.randn(1, 2000, 32, generator=g).cuda()
+    pooled = enc.pool_local(idx, net)
+    cells, _ = oracle.segment_max(net.cpu().permute(0, 2, 1), idx.cpu(), R * R)
+    want = cells.gather(2, idx.cpu().expand(-1, 32, -1)).permute(0, 2, 1)
+    assert torch.equal(pooled.cpu(), want)
+    fea = enc.generate_plane_features({'xy': idx}, c, 'xy')
+    want = oracle.segment_mean(c.cpu().permute(0, 2, 1), idx.cpu(), R * R).reshape(1, C, R, R)
+    assert (fea.cpu() - want).abs().max() <= 1e-5 * want.abs().max()
+    with pytest.raises(NotImplementedError):
+        enc.generate_plane_features({}, c, 'xz')
+
+
+def test_ragged_like_batches_are_independent():
+    """Tiles of one batch do not influence each other (tile-sharded data parallelism relies on it)."""
+    cfg, params, model = _build("berlin_small")
+    a = synthetic_cloud(1, 1500, seed=1).cuda()
+    b = synthetic_cloud(1, 1500, seed=2).cuda()
+    with torch.no_grad():
+        both, _ = model(input_cloud=torch.cat([a, b], 0))
+        ya, _ = model(input_cloud=a)
+        yb, _ = model(input_cloud=b)
+    assert (both[0] - ya[0]).abs().max() <= 1e-5 * ya.abs().max()
+    assert (both[1] - yb[0]).abs().max() <= 1e-5 * yb.abs().max()

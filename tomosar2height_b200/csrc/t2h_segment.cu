@@ -1,0 +1,315 @@
+// Deterministic segmented reductions over cell-sorted points (S1 / S2 of SURVEY §2.2).
+//
+// Replace torch_scatter.scatter_max + gather (pointnet.py:92-99) and torch_scatter.scatter_mean
+// (pointnet.py:101-111, alto.py:76-88, alto.py:187-197) and their autograd backwards.
+// One warp owns one cell (segment); a row of C floats is spread over LPR lanes as float4s, so a
+// warp consumes RPI = 32/LPR rows per iteration with fully coalesced 16-byte accesses.  No
+// atomics: the order of every floating-point sum is fixed by the (stable) sort.
+#include "t2h_common.cuh"
+
+namespace t2h {
+
+constexpr int kSegWarps = 8;  // warps (= segments) per CTA
+
+struct SegGeom {
+  const int32_t* perm;        // sorted position -> row (nullptr: identity)
+  const int32_t* cell_start;  // finest-level table
+  int64_t n_seg;
+  int shift;   // 2k for level r = R >> k
+  int morton;
+  int reso;    // resolution r of THIS level
+};
+
+// plane row (row-major (b, y, x)) of segment `seg` (key order of this level)
+__device__ __forceinline__ int64_t plane_row(const SegGeom& g, int64_t seg) {
+  if (!g.morton) return seg;
+  const int64_t cells = (int64_t)g.reso * g.reso;
+  int64_t b = seg / cells;
+  int ix, iy;
+  cell_decode((uint32_t)(seg - b * cells), g.reso, 1, ix, iy);
+  return b * cells + (int64_t)iy * g.reso + ix;
+}
+
+template <class RS>
+__global__ void __launch_bounds__(kSegWarps * kWarp)
+seg_max_fwd_kernel(const float* __restrict__ rows, SegGeom g, float* __restrict__ pooled,
+                   float* __restrict__ plane, int32_t* __restrict__ arg) {
+  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
+  if (seg >= g.n_seg) return;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int beg = g.cell_start[seg << g.shift], end = g.cell_start[(seg + 1) << g.shift];
+
+  float best[CH][4];
+  int bpos[CH][4];
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { best[c][k] = -FLT_MAX; bpos[c][k] = INT32_MAX; }
+
+  for (int i = beg + sub; i < end; i += RPI) {
+    const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+    const float* src = rows + row * C + l * 4;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 v = ld4(src + c * LPR * 4);
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (e[k] > best[c][k]) { best[c][k] = e[k]; bpos[c][k] = i; }  // strict >: first row wins ties
+    }
+  }
+  // merge the RPI sub-rows: larger value wins, equal values -> smaller sorted position
+#pragma unroll
+  for (int off = LPR; off < kWarp; off <<= 1) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float ov = __shfl_xor_sync(0xffffffffu, best[c][k], off);
+        int op = __shfl_xor_sync(0xffffffffu, bpos[c][k], off);
+        if (ov > best[c][k] || (ov == best[c][k] && op < bpos[c][k])) { best[c][k] = ov; bpos[c][k] = op; }
+      }
+  }
+  const bool empty = beg >= end;
+  const int64_t prow = plane_row(g, seg);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    float4 v;
+    int4 a;
+    int* ap = &a.x;
+    float* vp = &v.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool none = empty || bpos[c][k] == INT32_MAX;
+      vp[k] = none ? 0.0f : best[c][k];
+      ap[k] = none ? -1 : (g.perm ? g.perm[bpos[c][k]] : bpos[c][k]);
+      best[c][k] = vp[k];
+    }
+    if (sub == 0) {
+      const int64_t o = prow * C + (c * LPR + l) * 4;
+      if (plane) st4(plane + o, v);
+      *reinterpret_cast<int4*>(arg + o) = a;
+    }
+  }
+  if (pooled) {
+    for (int i = beg + sub; i < end; i += RPI) {
+      const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+      float* dst = pooled + row * C + l * 4;
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        st4(dst + c * LPR * 4, make_float4(best[c][0], best[c][1], best[c][2], best[c][3]));
+    }
+  }
+}
+
+template <class RS>
+__global__ void __launch_bounds__(kSegWarps * kWarp)
+seg_max_bwd_kernel(const float* __restrict__ grad_pooled, const float* __restrict__ grad_plane, SegGeom g,
+                   const int32_t* __restrict__ arg, float* __restrict__ grad_rows) {
+  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
+  if (seg >= g.n_seg) return;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int beg = g.cell_start[seg << g.shift], end = g.cell_start[(seg + 1) << g.shift];
+  if (beg >= end) return;
+  const int64_t prow = plane_row(g, seg);
+
+  float4 acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (grad_pooled) {
+    for (int i = beg + sub; i < end; i += RPI) {
+      const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+      const float* src = grad_pooled + row * C + l * 4;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float4 v = ld4(src + c * LPR * 4);
+        acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+      }
+    }
+#pragma unroll
+    for (int off = LPR; off < kWarp; off <<= 1)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float4 o = shfl_xor4(acc[c], off);
+        acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
+      }
+  }
+  int4 a[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int64_t o = prow * C + (c * LPR + l) * 4;
+    a[c] = *reinterpret_cast<const int4*>(arg + o);
+    if (grad_plane) {
+      float4 v = ld4(grad_plane + o);
+      acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+    }
+  }
+  for (int i = beg + sub; i < end; i += RPI) {
+    const int row32 = g.perm ? g.perm[i] : i;
+    float* dst = grad_rows + (int64_t)row32 * C + l * 4;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 v;
+      v.x = a[c].x == row32 ? acc[c].x : 0.f;
+      v.y = a[c].y == row32 ? acc[c].y : 0.f;
+      v.z = a[c].z == row32 ? acc[c].z : 0.f;
+      v.w = a[c].w == row32 ? acc[c].w : 0.f;
+      st4(dst + c * LPR * 4, v);
+    }
+  }
+}
+
+template <class RS>
+__global__ void __launch_bounds__(kSegWarps * kWarp)
+seg_reduce_fwd_kernel(const float* __restrict__ rows, SegGeom g, int mean, float* __restrict__ plane) {
+  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
+  if (seg >= g.n_seg) return;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int beg = g.cell_start[seg << g.shift], end = g.cell_start[(seg + 1) << g.shift];
+
+  float4 acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int i = beg + sub;
+  // two rows in flight per lane
+  for (; i + RPI < end; i += 2 * RPI) {
+    const int64_t r0 = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+    const int64_t r1 = g.perm ? (int64_t)g.perm[i + RPI] : (int64_t)(i + RPI);
+    float4 v0[CH], v1[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      v0[c] = ld4(rows + r0 * C + (c * LPR + l) * 4);
+      v1[c] = ld4(rows + r1 * C + (c * LPR + l) * 4);
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      acc[c].x += v0[c].x; acc[c].y += v0[c].y; acc[c].z += v0[c].z; acc[c].w += v0[c].w;
+      acc[c].x += v1[c].x; acc[c].y += v1[c].y; acc[c].z += v1[c].z; acc[c].w += v1[c].w;
+    }
+  }
+  for (; i < end; i += RPI) {
+    const int64_t r0 = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 v = ld4(rows + r0 * C + (c * LPR + l) * 4);
+      acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+    }
+  }
+#pragma unroll
+  for (int off = LPR; off < kWarp; off <<= 1)
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 o = shfl_xor4(acc[c], off);
+      acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
+    }
+  if (sub == 0) {
+    const float cnt = (float)max(end - beg, 1);
+    const int64_t prow = plane_row(g, seg);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 v = acc[c];
+      if (mean) { v.x = __fdiv_rn(v.x, cnt); v.y = __fdiv_rn(v.y, cnt); v.z = __fdiv_rn(v.z, cnt); v.w = __fdiv_rn(v.w, cnt); }
+      st4(plane + prow * C + (c * LPR + l) * 4, v);
+    }
+  }
+}
+
+template <class RS>
+__global__ void __launch_bounds__(kSegWarps * kWarp)
+seg_broadcast_kernel(const float* __restrict__ plane, SegGeom g, int mean, float* __restrict__ rows) {
+  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
+  if (seg >= g.n_seg) return;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int beg = g.cell_start[seg << g.shift], end = g.cell_start[(seg + 1) << g.shift];
+  if (beg >= end) return;
+  const float cnt = (float)(end - beg);
+  const int64_t prow = plane_row(g, seg);
+  float4 v[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    v[c] = ld4(plane + prow * C + (c * LPR + l) * 4);
+    if (mean) { v[c].x = __fdiv_rn(v[c].x, cnt); v[c].y = __fdiv_rn(v[c].y, cnt); v[c].z = __fdiv_rn(v[c].z, cnt); v[c].w = __fdiv_rn(v[c].w, cnt); }
+  }
+  for (int i = beg + sub; i < end; i += RPI) {
+    const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) st4(rows + row * C + (c * LPR + l) * 4, v[c]);
+  }
+}
+
+static int check_geom(const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso) {
+  if (!cell_start || n_seg < 0 || shift < 0 || shift > 30 || (shift & 1) || C <= 0 || reso <= 0) return T2H_ERR_INVALID_ARGUMENT;
+  if (shift && !morton) return T2H_ERR_INVALID_ARGUMENT;  // only Morton keys nest across levels
+  if (morton && ((reso & (reso - 1)) || n_seg % ((int64_t)reso * reso))) return T2H_ERR_INVALID_ARGUMENT;
+  return T2H_OK;
+}
+
+static inline unsigned seg_blocks(int64_t n_seg) { return (unsigned)((n_seg + kSegWarps - 1) / kSegWarps); }
+
+}  // namespace t2h
+
+using namespace t2h;
+
+extern "C" int t2h_seg_max_fwd(const float* rows, const int32_t* perm, const int32_t* cell_start, int64_t n_seg,
+                               int shift, int C, int morton, int reso, float* pooled, float* plane, int32_t* arg,
+                               t2h_stream_t stream) {
+  int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
+  if (st) return st;
+  if (!rows || !arg) return T2H_ERR_INVALID_ARGUMENT;
+  if (n_seg == 0) return T2H_OK;
+  SegGeom g{perm, cell_start, n_seg, shift, morton, reso};
+  T2H_DISPATCH_ROWSHAPE(C, seg_max_fwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
+                               rows, g, pooled, plane, arg));
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane, const int32_t* perm,
+                               const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                               const int32_t* arg, float* grad_rows, t2h_stream_t stream) {
+  int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
+  if (st) return st;
+  if (!arg || !grad_rows || (!grad_pooled && !grad_plane)) return T2H_ERR_INVALID_ARGUMENT;
+  if (n_seg == 0) return T2H_OK;
+  SegGeom g{perm, cell_start, n_seg, shift, morton, reso};
+  T2H_DISPATCH_ROWSHAPE(C, seg_max_bwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
+                               grad_pooled, grad_plane, g, arg, grad_rows));
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" int t2h_seg_reduce_fwd(const float* rows, const int32_t* perm, const int32_t* cell_start, int64_t n_seg,
+                                  int shift, int C, int morton, int reso, int mean, float* plane,
+                                  t2h_stream_t stream) {
+  int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
+  if (st) return st;
+  if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
+  if (n_seg == 0) return T2H_OK;
+  SegGeom g{perm, cell_start, n_seg, shift, morton, reso};
+  T2H_DISPATCH_ROWSHAPE(C, seg_reduce_fwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
+                               rows, g, mean, plane));
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" int t2h_seg_broadcast(const float* plane, const int32_t* perm, const int32_t* cell_start, int64_t n_seg,
+                                 int shift, int C, int morton, int reso, int mean, float* rows,
+                                 t2h_stream_t stream) {
+  int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
+  if (st) return st;
+  if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
+  if (n_seg == 0) return T2H_OK;
+  SegGeom g{perm, cell_start, n_seg, shift, morton, reso};
+  T2H_DISPATCH_ROWSHAPE(C, seg_broadcast_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
+                               plane, g, mean, rows));
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}

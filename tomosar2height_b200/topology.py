@@ -1,0 +1,160 @@
+"""Point -> cell topology: one stable sort of the tile batch serves every plane level.
+
+Replaces the per-call ``coordinate2index`` + atomic scatter of the reference
+(pointnet.py:69-70, alto.py:79-80,189-190).  See include/t2h.h for the key layout.
+"""
+import torch
+
+from . import _lib
+
+
+def _is_pow2(v: int) -> bool:
+    return v > 0 and (v & (v - 1)) == 0
+
+
+class CellLevel:
+    """What the segment / sampling kernels need for one plane resolution ``reso``.
+
+    ``perm`` is None when per-point rows are stored in sorted order (the fused model path),
+    otherwise it maps sorted position -> row.
+    """
+
+    __slots__ = ("topo", "reso", "shift", "morton", "perm", "cell_start", "xyz_sorted", "B", "N", "n_seg")
+
+    def __init__(self, topo, reso, shift, perm):
+        self.topo = topo
+        self.reso = reso
+        self.shift = shift
+        self.morton = int(topo.morton)
+        self.perm = perm
+        self.cell_start = topo.cell_start
+        self.xyz_sorted = topo.xyz_sorted
+        self.B, self.N = topo.B, topo.N
+        self.n_seg = topo.B * reso * reso
+
+    @property
+    def n_rows(self):
+        return self.B * self.N
+
+
+class Topology:
+    """Sort the points of a (B, N, 3) tile batch by (tile, cell) once.
+
+    Attributes
+      xyz_sorted  (B*N, 3) fp32 : coordinates in sorted order
+      perm        (B*N,) int32  : sorted position -> flat input index  (b*N + n)
+      cell_start  (B*R*R + 1,) int32
+      morton      bool          : Morton keys (power-of-two R) -> coarser levels share the sort
+    """
+
+    def __init__(self, xyz: torch.Tensor, reso: int):
+        _lib.require_cuda_f32(xyz, "Topology(xyz)")
+        if xyz.dim() != 3 or xyz.shape[2] < 2:
+            raise RuntimeError(f"Topology: expected (B, N, >=2) points, got {tuple(xyz.shape)}")
+        xyz = xyz.contiguous()
+        self.B, self.N, self.D = xyz.shape
+        self.reso = int(reso)
+        self.morton = _is_pow2(self.reso)
+        n = self.B * self.N
+        n_keys = self.B * self.reso * self.reso
+        dev = xyz.device
+        keys = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.call("t2h_xy_keys", _lib.ptr(xyz), n, self.D, self.N, self.reso, int(self.morton), _lib.ptr(keys))
+        self.keys_sorted, self.perm, self.cell_start = sort_keys(keys, n_keys)
+        self.xyz_sorted = torch.empty(n, self.D, dtype=torch.float32, device=dev)
+        _lib.call("t2h_gather_rows", _lib.ptr(xyz.view(n, self.D)), _lib.ptr(self.perm), n, self.D,
+                  _lib.ptr(self.xyz_sorted))
+        self._sub = {}
+
+    # -- levels ------------------------------------------------------------------------------
+    def _shift_for(self, reso: int):
+        if reso == self.reso:
+            return 0
+        if self.morton and _is_pow2(reso) and reso < self.reso:
+            k = (self.reso // reso).bit_length() - 1
+            return 2 * k
+        return None
+
+    def level(self, reso: int, rows_sorted: bool = True) -> CellLevel:
+        """Level descriptor for plane resolution ``reso``.
+
+        rows_sorted=True : per-point rows live in THIS topology's sorted order.
+        rows_sorted=False: rows live in the original input order.
+        A resolution that does not nest in the Morton keys (non power-of-two planes) gets its own
+        sort of the already-sorted coordinates, cached per resolution.
+        """
+        shift = self._shift_for(reso)
+        if shift is not None:
+            return CellLevel(self, reso, shift, None if rows_sorted else self.perm)
+        key = (reso, rows_sorted)
+        if key not in self._sub:
+            if rows_sorted:
+                sub = Topology(self.xyz_sorted.view(self.B, self.N, self.D), reso)
+            else:
+                raise RuntimeError("Topology.level: incompatible resolution for original-order rows; "
+                                   "build a Topology at that resolution instead")
+            self._sub[key] = sub
+        sub = self._sub[key]
+        return CellLevel(sub, reso, 0, sub.perm)
+
+    def sort_rows(self, rows: torch.Tensor) -> torch.Tensor:
+        """(B*N, C) rows in input order -> sorted order."""
+        return gather_rows(rows, self.perm)
+
+    def unsort_rows(self, rows: torch.Tensor) -> torch.Tensor:
+        return scatter_rows(rows, self.perm)
+
+
+def sort_keys(keys: torch.Tensor, n_keys: int):
+    """Stable sort of int32 keys -> (keys_sorted, perm, cell_start[n_keys + 1])."""
+    n = keys.numel()
+    dev = keys.device
+    lib = _lib.load()
+    ws_bytes = int(lib.t2h_sort_workspace_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    keys_sorted = torch.empty_like(keys)
+    perm = torch.empty_like(keys)
+    cell_start = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+    _lib.call("t2h_sort_by_cell", _lib.ptr(keys), n, n_keys, _lib.ptr(ws), ws_bytes, _lib.ptr(keys_sorted),
+              _lib.ptr(perm), _lib.ptr(cell_start))
+    return keys_sorted, perm, cell_start
+
+
+def gather_rows(rows: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    _lib.require_cuda_f32(rows, "gather_rows")
+    rows = rows.contiguous()
+    out = torch.empty_like(rows)
+    _lib.call("t2h_gather_rows", _lib.ptr(rows), _lib.ptr(perm), rows.shape[0], rows.shape[1], _lib.ptr(out))
+    return out
+
+
+def scatter_rows(rows: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    _lib.require_cuda_f32(rows, "scatter_rows")
+    rows = rows.contiguous()
+    out = torch.empty_like(rows)
+    _lib.call("t2h_scatter_rows", _lib.ptr(rows), _lib.ptr(perm), rows.shape[0], rows.shape[1], _lib.ptr(out))
+    return out
+
+
+class IndexLevel:
+    """Level descriptor for an arbitrary (B, 1, N) int64 index (torch_scatter-style API)."""
+
+    __slots__ = ("reso", "shift", "morton", "perm", "cell_start", "xyz_sorted", "B", "N", "n_seg", "dim_size")
+
+    def __init__(self, index: torch.Tensor, dim_size: int, check: bool = True):
+        if not index.is_cuda or index.dtype != torch.int64:
+            raise RuntimeError("IndexLevel: expected a CUDA int64 index")
+        B = index.shape[0]
+        N = index.shape[-1]
+        index = index.reshape(B, N).contiguous()
+        n = B * N
+        keys = torch.empty(n, dtype=torch.int32, device=index.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=index.device)
+        _lib.call("t2h_index_keys", _lib.ptr(index), n, N, dim_size, _lib.ptr(keys), _lib.ptr(flag))
+        if check and int(flag.item()) != 0:
+            raise IndexError(f"scatter index out of range [0, {dim_size})")
+        _, self.perm, self.cell_start = sort_keys(keys, B * dim_size)
+        self.reso, self.shift, self.morton = 1, 0, 0
+        self.xyz_sorted = None
+        self.B, self.N, self.dim_size = B, N, dim_size
+        self.n_seg = B * dim_size
