@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd training-step throughput of the TomoSAR2Height hot path on B200.
+
+Workload (BASELINE.json configs[1]): point-cloud-only training step, batch of 32 synthetic
+Berlin-shaped tiles (N = 262 144 points each, R = 256, ALTO depth 5, conv decoder, 512^2 nDSM),
+fp32, forward + L1 loss + backward over the batch in micro-batches, one AdamW step.
+One process per GPU; N > 1 = weak scaling (every rank trains on its own 32 tiles) with ONE flat
+fp32 gradient all-reduce (SUM) per step.
+
+Prints ONE JSON line (see the driver contract): value = points/s with inputs resident in HBM,
+e2e = the same step through the public API from pinned host buffers (H2D inside the timed region,
+loss read back), roofline = the dominant hand-written kernel against the measured HBM peak,
+cpu_baseline = the CPU oracle (reference restatement) on this box's host cores.
+
+`--impl reference` times the reference's CPU path (the oracle port; the real reference needs
+torch_scatter/open3d/rasterio which are not installable here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+import torch  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tiles", type=int, default=32, help="tiles per step per GPU (batch)")
+    ap.add_argument("--points", type=int, default=262144, help="points per tile")
+    ap.add_argument("--micro-batch", type=int, default=4, help="tiles per forward/backward")
+    ap.add_argument("--conv-tf32", action="store_true", help="let the retained cuDNN convs use TF32 (reference GPU default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-points", type=int, default=262144, help="points of the CPU-baseline tile")
+    return ap.parse_args()
+
+
+def synthetic_batch(tiles, points, seed):
+    from cases import synthetic_cloud, synthetic_targets
+    cloud = synthetic_cloud(tiles, points, seed, clustered=True)
+    dsm, _ = synthetic_targets(tiles, 512, seed)
+    return cloud, dsm
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_step(cfg, params, cloud, dsm):
+    """One tile through the CPU oracle: forward + L1 loss + backward (trainer.py:61-70)."""
+    import oracle
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    t0 = time.perf_counter()
+    pa, pb = oracle.oracle_forward(P, cfg, cloud)
+    loss = oracle.oracle_loss(pa, pb, dsm, False)
+    loss.backward()
+    return time.perf_counter() - t0, float(loss)
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from tomosar2height_b200.config import berlin_config
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = berlin_config()
+    params = oracle.synth_state_dict(oracle.reference_param_shapes(cfg), seed=0)
+    n = args.cpu_points
+    cloud, dsm = synthetic_batch(1, n, seed=0)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(cfg, params, cloud, dsm)
+    times = [cpu_reference_step(cfg, params, cloud, dsm)[0] for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    value = n / t
+    line = {
+        "impl": "reference", "metric": "fwd+bwd points/s", "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ndsm_px_per_s": 512 * 512 / t,
+        "config": {"workload": "cloud-only training step (fwd+L1+bwd), Berlin-shaped tiles, R=256, ALTO depth 5",
+                   "tiles_per_step": 1, "points_per_tile": n},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
+                         "sample": f"1 tile of {n} points per step, fwd+L1+bwd through oracle/ (torch CPU, {cores} threads)"},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import tomosar2height_b200 as t2h
+    from tomosar2height_b200 import _lib
+    from tomosar2height_b200.parallel import FlatGradients
+    from tomosar2height_b200.profiling import KernelTimer
+    import oracle  # parameter recipe + cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = bool(args.conv_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+
+    cfg = t2h.berlin_config()
+    params = oracle.synth_state_dict(oracle.reference_param_shapes(cfg), seed=0)
+    model = t2h.TomoSAR2Height(cfg)
+    model.load_state_dict(params)
+    model = model.to(dev).train()
+    flat = FlatGradients(model)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)  # train.py:97
+
+    T, N, mb = args.tiles, args.points, args.micro_batch
+    cloud_h, dsm_h = synthetic_batch(T, N, seed=100 + rank)
+    cloud_h, dsm_h = cloud_h.pin_memory(), dsm_h.pin_memory()
+    cloud_d, dsm_d = cloud_h.to(dev), dsm_h.to(dev)
+
+    def train_step(cloud, dsm):
+        flat.zero_()
+        total = torch.zeros((), device=dev)
+        for i in range(0, T, mb):
+            pa, _ = model(input_cloud=cloud[i:i + mb])
+            # per-tile mean L1, summed over tiles: the reference accumulates un-normalised tile grads
+            loss = (pa.squeeze(-1) - dsm[i:i + mb]).abs().mean(dim=(1, 2)).sum()
+            loss.backward()
+            total += loss.detach()
+        flat.all_reduce()
+        opt.step()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        train_step(cloud_d, dsm_d)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ---------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    calls0 = _lib.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with KernelTimer(n_rows=mb * N) as kt:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            train_step(cloud_d, dsm_d)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    clock_info = clocks.stop()
+    launches = _lib.launch_count - calls0
+    kernels = kt.summary()
+
+    # ---- timed region 2: end to end from pinned host buffers --------------------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        c = cloud_h.to(dev, non_blocking=True)
+        d = dsm_h.to(dev, non_blocking=True)
+        last = train_step(c, d).item()  # device -> host read of the step's loss
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        hbm_peak, _tf, peak_src = load_peaks()
+        pts = world * T * N * args.steps
+        value = pts / (ms / 1e3)
+        mine = {k: v for k, v in kernels.items() if v["bytes_per_launch"] > 0}
+        top = max(mine, key=lambda k: mine[k]["ms_total"]) if mine else None
+        roofline = None
+        if top:
+            k = mine[top]
+            roofline = {"bound": "hbm", "kernel": top, "achieved": k["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": k["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "launches": k["launches"], "ms_avg": k["ms_avg"], "bytes_per_launch": k["bytes_per_launch"],
+                        "share_of_step": k["ms_total"] / ms}
+        line = {
+            "metric": "fwd+bwd points/s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ndsm_px_per_s": world * T * 512 * 512 * args.steps / (ms / 1e3),
+            "config": {"workload": "cloud-only training step (fwd+L1+bwd+AdamW), Berlin-shaped tiles, R=256, ALTO depth 5, conv decoder",
+                       "tiles_per_step_per_gpu": T, "points_per_tile": N, "micro_batch_tiles": mb, "parallelism": f"dp{world}",
+                       "conv_tf32": bool(args.conv_tf32), "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)"},
+            "e2e": {"value": pts / (ms_e2e / 1e3), "unit": "points/s", "h2d_bytes_per_step": cloud_h.numel() * 4 + dsm_h.numel() * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "loss": last},
+            "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,
+            "kernels": {k: {kk: round(vv, 4) if isinstance(vv, float) else vv for kk, vv in v.items()} for k, v in kernels.items()},
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            n_cpu = args.cpu_points
+            c1, d1 = synthetic_batch(1, n_cpu, seed=0)
+            t_cpu, _ = cpu_reference_step(cfg, params, c1, d1)
+            line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "points/s", "cores": cores, "kind": "port",
+                                    "sample": f"1 tile of {n_cpu} points, fwd+L1+bwd once through oracle/ (torch CPU, {cores} threads), {t_cpu:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

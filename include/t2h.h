@@ -77,10 +77,12 @@ int t2h_scatter_rows(const float* src, const int32_t* perm, int64_t n_rows, int 
  * (= smallest point index, the torch_scatter CPU rule), empty -> 0 / arg -1.
  *   pooled (n_rows, C), nullable: the max broadcast back to every row of the segment
  *   plane  (n_seg, C),  nullable: the per-cell max, rows in row-major (b, y, x) cell order
- *   arg    (n_seg, C)  int32   : winning ROW index (same row order as plane), -1 if empty     */
-int t2h_seg_max_fwd(const float* rows, const int32_t* perm, const int32_t* cell_start,
-                    int64_t n_seg, int shift, int C, int morton, int reso, float* pooled,
-                    float* plane, int32_t* arg, t2h_stream_t stream);
+ *   arg    (n_seg, C)  int32   : winning ROW index (same row order as plane), -1 if empty
+ *   tie_rank, nullable: original point index of every sorted position; needed for the tie rule
+ *     when a segment spans several sort keys (shift > 0), where sorted order != point order       */
+int t2h_seg_max_fwd(const float* rows, const int32_t* perm, const int32_t* tie_rank,
+                    const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton,
+                    int reso, float* pooled, float* plane, int32_t* arg, t2h_stream_t stream);
 /* grad_rows[row, c] = (row == arg[seg, c]) ? sum_{rows of seg} grad_pooled[., c] + grad_plane[seg, c] : 0 */
 int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane, const int32_t* perm,
                     const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton,

@@ -31,7 +31,7 @@ SIGNATURES = {
     "t2h_sort_by_cell": [_p, _i64, _i64, _p, _sz, _p, _p, _p, _p],
     "t2h_gather_rows": [_p, _p, _i64, _i32, _p, _p],
     "t2h_scatter_rows": [_p, _p, _i64, _i32, _p, _p],
-    "t2h_seg_max_fwd": [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p],
+    "t2h_seg_max_fwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p],
     "t2h_seg_max_bwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
     "t2h_seg_reduce_fwd": [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_seg_broadcast": [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],

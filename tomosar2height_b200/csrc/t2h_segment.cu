@@ -13,6 +13,8 @@ constexpr int kSegWarps = 8;  // warps (= segments) per CTA
 
 struct SegGeom {
   const int32_t* perm;        // sorted position -> row (nullptr: identity)
+  const int32_t* tie;         // sorted position -> original point index, for argmax ties when the
+                              // sorted order inside a segment is not the point order (nullptr: it is)
   const int32_t* cell_start;  // finest-level table
   int64_t n_seg;
   int shift;   // 2k for level r = R >> k
@@ -56,8 +58,13 @@ seg_max_fwd_kernel(const float* __restrict__ rows, SegGeom g, float* __restrict_
       float4 v = ld4(src + c * LPR * 4);
       const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (e[k] > best[c][k]) { best[c][k] = e[k]; bpos[c][k] = i; }  // strict >: first row wins ties
+      for (int k = 0; k < 4; ++k) {
+        // strict >: the first row wins ties (rows of one fine cell are in point order); inside a
+        // coarser segment equal values are resolved by the original point index
+        bool take = e[k] > best[c][k];
+        if (g.tie && e[k] == best[c][k] && bpos[c][k] != INT32_MAX) take = g.tie[i] < g.tie[bpos[c][k]];
+        if (take) { best[c][k] = e[k]; bpos[c][k] = i; }
+      }
     }
   }
   // merge the RPI sub-rows: larger value wins, equal values -> smaller sorted position
@@ -69,7 +76,10 @@ seg_max_fwd_kernel(const float* __restrict__ rows, SegGeom g, float* __restrict_
       for (int k = 0; k < 4; ++k) {
         float ov = __shfl_xor_sync(0xffffffffu, best[c][k], off);
         int op = __shfl_xor_sync(0xffffffffu, bpos[c][k], off);
-        if (ov > best[c][k] || (ov == best[c][k] && op < bpos[c][k])) { best[c][k] = ov; bpos[c][k] = op; }
+        bool take = ov > best[c][k];
+        if (ov == best[c][k] && op != INT32_MAX && bpos[c][k] != INT32_MAX)
+          take = g.tie ? (g.tie[op] < g.tie[bpos[c][k]]) : (op < bpos[c][k]);
+        if (take) { best[c][k] = ov; bpos[c][k] = op; }
       }
   }
   const bool empty = beg >= end;
@@ -258,14 +268,14 @@ static inline unsigned seg_blocks(int64_t n_seg) { return (unsigned)((n_seg + kS
 
 using namespace t2h;
 
-extern "C" int t2h_seg_max_fwd(const float* rows, const int32_t* perm, const int32_t* cell_start, int64_t n_seg,
-                               int shift, int C, int morton, int reso, float* pooled, float* plane, int32_t* arg,
-                               t2h_stream_t stream) {
+extern "C" int t2h_seg_max_fwd(const float* rows, const int32_t* perm, const int32_t* tie_rank,
+                               const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                               float* pooled, float* plane, int32_t* arg, t2h_stream_t stream) {
   int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
   if (st) return st;
   if (!rows || !arg) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, cell_start, n_seg, shift, morton, reso};
+  SegGeom g{perm, tie_rank, cell_start, n_seg, shift, morton, reso};
   T2H_DISPATCH_ROWSHAPE(C, seg_max_fwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
                                rows, g, pooled, plane, arg));
   T2H_CHECK_LAUNCH();
@@ -279,7 +289,7 @@ extern "C" int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane
   if (st) return st;
   if (!arg || !grad_rows || (!grad_pooled && !grad_plane)) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, cell_start, n_seg, shift, morton, reso};
+  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso};
   T2H_DISPATCH_ROWSHAPE(C, seg_max_bwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
                                grad_pooled, grad_plane, g, arg, grad_rows));
   T2H_CHECK_LAUNCH();
@@ -293,7 +303,7 @@ extern "C" int t2h_seg_reduce_fwd(const float* rows, const int32_t* perm, const 
   if (st) return st;
   if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, cell_start, n_seg, shift, morton, reso};
+  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso};
   T2H_DISPATCH_ROWSHAPE(C, seg_reduce_fwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
                                rows, g, mean, plane));
   T2H_CHECK_LAUNCH();
@@ -307,7 +317,7 @@ extern "C" int t2h_seg_broadcast(const float* plane, const int32_t* perm, const 
   if (st) return st;
   if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, cell_start, n_seg, shift, morton, reso};
+  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso};
   T2H_DISPATCH_ROWSHAPE(C, seg_broadcast_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
                                plane, g, mean, rows));
   T2H_CHECK_LAUNCH();

@@ -37,7 +37,7 @@ class _SegMaxPool(torch.autograd.Function):
         pooled = torch.empty_like(rows)
         arg = torch.empty(level.n_seg, C, dtype=torch.int32, device=rows.device)
         plane = torch.empty(level.n_seg, C, dtype=torch.float32, device=rows.device) if want_plane else None
-        call("t2h_seg_max_fwd", ptr(rows), *_geom(level), C, level.morton, level.reso, ptr(pooled), ptr(plane), ptr(arg))
+        call("t2h_seg_max_fwd", ptr(rows), ptr(level.perm), ptr(level.tie), *_geom(level)[1:], C, level.morton, level.reso, ptr(pooled), ptr(plane), ptr(arg))
         ctx.level = level
         ctx.save_for_backward(arg)
         ctx.mark_non_differentiable(arg)
@@ -66,7 +66,7 @@ class _SegMaxPlane(torch.autograd.Function):
         C = rows.shape[1]
         arg = torch.empty(level.n_seg, C, dtype=torch.int32, device=rows.device)
         plane = torch.empty(level.n_seg, C, dtype=torch.float32, device=rows.device)
-        call("t2h_seg_max_fwd", ptr(rows), *_geom(level), C, level.morton, level.reso, None, ptr(plane), ptr(arg))
+        call("t2h_seg_max_fwd", ptr(rows), ptr(level.perm), ptr(level.tie), *_geom(level)[1:], C, level.morton, level.reso, None, ptr(plane), ptr(arg))
         ctx.level = level
         ctx.n_rows = rows.shape[0]
         ctx.save_for_backward(arg)

@@ -1,0 +1,45 @@
+"""Tile-sharded data parallelism: one process per GPU, one gradient all-reduce per optimizer step.
+
+Tiles are independent units: inference shards the tile list with no collective;
+training replicates the model, shards the tiles and sums the gradients once per optimizer step
+over a single flat fp32 buffer (SUM, not AVG: the reference accumulates un-normalised tile
+gradients, trainer.py:70-79).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_tiles(n_tiles: int, rank: int, world: int):
+    """Contiguous block partition of the tile list (spatially adjacent tiles stay on one GPU)."""
+    base, rem = divmod(n_tiles, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+class FlatGradients:
+    """Re-homes every parameter's ``.grad`` into one contiguous buffer so that the whole model is
+    reduced by ONE collective (NCCL picks NVLS / NVSwitch on a B200 box)."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        offset = 0
+        for p in self.params:
+            n = p.numel()
+            # as_strided keeps the parameter's own (e.g. channels_last) strides
+            p.grad = self.flat[offset:offset + n].as_strided(p.shape, p.stride())
+            offset += n
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce(self, async_op=False):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        return None
+
+    @property
+    def nbytes(self):
+        return self.flat.numel() * self.flat.element_size()

@@ -1,0 +1,112 @@
+"""Per-kernel device timing and algorithmic-traffic accounting for the C-ABI calls.
+
+``KernelTimer`` brackets every ``_lib.call`` with CUDA events on the launching stream while it is
+active and accumulates, per entry point, the launch count, the device time and the ALGORITHMIC
+bytes of SURVEY.md §8(d) (fp32 features, int32 indices):
+
+  S1 fwd  seg_max_fwd      read 4NC + 4N            write 4NC (+ 4MC plane) + 4MC (arg)
+  S1 bwd  seg_max_bwd      read 4NC + 4MC           write 4NC
+  S2 fwd  seg_reduce_fwd   read 4NC + 4N            write 4MC
+  S2 bwd  seg_broadcast    read 4MC + 4N            write 4NC
+  G1 fwd  bilinear_sample_fwd  read 4MC + 8N        write 4NC
+  G2 bwd  bilinear_sample_bwd  read 4NC + 8N        write 4MC
+  G3      upsample fwd/bwd     read 4*B*C*h*w       write 4*B*C*H*W   (and the reverse)
+
+N = points, M = B*r*r plane cells, C = channels.  (4N is the per-point share of the cell table /
+permutation; arg is int32 here, not the reference's int64.)
+"""
+import torch
+
+from . import _lib
+
+
+def _bytes(name, a):
+    """algorithmic bytes of one call from its positional ctypes arguments (see include/t2h.h)."""
+    if name == "t2h_seg_max_fwd":
+        n_seg, C = a[4], a[6]
+        rows = _bytes.n_rows
+        return 4 * rows * C + 4 * rows + (4 * rows * C if a[9] else 0) + (4 * n_seg * C if a[10] else 0) + 4 * n_seg * C
+    if name == "t2h_seg_max_bwd":
+        n_seg, C = a[4], a[6]
+        rows = _bytes.n_rows
+        return 4 * rows * C + 4 * n_seg * C + 4 * rows * C
+    if name in ("t2h_seg_reduce_fwd", "t2h_seg_broadcast"):
+        n_seg, C = a[3], a[5]
+        rows = _bytes.n_rows
+        return 4 * rows * C + 4 * rows + 4 * n_seg * C
+    if name == "t2h_bilinear_sample_fwd":
+        reso, C, n, n_per = a[1], a[2], a[6], a[7]
+        return 4 * (n // n_per) * reso * reso * C + 8 * n + 4 * n * C
+    if name == "t2h_bilinear_sample_bwd":
+        reso, C, n_seg = a[1], a[2], a[7]
+        rows = _bytes.n_rows
+        return 4 * rows * C + 8 * rows + 4 * n_seg * C
+    if name in ("t2h_upsample_bilinear_fwd", "t2h_upsample_bilinear_bwd"):
+        B, h, w, C, oh, ow = a[1:7]
+        return 4 * B * C * (h * w + oh * ow)
+    if name in ("t2h_gather_rows", "t2h_scatter_rows"):
+        n, width = a[2], a[3]
+        return 8 * n * width + 4 * n
+    if name == "t2h_xy_keys":
+        return 12 * a[1] + 4 * a[1]
+    if name == "t2h_sort_by_cell":
+        return 4 * 16 * a[1] + 4 * a[2]  # 4 radix passes x (key+value in, key+value out) + cell table
+    if name == "t2h_cell_index":
+        return 16 * a[1]
+    return 0
+
+
+_bytes.n_rows = 0
+
+
+class KernelTimer:
+    """with KernelTimer(n_rows=B*N) as kt: ...   then kt.summary() -> {name: {...}}"""
+
+    def __init__(self, n_rows):
+        self.n_rows = n_rows
+        self.records = {}
+        self._orig = None
+
+    def __enter__(self):
+        self._orig = _lib.call
+        _bytes.n_rows = self.n_rows
+        timer = self
+
+        def timed_call(name, *args):
+            start = torch.cuda.Event(enable_timing=True)
+            stop = torch.cuda.Event(enable_timing=True)
+            start.record()
+            timer._orig(name, *args)
+            stop.record()
+            timer.records.setdefault(name, []).append((start, stop, _bytes(name, args)))
+
+        _lib.call = timed_call
+        for mod in _patch_targets():
+            mod.call = timed_call
+        return self
+
+    def __exit__(self, *exc):
+        _lib.call = self._orig
+        for mod in _patch_targets():
+            mod.call = self._orig
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+            nbytes = sum(b for _, _, b in recs)
+            out[name] = {
+                "launches": len(recs),
+                "ms_total": ms,
+                "ms_avg": ms / len(recs),
+                "bytes_per_launch": nbytes / len(recs),
+                "gbs": (nbytes / 1e9) / (ms / 1e3) if ms > 0 else 0.0,
+            }
+        return out
+
+
+def _patch_targets():
+    from . import functional
+    return [functional]

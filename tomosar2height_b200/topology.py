@@ -19,14 +19,17 @@ class CellLevel:
     otherwise it maps sorted position -> row.
     """
 
-    __slots__ = ("topo", "reso", "shift", "morton", "perm", "cell_start", "xyz_sorted", "B", "N", "n_seg")
+    __slots__ = ("topo", "reso", "shift", "morton", "perm", "tie", "cell_start", "xyz_sorted", "B", "N", "n_seg")
 
-    def __init__(self, topo, reso, shift, perm):
+    def __init__(self, topo, reso, shift, perm, tie=None):
         self.topo = topo
         self.reso = reso
         self.shift = shift
         self.morton = int(topo.morton)
         self.perm = perm
+        # argmax ties go to the smallest ORIGINAL point index; inside one sort key the stable sort
+        # already guarantees that, a coarser segment (shift > 0) needs the explicit rank
+        self.tie = tie if tie is not None else (topo.perm if shift > 0 else None)
         self.cell_start = topo.cell_start
         self.xyz_sorted = topo.xyz_sorted
         self.B, self.N = topo.B, topo.N
@@ -95,7 +98,9 @@ class Topology:
                                    "build a Topology at that resolution instead")
             self._sub[key] = sub
         sub = self._sub[key]
-        return CellLevel(sub, reso, 0, sub.perm)
+        if not hasattr(sub, "origin"):
+            sub.origin = self.perm[sub.perm.long()].contiguous()  # sub-sorted position -> original index
+        return CellLevel(sub, reso, 0, sub.perm, tie=sub.origin)
 
     def sort_rows(self, rows: torch.Tensor) -> torch.Tensor:
         """(B*N, C) rows in input order -> sorted order."""
@@ -139,7 +144,7 @@ def scatter_rows(rows: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
 class IndexLevel:
     """Level descriptor for an arbitrary (B, 1, N) int64 index (torch_scatter-style API)."""
 
-    __slots__ = ("reso", "shift", "morton", "perm", "cell_start", "xyz_sorted", "B", "N", "n_seg", "dim_size")
+    __slots__ = ("reso", "shift", "morton", "perm", "tie", "cell_start", "xyz_sorted", "B", "N", "n_seg", "dim_size")
 
     def __init__(self, index: torch.Tensor, dim_size: int, check: bool = True):
         if not index.is_cuda or index.dtype != torch.int64:
@@ -155,6 +160,6 @@ class IndexLevel:
             raise IndexError(f"scatter index out of range [0, {dim_size})")
         _, self.perm, self.cell_start = sort_keys(keys, B * dim_size)
         self.reso, self.shift, self.morton = 1, 0, 0
-        self.xyz_sorted = None
+        self.xyz_sorted, self.tie = None, None
         self.B, self.N, self.dim_size = B, N, dim_size
         self.n_seg = B * dim_size
