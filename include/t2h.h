@@ -116,6 +116,31 @@ int t2h_upsample_bilinear_fwd(const float* in, int B, int h, int w, int C, int o
 int t2h_upsample_bilinear_bwd(const float* grad_out, int B, int h, int w, int C, int out_h,
                               int out_w, float* grad_in, t2h_stream_t stream);
 
+/* ---- a6-a9: nn.Linear on the point path (block/resnet.py:46-54, pointnet.py:36-40,72-82,
+ *      alto.py:63-69,123-128,164-170,248-253, pixel.py:48-58) ------------------------------------
+ * 3xTF32 on tcgen05 tensor cores (fp32 in/out, fp32-grade accuracy, fp32 accumulation in TMEM).
+ *   out[r, n] = sum_k act(x[r, k]) * w[n, k] + bias[n]   (zeroed where mask[r, n] <= 0)   + residual[r, n]
+ * x may be the concatenation [x1 | x2] along k (the torch.cat of pointnet.py:78) without materialising
+ * it; act = ReLU when relu_in != 0.  The weight is passed pre-split (t2h_split_tf32) as w_hi / w_lo,
+ * row-major [n_out, k1 + k2].  The same entry point serves the input-gradient GEMM of the backward
+ * (x = grad_out, w = weight^T, mask = saved pre-activation, residual = gradient accumulated so far). */
+int t2h_split_tf32(const float* w, int64_t n, float* hi, float* lo, t2h_stream_t stream);
+int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const float* x2, int64_t ld_x2, int k2,
+                   int64_t rows, const float* w_hi, const float* w_lo, int n_out, const float* bias,
+                   int relu_in, const float* mask, int64_t ld_mask, const float* residual,
+                   int64_t ld_res, float* out, int64_t ld_out, t2h_stream_t stream);
+
+/* weight gradient grad_w[n, k] = sum_r grad_out[r, n] * act(x[r, k]) (autograd backward of nn.Linear):
+ * 3xTF32 tcgen05 GEMM over MN-major operands, split over the rows, partials summed in a fixed order */
+size_t t2h_linear_wgrad_workspace_bytes(int64_t rows, int n_out, int k_in);
+int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float* x, int64_t ld_x, int64_t rows,
+                     int n_out, int k_in, int relu_in, void* workspace, size_t workspace_bytes,
+                     float* grad_w, int64_t ld_w, t2h_stream_t stream);
+/* bias gradient: out[c] = sum_r g[r, c], two-stage and deterministic */
+size_t t2h_colsum_workspace_bytes(int64_t rows, int n);
+int t2h_colsum(const float* g, int64_t ld_g, int64_t rows, int n, void* workspace,
+               size_t workspace_bytes, float* out, t2h_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,119 @@
+"""tcgen05 3xTF32 linear layer (t2h_linear_*) vs an fp64 evaluation of the same layer."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _split(w):
+    from tomosar2height_b200 import _lib
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _lib.call("t2h_split_tf32", _lib.ptr(w), w.numel(), _lib.ptr(hi), _lib.ptr(lo))
+    return hi, lo
+
+
+def _linear_raw(x1, w, bias=None, x2=None, relu_in=False, mask=None, residual=None):
+    from tomosar2height_b200 import _lib
+    rows, k1 = x1.shape
+    k2 = 0 if x2 is None else x2.shape[1]
+    n_out = w.shape[0]
+    hi, lo = _split(w.contiguous())
+    out = torch.empty(rows, n_out, device=x1.device, dtype=torch.float32)
+    _lib.call("t2h_linear_fwd", _lib.ptr(x1), x1.stride(0), k1, _lib.ptr(x2), 0 if x2 is None else x2.stride(0), k2, rows,
+              _lib.ptr(hi), _lib.ptr(lo), n_out, _lib.ptr(bias), int(relu_in), _lib.ptr(mask),
+              0 if mask is None else mask.stride(0), _lib.ptr(residual), 0 if residual is None else residual.stride(0),
+              _lib.ptr(out), out.stride(0))
+    return out
+
+
+@pytest.mark.parametrize("rows,K,N", [(128, 32, 32), (1000, 64, 32), (4096, 32, 64), (777, 128, 256), (3000, 512, 1024),
+                                     (2500, 1024, 512), (130, 96, 48), (5000, 256, 128)])
+def test_linear_fwd_matches_fp64(rows, K, N):
+    g = torch.Generator().manual_seed(rows + K + N)
+    x = torch.randn(rows, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    y = _linear_raw(x, w, b)
+    ref = x.double() @ w.double().t() + b.double()
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err
+    # cuBLAS fp32 for comparison: the 3xTF32 result must be as close to fp64 as plain fp32 is (within 4x)
+    err32 = ((x @ w.t() + b).double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 20 * err32 + 1e-6, (err, err32)
+
+
+def test_linear_epilogues_and_concat():
+    g = torch.Generator().manual_seed(0)
+    rows = 1500
+    a = torch.randn(rows, 32, generator=g).cuda()
+    b2 = torch.randn(rows, 32, generator=g).cuda()
+    w = (torch.randn(32, 64, generator=g) / 8).cuda()
+    bias = torch.randn(32, generator=g).cuda()
+    res = torch.randn(rows, 32, generator=g).cuda()
+    mask = torch.randn(rows, 32, generator=g).cuda()
+    y = _linear_raw(a, w, bias, x2=b2, relu_in=True, mask=mask, residual=res)
+    x = torch.cat([a, b2], 1).double().relu()
+    ref = (x @ w.double().t() + bias.double()) * (mask > 0).double() + res.double()
+    assert (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+    # strided views (columns of a wider buffer) as inputs / outputs
+    wide = torch.randn(rows, 128, generator=g).cuda()
+    y2 = _linear_raw(wide[:, 64:96], w[:, :32].contiguous(), None)
+    ref2 = wide[:, 64:96].double() @ w[:, :32].double().t()
+    assert (y2.double() - ref2).abs().max().item() < 2e-6 * ref2.abs().max().item()
+
+
+@pytest.mark.parametrize("rows,K,N", [(128, 32, 32), (1000, 64, 32), (5000, 32, 64), (3000, 128, 256), (2000, 512, 1024),
+                                     (4100, 1024, 512), (130, 96, 48), (9000, 256, 128), (40, 64, 64)])
+@pytest.mark.parametrize("relu_in", [False, True])
+def test_linear_autograd_matches_fp64(rows, K, N, relu_in):
+    from tomosar2height_b200.linear import linear
+    g = torch.Generator().manual_seed(rows * 7 + K + N)
+    x = torch.randn(rows, K, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().requires_grad_(True)
+    b = torch.randn(N, generator=g).cuda().requires_grad_(True)
+    res = torch.randn(rows, N, generator=g).cuda().requires_grad_(True)
+    gy = torch.randn(rows, N, generator=g).cuda()
+    y = linear(x, w, b, relu_in=relu_in, residual=res)
+    y.backward(gy)
+    xd, wd, bd, rd = (t.detach().double().requires_grad_(True) for t in (x, w, b, res))
+    yd = (xd.relu() if relu_in else xd) @ wd.t() + bd + rd
+    yd.backward(gy.double())
+
+    def rel(a, ref):
+        return (a.double() - ref).abs().max().item() / ref.abs().max().item()
+
+    # tensor-core fp32 accumulation rounds once per MMA k-step: allow a slow growth with depth
+    tol = 1e-5 * max(1.0, max(K, N) / 256)
+    assert rel(y, yd) < tol, rel(y, yd)
+    assert rel(x.grad, xd.grad) < tol, rel(x.grad, xd.grad)
+    assert rel(w.grad, wd.grad) < tol, rel(w.grad, wd.grad)
+    assert rel(b.grad, bd.grad) < 1e-5
+    assert torch.equal(res.grad, gy)
+
+
+def test_linear_concat_autograd():
+    from tomosar2height_b200.linear import linear
+    g = torch.Generator().manual_seed(5)
+    rows = 2345
+    a = torch.randn(rows, 32, generator=g).cuda().requires_grad_(True)
+    b2 = torch.randn(rows, 32, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(32, 64, generator=g) / 8).cuda().requires_grad_(True)
+    gy = torch.randn(rows, 32, generator=g).cuda()
+    y = linear(a, w, None, x2=b2, relu_in=True)
+    y.backward(gy)
+    ad, bd, wd = (t.detach().double().requires_grad_(True) for t in (a, b2, w))
+    yd = torch.cat([ad, bd], 1).relu() @ wd.t()
+    yd.backward(gy.double())
+    for got, ref in ((y, yd), (a.grad, ad.grad), (b2.grad, bd.grad), (w.grad, wd.grad)):
+        assert (got.double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+
+
+def test_weight_split_cache_tracks_updates():
+    from tomosar2height_b200.linear import linear
+    w = torch.randn(32, 32).cuda().requires_grad_(True)
+    x = torch.randn(256, 32).cuda()
+    y0 = linear(x, w)
+    with torch.no_grad():
+        w.mul_(2.0)  # optimizer-style in-place update bumps the version counter
+    y1 = linear(x, w)
+    assert (y1 - 2 * y0).abs().max().item() < 1e-5 * y0.abs().max().item()

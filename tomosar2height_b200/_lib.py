@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libt2h.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["t2h_topology.cu", "t2h_segment.cu", "t2h_sample.cu"]
+SOURCES = ["t2h_topology.cu", "t2h_segment.cu", "t2h_sample.cu", "t2h_linear.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -39,8 +39,15 @@ SIGNATURES = {
     "t2h_bilinear_sample_bwd": [_p, _i32, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _p],
     "t2h_upsample_bilinear_fwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_upsample_bilinear_bwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
+    "t2h_split_tf32": [_p, _i64, _p, _p, _p],
+    "t2h_linear_wgrad_workspace_bytes": [_i64, _i32, _i32],
+    "t2h_linear_wgrad": [_p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p, _i64, _p],
+    "t2h_colsum_workspace_bytes": [_i64, _i32],
+    "t2h_colsum": [_p, _i64, _i64, _i32, _p, _sz, _p, _p],
+    "t2h_linear_fwd": [_p, _i64, _i32, _p, _i64, _i32, _i64, _p, _p, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p],
 }
-_RESTYPE = {"t2h_status_string": ctypes.c_char_p, "t2h_sort_workspace_bytes": _sz}
+_RESTYPE = {"t2h_status_string": ctypes.c_char_p, "t2h_sort_workspace_bytes": _sz,
+            "t2h_linear_wgrad_workspace_bytes": _sz, "t2h_colsum_workspace_bytes": _sz}
 
 _lib = None
 _lock = threading.Lock()

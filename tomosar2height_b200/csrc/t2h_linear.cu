@@ -1,0 +1,606 @@
+// Per-point MLP layers on the 5th-gen tensor cores (M1-M3 of SURVEY §2.2).
+//
+// Replaces nn.Linear / cuBLAS sgemm on the point path (pointnet.py:36-40,72-82, resnet.py:46-54,
+// alto.py:63-69,123-128,164-170,248-253, pixel.py:48-58) and its autograd backward.
+//
+//   y[r, n] = sum_k act(x[r, k]) * w[n, k] + bias[n]      (* mask[r, n] > 0)  (+ residual[r, n])
+//
+// fp32 in / fp32 out with fp32-grade accuracy: every operand is split into two TF32 terms
+// (hi + lo) and three tcgen05.mma.kind::tf32 products are accumulated in TMEM in fp32
+// (hi*hi + lo*hi + hi*lo, "3xTF32").  One CTA computes a 128-row x BLOCK_N tile:
+//   warp 0     TMA producer: x chunk (128 x 32 fp32, SWIZZLE_128B) + pre-split weight chunks
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2-5  in-place operand transform (optional ReLU, hi/lo split) and, after the K loop,
+//              the epilogue (tcgen05.ld -> bias / mask / residual -> global)
+// connected by mbarrier pipelines (TMA -> transform -> MMA -> slot free; MMA -> epilogue).
+#include "t2h_common.cuh"
+#include "t2h_tc.cuh"
+#include <cstdlib>
+
+namespace t2h {
+namespace gemm {
+
+using namespace tc;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;   // fp32 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 8;     // tf32
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
+constexpr int kThreads = 192;
+
+struct LinearArgs {
+  int64_t rows;
+  int n_out;
+  int k_chunks;    // total 32-wide K chunks (source 1 then source 2)
+  int k1_chunks;   // chunks taken from the first x source
+  int relu_in;
+  const float* bias;       // [n_out] or nullptr
+  const float* mask;       // [rows, ld_mask] or nullptr: result zeroed where mask <= 0
+  int64_t ld_mask;
+  const float* residual;   // [rows, ld_res] or nullptr (may alias out)
+  int64_t ld_res;
+  float* out;              // [rows, ld_out]
+  int64_t ld_out;
+};
+
+template <int BLOCK_N>
+struct Smem {
+  static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int STAGES = (BLOCK_N <= 64) ? 2 : ((BLOCK_N == 128) ? 3 : 2);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads)
+linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
+                     const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                     const LinearArgs p) {
+  using S = Smem<BLOCK_N>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + STAGES * S::STAGE_BYTES;
+  auto full_tma = [&](int s) { return bars + 8u * s; };
+  auto full_ab = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  const uint32_t tmem_full = bars + 8u * (3 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * S::STAGE_BYTES + 8 * (3 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * BLOCK_N;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_tma(s), 1);
+      mbar_init(full_ab(s), 128);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_x1);
+    tma_prefetch_desc(&tm_whi);
+    tma_prefetch_desc(&tm_wlo);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N < 32 ? 32 : BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        const uint32_t stage = base + s * S::STAGE_BYTES;
+        mbar_arrive_expect_tx(full_tma(s), A_BYTES + 2 * S::W_BYTES);
+        if (kc < p.k1_chunks) tma_load_2d(stage, &tm_x1, full_tma(s), kc * BLOCK_K, m0);
+        else                  tma_load_2d(stage, &tm_x2, full_tma(s), (kc - p.k1_chunks) * BLOCK_K, m0);
+        tma_load_2d(stage + 2 * A_BYTES, &tm_whi, full_tma(s), kc * BLOCK_K, n0);
+        tma_load_2d(stage + 2 * A_BYTES + S::W_BYTES, &tm_wlo, full_tma(s), kc * BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(full_tma(s), ph);
+        mbar_wait(full_ab(s), ph);
+        tc_fence_after();
+        const uint32_t stage = base + s * S::STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint32_t koff = k * UMMA_K * 4;  // 32 bytes along the swizzled 128-byte row
+          const uint64_t a_hi = make_smem_desc(stage + koff, 16, 1024);
+          const uint64_t a_lo = make_smem_desc(stage + A_BYTES + koff, 16, 1024);
+          const uint64_t b_hi = make_smem_desc(stage + 2 * A_BYTES + koff, 16, 1024);
+          const uint64_t b_lo = make_smem_desc(stage + 2 * A_BYTES + S::W_BYTES + koff, 16, 1024);
+          mma_tf32(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
+          mma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
+          mma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
+        }
+        mma_commit(empty(s));  // slot reusable once these MMAs have read their operands
+      }
+      mma_commit(tmem_full);
+    }
+  } else {
+    // ---- operand transform: thread t owns row t of the 128 x 32 chunk ------------------------
+    const int t = threadIdx.x - 64;
+    for (int kc = 0; kc < p.k_chunks; ++kc) {
+      const int s = kc % STAGES;
+      const uint32_t ph = (kc / STAGES) & 1;
+      mbar_wait(full_tma(s), ph);
+      float* hi_row = reinterpret_cast<float*>(base_ptr + s * S::STAGE_BYTES + t * 128);
+      float* lo_row = reinterpret_cast<float*>(base_ptr + s * S::STAGE_BYTES + A_BYTES + t * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = ((j + t) & 7) * 4;  // rotate chunks across threads: conflict-free 16-byte accesses
+        float4 v = *reinterpret_cast<float4*>(hi_row + c);
+        if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        *reinterpret_cast<float4*>(hi_row + c) = h;
+        *reinterpret_cast<float4*>(lo_row + c) = l;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(full_ab(s));
+    }
+    // ---- epilogue ------------------------------------------------------------------------------
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int64_t row = (int64_t)m0 + quarter * 32 + lane;
+    const bool row_ok = row < p.rows;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      float v[32];
+      __syncwarp();
+      tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int n = n0 + c0 + g * 4;
+        if (n >= p.n_out || !row_ok) continue;
+        float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        if (p.bias) {
+          const float4 b = ld4(p.bias + n);
+          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        if (p.mask) {
+          const float4 m = ld4(p.mask + row * p.ld_mask + n);
+          o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+        }
+        if (p.residual) {
+          const float4 r = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + n);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        st4(p.out + row * p.ld_out + n, o);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, BLOCK_N < 32 ? 32 : BLOCK_N);
+}
+
+
+// ---- weight gradient: dW[n, k] = sum_r g[r, n] * act(x[r, k]) ------------------------------------
+// The reduction runs over the ROWS, so both operands are "MN-major": the row-major tiles
+// g[32 rows x 128 n] and x[32 rows x BLOCK_N k] are loaded by TMA as 32-float (128-byte) wide boxes
+// and fed to tcgen05.mma with MN-major descriptors (no transposes anywhere).  Each CTA owns one
+// 128 x BLOCK_N tile of dW for one slice of the rows and writes an fp32 partial; the partials are
+// summed in a fixed order by wgrad_reduce_kernel (deterministic, no atomics).
+constexpr int WG_ROWS = 32;                    // rows per pipeline stage (4 MMA k-steps of 8)
+constexpr int WG_GROUP_BYTES = WG_ROWS * 128;  // one 32-float-wide box
+
+struct WgradArgs {
+  int64_t rows;
+  int n_out;       // M extent (columns of g)
+  int k_in;        // N extent (columns of x)
+  int relu_in;
+  int64_t rows_per_split;  // multiple of WG_ROWS
+  float* partial;  // [splits, n_out, k_in]
+  int debug;
+};
+
+template <int BLOCK_N>
+struct WgSmem {
+  static constexpr int A_B = 4 * WG_GROUP_BYTES;                 // 128 n-values
+  static constexpr int B_B = (BLOCK_N / 32) * WG_GROUP_BYTES;
+  static constexpr int STAGE_BYTES = 2 * (A_B + B_B);            // raw/hi + lo
+  static constexpr int STAGES = (BLOCK_N <= 64) ? 3 : 2;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads)
+wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, const WgradArgs p) {
+  using S = WgSmem<BLOCK_N>;
+  constexpr int STAGES = S::STAGES;
+  constexpr int A_B = S::A_B, B_B = S::B_B;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + STAGES * S::STAGE_BYTES;
+  auto full_tma = [&](int s) { return bars + 8u * s; };
+  auto full_ab = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  const uint32_t tmem_full = bars + 8u * (3 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * S::STAGE_BYTES + 8 * (3 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_M;   // rows of dW
+  const int k0 = blockIdx.y * BLOCK_N;   // columns of dW
+  const int64_t r_begin = (int64_t)blockIdx.z * p.rows_per_split;
+  const int64_t r_end = min(r_begin + p.rows_per_split, p.rows);
+  const int n_iter = r_end > r_begin ? (int)((r_end - r_begin + WG_ROWS - 1) / WG_ROWS) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_tma(s), 1);
+      mbar_init(full_ab(s), 128);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        const uint32_t stage = base + s * S::STAGE_BYTES;
+        const int r = (int)(r_begin + (int64_t)it * WG_ROWS);
+        mbar_arrive_expect_tx(full_tma(s), A_B + B_B);
+        // rows past r_end of this split but inside the tensor would be double counted: the split size
+        // is a multiple of WG_ROWS, so only the global tail is partial and TMA zero-fills it
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) tma_load_2d(stage + gq * WG_GROUP_BYTES, &tm_g, full_tma(s), n0 + gq * 32, r);
+#pragma unroll
+        for (int gq = 0; gq < BLOCK_N / 32; ++gq)
+          tma_load_2d(stage + A_B + gq * WG_GROUP_BYTES, &tm_x, full_tma(s), k0 + gq * 32, r);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 1, 1);
+      if (p.debug == 2) idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
+      if (p.debug == 3) idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 1, 0);
+      if (p.debug == 4) idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 1);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(full_tma(s), ph);
+        mbar_wait(full_ab(s), ph);
+        tc_fence_after();
+        const uint32_t a_hi0 = base + s * S::STAGE_BYTES, b_hi0 = a_hi0 + A_B;
+        const uint32_t a_lo0 = a_hi0 + A_B + B_B, b_lo0 = a_lo0 + A_B;
+#pragma unroll
+        for (int k = 0; k < WG_ROWS / UMMA_K; ++k) {
+          const uint32_t koff = k * 1024;  // 8 rows x 128 bytes
+          const uint64_t a_hi = make_smem_desc(a_hi0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
+          const uint64_t a_lo = make_smem_desc(a_lo0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
+          const uint64_t b_hi = make_smem_desc(b_hi0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
+          const uint64_t b_lo = make_smem_desc(b_lo0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
+          mma_tf32(tmem_d, a_lo, b_hi, idesc, (it | k) != 0);
+          mma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
+          mma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
+        }
+        mma_commit(empty(s));
+      }
+      mma_commit(tmem_full);
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(full_tma(s), ph);
+      float4* hi = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES + A_B + B_B);
+      // the split is element-wise, hence independent of the swizzled placement
+#pragma unroll 4
+      for (int c = t; c < (A_B + B_B) / 16; c += 128) {
+        float4 v = hi[c];
+        if (p.relu_in && c >= A_B / 16) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        hi[c] = h;
+        lo[c] = l;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(full_ab(s));
+    }
+    const int quarter = warp & 3;
+    const int n = n0 + quarter * 32 + lane;
+    float* dst = p.partial + ((int64_t)blockIdx.z * p.n_out + n) * p.k_in;
+    if (n_iter > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      float v[32];
+      if (n_iter > 0) {
+        __syncwarp();
+        tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        if (p.debug == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 1.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+#pragma unroll
+      for (int gq = 0; gq < 8; ++gq) {
+        const int k = k0 + c0 + gq * 4;
+        if (n < p.n_out && k < p.k_in) st4(dst + k, make_float4(v[gq * 4], v[gq * 4 + 1], v[gq * 4 + 2], v[gq * 4 + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, BLOCK_N);
+}
+
+// dst[n, k] (ld) = sum over splits of partial[s, n, k], fixed order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int n_out, int k_in,
+                                    float* __restrict__ dst, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  const int64_t total4 = (int64_t)n_out * k_in / 4;
+  if (i >= total4) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = ld4(partial + ((int64_t)s * n_out * k_in) + i * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const int64_t e = i * 4;
+  st4(dst + (e / k_in) * ld + (e % k_in), acc);
+}
+
+// column sums (bias gradient): partial[b, c] = sum of rows [b*rpb, (b+1)*rpb) of g[:, c]
+template <int CW>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ g, int64_t rows, int n, int64_t ld,
+                                                             int64_t rows_per_block, float* __restrict__ partial) {
+  __shared__ float red[256];
+  constexpr int RY = 256 / CW;
+  const int tx = threadIdx.x % CW, ty = threadIdx.x / CW;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, rows);
+  for (int c = tx + blockIdx.y * CW; c < n; c += CW * gridDim.y) {
+    float acc = 0.f;
+    for (int64_t r = r0 + ty; r < r1; r += RY) acc += g[r * ld + c];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (ty == 0) {
+      for (int j = 1; j < RY; ++j) acc += red[j * CW + tx];
+      partial[(int64_t)blockIdx.x * n + c] = acc;
+    }
+    __syncthreads();
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int blocks, int n, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float acc = 0.f;
+  for (int b = 0; b < blocks; ++b) acc += partial[(int64_t)b * n + c];
+  out[c] = acc;
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float h, l;
+  split_tf32(w[i], h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return q == cudaDriverEntryPointSuccess ? (EncodeTiledFn)ptr : nullptr;
+  }();
+  return fn;
+}
+
+// 2-D fp32 tensor [outer, inner] (inner contiguous), box [box_outer, box_inner], 128-byte swizzle
+static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                     uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N>
+static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const float* w_hi, const float* w_lo, int k_total,
+                         const LinearArgs& args, cudaStream_t stream) {
+  CUtensorMap whi, wlo;
+  if (!make_map(&whi, w_hi, k_total, args.n_out, k_total, BLOCK_K, BLOCK_N)) return T2H_ERR_CUDA;
+  if (!make_map(&wlo, w_lo, k_total, args.n_out, k_total, BLOCK_K, BLOCK_N)) return T2H_ERR_CUDA;
+  auto kern = linear_tf32x3_kernel<BLOCK_N>;
+  static bool configured = false;  // idempotent attribute, racing threads set the same value
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BLOCK_N>::TOTAL) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return T2H_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)((args.rows + BLOCK_M - 1) / BLOCK_M), (unsigned)((args.n_out + BLOCK_N - 1) / BLOCK_N));
+  kern<<<grid, kThreads, Smem<BLOCK_N>::TOTAL, stream>>>(x1, x2, whi, wlo, args);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+}  // namespace gemm
+}  // namespace t2h
+
+using namespace t2h;
+using namespace t2h::gemm;
+
+extern "C" int t2h_split_tf32(const float* w, int64_t n, float* hi, float* lo, t2h_stream_t stream) {
+  if (!w || !hi || !lo || n < 0) return T2H_ERR_INVALID_ARGUMENT;
+  if (n == 0) return T2H_OK;
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, n, hi, lo);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const float* x2, int64_t ld_x2, int k2,
+                              int64_t rows, const float* w_hi, const float* w_lo, int n_out, const float* bias,
+                              int relu_in, const float* mask, int64_t ld_mask, const float* residual, int64_t ld_res,
+                              float* out, int64_t ld_out, t2h_stream_t stream) {
+  if (!x1 || !w_hi || !w_lo || !out || rows < 0 || k1 <= 0 || k2 < 0 || n_out <= 0) return T2H_ERR_INVALID_ARGUMENT;
+  if (k2 > 0 && !x2) return T2H_ERR_INVALID_ARGUMENT;
+  // TMA: 16-byte aligned bases and row pitches; a second source must start on a chunk boundary
+  if ((k1 % 4) || (k2 % 4) || (ld_x1 % 4) || (k2 > 0 && ((ld_x2 % 4) || (k1 % BLOCK_K))) || (n_out % 4) ||
+      (ld_out % 4) || (residual && (ld_res % 4)) || (mask && (ld_mask % 4)))
+    return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)out | (uintptr_t)bias |
+       (uintptr_t)mask | (uintptr_t)residual) & 15)
+    return T2H_ERR_INVALID_ARGUMENT;
+  if (rows == 0) return T2H_OK;
+  CUtensorMap m1, m2;
+  if (!make_map(&m1, x1, k1, rows, ld_x1, BLOCK_K, BLOCK_M)) return T2H_ERR_CUDA;
+  if (k2 > 0) { if (!make_map(&m2, x2, k2, rows, ld_x2, BLOCK_K, BLOCK_M)) return T2H_ERR_CUDA; }
+  else m2 = m1;
+  LinearArgs a;
+  a.rows = rows; a.n_out = n_out;
+  a.k1_chunks = (k1 + BLOCK_K - 1) / BLOCK_K;
+  a.k_chunks = a.k1_chunks + (k2 + BLOCK_K - 1) / BLOCK_K;
+  a.relu_in = relu_in; a.bias = bias; a.mask = mask; a.ld_mask = ld_mask;
+  a.residual = residual; a.ld_res = ld_res; a.out = out; a.ld_out = ld_out;
+  const int k_total = k1 + k2;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_out <= 32) return launch_linear<32>(m1, m2, w_hi, w_lo, k_total, a, s);
+  if (n_out <= 64) return launch_linear<64>(m1, m2, w_hi, w_lo, k_total, a, s);
+  if (n_out <= 128) return launch_linear<128>(m1, m2, w_hi, w_lo, k_total, a, s);
+  return launch_linear<256>(m1, m2, w_hi, w_lo, k_total, a, s);
+}
+
+// ---- weight / bias gradient -----------------------------------------------------------------------
+static int wgrad_splits(int64_t rows, int tiles) {
+  int64_t want = (2 * kSMs + tiles - 1) / tiles;              // ~2 CTAs per SM in flight
+  int64_t max_splits = (rows + WG_ROWS - 1) / WG_ROWS;
+  if (want > max_splits) want = max_splits;
+  if (want > 512) want = 512;
+  return (int)(want < 1 ? 1 : want);
+}
+
+extern "C" size_t t2h_linear_wgrad_workspace_bytes(int64_t rows, int n_out, int k_in) {
+  if (rows <= 0 || n_out <= 0 || k_in <= 0) return 256;
+  const int bn = k_in <= 32 ? 32 : (k_in <= 64 ? 64 : (k_in <= 128 ? 128 : 256));
+  const int tiles = ((n_out + BLOCK_M - 1) / BLOCK_M) * ((k_in + bn - 1) / bn);
+  return (size_t)wgrad_splits(rows, tiles) * n_out * k_in * sizeof(float) + 256;
+}
+
+template <int BLOCK_N>
+static int launch_wgrad(const float* g, int64_t ld_g, const float* x, int64_t ld_x, WgradArgs a, int splits,
+                        cudaStream_t stream) {
+  CUtensorMap mg, mx;
+  if (!make_map(&mg, g, a.n_out, a.rows, ld_g, 32, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
+  if (!make_map(&mx, x, a.k_in, a.rows, ld_x, 32, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
+  auto kern = wgrad_tf32x3_kernel<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<BLOCK_N>::TOTAL) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return T2H_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)((a.n_out + BLOCK_M - 1) / BLOCK_M), (unsigned)((a.k_in + BLOCK_N - 1) / BLOCK_N), (unsigned)splits);
+  kern<<<grid, kThreads, WgSmem<BLOCK_N>::TOTAL, stream>>>(mg, mx, a);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float* x, int64_t ld_x, int64_t rows,
+                                int n_out, int k_in, int relu_in, void* workspace, size_t workspace_bytes,
+                                float* grad_w, int64_t ld_w, t2h_stream_t stream) {
+  if (!grad_out || !x || !grad_w || !workspace || rows < 0 || n_out <= 0 || k_in <= 0) return T2H_ERR_INVALID_ARGUMENT;
+  if ((n_out % 4) || (k_in % 4) || (ld_g % 4) || (ld_x % 4) || (ld_w % 4)) return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)grad_out | (uintptr_t)x | (uintptr_t)grad_w | (uintptr_t)workspace) & 15) return T2H_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < t2h_linear_wgrad_workspace_bytes(rows, n_out, k_in)) return T2H_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int bn = k_in <= 32 ? 32 : (k_in <= 64 ? 64 : (k_in <= 128 ? 128 : 256));
+  const int tiles = ((n_out + BLOCK_M - 1) / BLOCK_M) * ((k_in + bn - 1) / bn);
+  const int splits = rows > 0 ? wgrad_splits(rows, tiles) : 1;
+  WgradArgs a;
+  a.rows = rows; a.n_out = n_out; a.k_in = k_in; a.relu_in = relu_in;
+  int64_t per = (rows + splits - 1) / splits;
+  a.rows_per_split = ((per + WG_ROWS - 1) / WG_ROWS) * WG_ROWS;
+  if (a.rows_per_split < WG_ROWS) a.rows_per_split = WG_ROWS;
+  a.partial = (float*)workspace;
+  { const char* e = getenv("T2H_WGRAD_DEBUG"); a.debug = e ? atoi(e) : 0; }
+  int st = T2H_OK;
+  if (rows > 0) {
+    if (bn == 32) st = launch_wgrad<32>(grad_out, ld_g, x, ld_x, a, splits, s);
+    else if (bn == 64) st = launch_wgrad<64>(grad_out, ld_g, x, ld_x, a, splits, s);
+    else if (bn == 128) st = launch_wgrad<128>(grad_out, ld_g, x, ld_x, a, splits, s);
+    else st = launch_wgrad<256>(grad_out, ld_g, x, ld_x, a, splits, s);
+    if (st) return st;
+  }
+  const int64_t total4 = (int64_t)n_out * k_in / 4;
+  wgrad_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(a.partial, rows > 0 ? splits : 0, n_out, k_in, grad_w, ld_w);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" size_t t2h_colsum_workspace_bytes(int64_t rows, int n) {
+  (void)rows;
+  return (size_t)4 * kSMs * (n > 0 ? n : 1) * sizeof(float) + 256;
+}
+
+extern "C" int t2h_colsum(const float* g, int64_t ld_g, int64_t rows, int n, void* workspace, size_t workspace_bytes,
+                          float* out, t2h_stream_t stream) {
+  if (!g || !out || !workspace || rows < 0 || n <= 0) return T2H_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < t2h_colsum_workspace_bytes(rows, n)) return T2H_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = 4 * kSMs;
+  int64_t rpb = (rows + blocks - 1) / blocks;
+  if (rpb < 8) rpb = 8;
+  blocks = (int)((rows + rpb - 1) / rpb);
+  float* partial = (float*)workspace;
+  if (blocks > 0) {
+    if (n <= 32) colsum_partial_kernel<32><<<dim3(blocks, 1), 256, 0, s>>>(g, rows, n, ld_g, rpb, partial);
+    else if (n <= 64) colsum_partial_kernel<64><<<dim3(blocks, 1), 256, 0, s>>>(g, rows, n, ld_g, rpb, partial);
+    else if (n <= 128) colsum_partial_kernel<128><<<dim3(blocks, 1), 256, 0, s>>>(g, rows, n, ld_g, rpb, partial);
+    else colsum_partial_kernel<256><<<dim3(blocks, 1), 256, 0, s>>>(g, rows, n, ld_g, rpb, partial);
+    T2H_CHECK_LAUNCH();
+  }
+  colsum_final_kernel<<<(n + 255) / 256, 256, 0, s>>>(partial, blocks, n, out);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
