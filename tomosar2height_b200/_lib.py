@@ -33,10 +33,10 @@ SIGNATURES = {
     "t2h_scatter_rows": [_p, _p, _i64, _i32, _p, _p],
     "t2h_seg_max_fwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p],
     "t2h_seg_max_bwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
-    "t2h_seg_reduce_fwd": [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
+    "t2h_seg_reduce_fwd": [_p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_seg_broadcast": [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_bilinear_sample_fwd": [_p, _i32, _i32, _p, _i64, _p, _i64, _i64, _p, _p],
-    "t2h_bilinear_sample_bwd": [_p, _i32, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _p],
+    "t2h_bilinear_sample_bwd": [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _p],
     "t2h_upsample_bilinear_fwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_upsample_bilinear_bwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_split_tf32": [_p, _i64, _p, _p, _p],

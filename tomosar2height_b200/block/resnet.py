@@ -5,7 +5,8 @@ size_in != size_out.  Parameters are ordinary fp32 ``nn.Linear`` weights with th
 names (fc_0, fc_1, shortcut) so checkpoints load unchanged.
 """
 import torch.nn as nn
-import torch.nn.functional as F
+
+from ..linear import linear
 
 
 class ResnetBlockFC(nn.Module):
@@ -20,8 +21,15 @@ class ResnetBlockFC(nn.Module):
         self.shortcut = None if size_in == size_out else nn.Linear(size_in, size_out, bias=False)
         nn.init.zeros_(self.fc_1.weight)  # resnet.py:34 (overwritten by the model-level Xavier init)
 
-    def forward(self, x):
-        hidden = self.fc_0(F.relu(x))
-        dx = self.fc_1(F.relu(hidden))
-        skip = x if self.shortcut is None else self.shortcut(x)
-        return skip + dx
+    def forward(self, x, x2=None):
+        """``x`` (..., size_in), or the two halves ``x | x2`` of a concatenated input (the
+        ``torch.cat([net, pooled])`` of pointnet.py:78 is never materialised).  Three tcgen05 GEMMs with
+        ReLU-on-load, bias and the residual add fused (t2h_linear_fwd)."""
+        hidden = linear(x, self.fc_0.weight, self.fc_0.bias, x2=x2, relu_in=True)
+        if self.shortcut is None:
+            if x2 is not None:
+                raise RuntimeError("ResnetBlockFC: a split input needs a shortcut projection")
+            skip = x
+        else:
+            skip = linear(x, self.shortcut.weight, None, x2=x2)
+        return linear(hidden, self.fc_1.weight, self.fc_1.bias, relu_in=True, residual=skip)

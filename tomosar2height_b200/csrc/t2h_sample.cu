@@ -48,7 +48,8 @@ sample_fwd_kernel(const float* __restrict__ plane, int reso, const float* __rest
   for (int64_t i = first + sub; i < last; i += RPI) {
     const int64_t row = perm ? (int64_t)perm[i] : i;
     const int64_t b = row / n_per_batch;
-    const Taps t = make_taps(__ldg(xyz + i * stride), __ldg(xyz + i * stride + 1), reso);
+    const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + i * stride));
+    const Taps t = make_taps(pxy.x, pxy.y, reso);
     // taps beyond the last row/column carry zero weight (ix == r-1 exactly); clamp the address
     const int x1 = min(t.x0 + 1, reso - 1), y1 = min(t.y0 + 1, reso - 1);
     const float w_nw = __fmul_rn(t.wx0, t.wy0);
@@ -75,47 +76,59 @@ sample_fwd_kernel(const float* __restrict__ plane, int reso, const float* __rest
   }
 }
 
-// One warp per plane cell (enumerated in key order of this level, so a CTA covers a compact
-// block of cells when keys are Morton codes).
-template <class RS>
+// WPS warps per plane cell (cells enumerated in key order of this level, so a CTA covers a compact
+// block of cells when keys are Morton codes).  Every warp scans a slice of each neighbour cell's
+// points; slices are combined through shared memory in slice order (fixed summation order).
+template <class RS, int WPS>
 __global__ void __launch_bounds__(kSampleWarps * kWarp)
 sample_bwd_kernel(const float* __restrict__ grad_rows, int reso, const float* __restrict__ xyz, int64_t stride,
                   const int32_t* __restrict__ perm, const int32_t* __restrict__ cell_start, int64_t n_seg, int shift,
                   int morton, float* __restrict__ grad_plane) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  const int lane = threadIdx.x & 31;
+  constexpr int SEGS = kSampleWarps / WPS;
+  __shared__ float4 part_sum[WPS > 1 ? kSampleWarps * (C / 4) : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR;
-  const int64_t seg = (int64_t)blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
-  if (seg >= n_seg) return;
+  const int64_t seg = (int64_t)blockIdx.x * SEGS + warp / WPS;
+  const int part = warp % WPS;
+  const bool valid = seg < n_seg;
   const int64_t cells = (int64_t)reso * reso;
-  const int64_t b = seg / cells;
-  int cx, cy;
-  cell_decode((uint32_t)(seg - b * cells), reso, morton, cx, cy);
+  const int64_t b = valid ? seg / cells : 0;
+  int cx = 0, cy = 0;
+  if (valid) cell_decode((uint32_t)(seg - b * cells), reso, morton, cx, cy);
 
   float4 acc[CH];
 #pragma unroll
   for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int ny = cy + dy;
-    if (ny < 0 || ny >= reso) continue;
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int nx = cx + dx;
-      if (nx < 0 || nx >= reso) continue;
-      const int64_t key = b * cells + cell_code((uint32_t)nx, (uint32_t)ny, reso, morton);
-      const int beg = cell_start[key << shift], end = cell_start[(key + 1) << shift];
-      for (int i = beg + sub; i < end; i += RPI) {
-        const Taps t = make_taps(__ldg(xyz + (int64_t)i * stride), __ldg(xyz + (int64_t)i * stride + 1), reso);
-        const float wx = (t.x0 == cx) ? t.wx0 : ((t.x0 + 1 == cx) ? t.wx1 : 0.f);
-        const float wy = (t.y0 == cy) ? t.wy0 : ((t.y0 + 1 == cy) ? t.wy1 : 0.f);
-        const float w = __fmul_rn(wx, wy);
-        if (w != 0.f) {
-          const int64_t row = perm ? (int64_t)perm[i] : (int64_t)i;
-          const float* src = grad_rows + row * C + l * 4;
+  if (valid) {
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int ny = cy + dy;
+      if (ny < 0 || ny >= reso) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int nx = cx + dx;
+        if (nx < 0 || nx >= reso) continue;
+        const int64_t key = b * cells + cell_code((uint32_t)nx, (uint32_t)ny, reso, morton);
+        int beg = cell_start[key << shift], end = cell_start[(key + 1) << shift];
+        if (WPS > 1) {
+          const int slice = (end - beg + WPS - 1) / WPS;
+          beg = min(beg + part * slice, end);
+          end = min(beg + slice, end);
+        }
+        for (int i = beg + sub; i < end; i += RPI) {
+          const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + (int64_t)i * stride));
+          const Taps t = make_taps(pxy.x, pxy.y, reso);
+          const float wx = (t.x0 == cx) ? t.wx0 : ((t.x0 + 1 == cx) ? t.wx1 : 0.f);
+          const float wy = (t.y0 == cy) ? t.wy0 : ((t.y0 + 1 == cy) ? t.wy1 : 0.f);
+          const float w = __fmul_rn(wx, wy);
+          if (w != 0.f) {
+            const int64_t row = perm ? (int64_t)perm[i] : (int64_t)i;
+            const float* src = grad_rows + row * C + l * 4;
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const float4 gq = ld4(src + c * LPR * 4);
-            acc[c].x += w * gq.x; acc[c].y += w * gq.y; acc[c].z += w * gq.z; acc[c].w += w * gq.w;
+            for (int c = 0; c < CH; ++c) {
+              const float4 gq = ld4(src + c * LPR * 4);
+              acc[c].x += w * gq.x; acc[c].y += w * gq.y; acc[c].z += w * gq.z; acc[c].w += w * gq.w;
+            }
           }
         }
       }
@@ -128,7 +141,22 @@ sample_bwd_kernel(const float* __restrict__ grad_rows, int reso, const float* __
       float4 o = shfl_xor4(acc[c], off);
       acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
     }
-  if (sub == 0) {
+  if (WPS > 1) {
+    if (sub == 0 && part > 0) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) part_sum[warp * (C / 4) + c * LPR + l] = acc[c];
+    }
+    __syncthreads();
+    if (part == 0 && sub == 0) {
+      for (int q = 1; q < WPS; ++q)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const float4 o = part_sum[(warp + q) * (C / 4) + c * LPR + l];
+          acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
+        }
+    }
+  }
+  if (valid && part == 0 && sub == 0) {
     float* dst = grad_plane + ((b * reso + cy) * (int64_t)reso + cx) * C + l * 4;
 #pragma unroll
     for (int c = 0; c < CH; ++c) st4(dst + c * LPR * 4, acc[c]);
@@ -234,7 +262,8 @@ using namespace t2h;
 extern "C" int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, const float* xyz_sorted,
                                        int64_t point_stride, const int32_t* perm, int64_t n_points,
                                        int64_t n_per_batch, float* out_rows, t2h_stream_t stream) {
-  if (!plane || !xyz_sorted || !out_rows || reso <= 0 || point_stride < 2 || n_points < 0 || n_per_batch <= 0)
+  if (!plane || !xyz_sorted || !out_rows || reso <= 0 || point_stride < 2 || (point_stride & 1) || n_points < 0 ||
+      n_per_batch <= 0)
     return T2H_ERR_INVALID_ARGUMENT;
   if (n_points == 0) return T2H_OK;
   const int64_t warps = (n_points + kPointsPerWarp - 1) / kPointsPerWarp;
@@ -245,19 +274,28 @@ extern "C" int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, cons
   return T2H_OK;
 }
 
-extern "C" int t2h_bilinear_sample_bwd(const float* grad_rows, int reso, int C, const float* xyz_sorted,
-                                       int64_t point_stride, const int32_t* perm, const int32_t* cell_start,
-                                       int64_t n_seg, int shift, int morton, float* grad_plane,
-                                       t2h_stream_t stream) {
-  if (!grad_rows || !xyz_sorted || !cell_start || !grad_plane || reso <= 0 || point_stride < 2 || n_seg < 0 ||
+extern "C" int t2h_bilinear_sample_bwd(const float* grad_rows, int64_t n_points, int reso, int C,
+                                       const float* xyz_sorted, int64_t point_stride, const int32_t* perm,
+                                       const int32_t* cell_start, int64_t n_seg, int shift, int morton,
+                                       float* grad_plane, t2h_stream_t stream) {
+  if (!grad_rows || !xyz_sorted || !cell_start || !grad_plane || reso <= 0 || point_stride < 2 || (point_stride & 1) ||
+      n_points < 0 || n_seg < 0 ||
       shift < 0 || (shift & 1) || (shift && !morton) || n_seg % ((int64_t)reso * reso))
     return T2H_ERR_INVALID_ARGUMENT;
   if (morton && (reso & (reso - 1))) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  const unsigned blocks = (unsigned)((n_seg + kSampleWarps - 1) / kSampleWarps);
-  T2H_DISPATCH_ROWSHAPE(C, sample_bwd_kernel<RS><<<blocks, kSampleWarps * kWarp, 0, (cudaStream_t)stream>>>(
-                               grad_rows, reso, xyz_sorted, point_stride, perm, cell_start, n_seg, shift, morton,
-                               grad_plane));
+  // ~9 neighbour cells are scanned per plane cell: split the scan over several warps on coarse levels
+  const int64_t avg = n_points / n_seg;
+  int wps = 1;
+  while (wps < kSampleWarps && avg >= 4 * wps) wps *= 2;
+  const unsigned blocks = (unsigned)((n_seg * wps + kSampleWarps - 1) / kSampleWarps);
+  cudaStream_t s = (cudaStream_t)stream;
+#define T2H_SBWD(W) sample_bwd_kernel<RS, W><<<blocks, kSampleWarps * kWarp, 0, s>>>( \
+      grad_rows, reso, xyz_sorted, point_stride, perm, cell_start, n_seg, shift, morton, grad_plane)
+  T2H_DISPATCH_ROWSHAPE(C, {
+    if (wps == 1) T2H_SBWD(1); else if (wps == 2) T2H_SBWD(2); else if (wps == 4) T2H_SBWD(4); else T2H_SBWD(8);
+  });
+#undef T2H_SBWD
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }

@@ -173,22 +173,36 @@ seg_max_bwd_kernel(const float* __restrict__ grad_pooled, const float* __restric
   }
 }
 
-template <class RS>
+// WPS warps cooperate on one segment (coarse levels hold hundreds of points per cell): each warp
+// reduces a contiguous slice of the segment's rows, the slices are combined through shared memory
+// in slice order, so the summation order stays fixed.
+template <class RS, int WPS>
 __global__ void __launch_bounds__(kSegWarps * kWarp)
 seg_reduce_fwd_kernel(const float* __restrict__ rows, SegGeom g, int mean, float* __restrict__ plane) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  const int lane = threadIdx.x & 31;
-  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
-  if (seg >= g.n_seg) return;
+  constexpr int SEGS = kSegWarps / WPS;  // segments per CTA
+  __shared__ float4 part_sum[WPS > 1 ? kSegWarps * (C / 4) : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t seg = (int64_t)blockIdx.x * SEGS + warp / WPS;
+  const int part = warp % WPS;
+  const bool valid = seg < g.n_seg;
   const int sub = lane / LPR, l = lane % LPR;
-  const int beg = g.cell_start[seg << g.shift], end = g.cell_start[(seg + 1) << g.shift];
+  int beg = 0, end = 0;
+  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
+  const int len = end - beg;
+  int my_beg = beg, my_end = end;
+  if (WPS > 1) {
+    const int slice = (len + WPS - 1) / WPS;
+    my_beg = min(beg + part * slice, end);
+    my_end = min(my_beg + slice, end);
+  }
 
   float4 acc[CH];
 #pragma unroll
   for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int i = beg + sub;
+  int i = my_beg + sub;
   // two rows in flight per lane
-  for (; i + RPI < end; i += 2 * RPI) {
+  for (; i + RPI < my_end; i += 2 * RPI) {
     const int64_t r0 = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
     const int64_t r1 = g.perm ? (int64_t)g.perm[i + RPI] : (int64_t)(i + RPI);
     float4 v0[CH], v1[CH];
@@ -203,7 +217,7 @@ seg_reduce_fwd_kernel(const float* __restrict__ rows, SegGeom g, int mean, float
       acc[c].x += v1[c].x; acc[c].y += v1[c].y; acc[c].z += v1[c].z; acc[c].w += v1[c].w;
     }
   }
-  for (; i < end; i += RPI) {
+  for (; i < my_end; i += RPI) {
     const int64_t r0 = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -218,8 +232,23 @@ seg_reduce_fwd_kernel(const float* __restrict__ rows, SegGeom g, int mean, float
       float4 o = shfl_xor4(acc[c], off);
       acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
     }
-  if (sub == 0) {
-    const float cnt = (float)max(end - beg, 1);
+  if (WPS > 1) {
+    if (sub == 0 && part > 0) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) part_sum[warp * (C / 4) + c * LPR + l] = acc[c];
+    }
+    __syncthreads();
+    if (part == 0 && sub == 0) {
+      for (int q = 1; q < WPS; ++q)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const float4 o = part_sum[(warp + q) * (C / 4) + c * LPR + l];
+          acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
+        }
+    }
+  }
+  if (valid && part == 0 && sub == 0) {
+    const float cnt = (float)max(len, 1);
     const int64_t prow = plane_row(g, seg);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -264,6 +293,14 @@ static int check_geom(const int32_t* cell_start, int64_t n_seg, int shift, int C
 
 static inline unsigned seg_blocks(int64_t n_seg) { return (unsigned)((n_seg + kSegWarps - 1) / kSegWarps); }
 
+// warps per segment from the mean segment length: ~8+ rows per warp, at most the whole CTA
+static inline int warps_per_segment(int64_t n_rows, int64_t n_seg) {
+  const int64_t avg = n_seg > 0 ? n_rows / n_seg : 0;
+  int wps = 1;
+  while (wps < kSegWarps && avg >= 16 * wps) wps *= 2;
+  return wps;
+}
+
 }  // namespace t2h
 
 using namespace t2h;
@@ -296,16 +333,23 @@ extern "C" int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane
   return T2H_OK;
 }
 
-extern "C" int t2h_seg_reduce_fwd(const float* rows, const int32_t* perm, const int32_t* cell_start, int64_t n_seg,
-                                  int shift, int C, int morton, int reso, int mean, float* plane,
+extern "C" int t2h_seg_reduce_fwd(const float* rows, int64_t n_rows, const int32_t* perm, const int32_t* cell_start,
+                                  int64_t n_seg, int shift, int C, int morton, int reso, int mean, float* plane,
                                   t2h_stream_t stream) {
   int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
   if (st) return st;
   if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
   SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso};
-  T2H_DISPATCH_ROWSHAPE(C, seg_reduce_fwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
-                               rows, g, mean, plane));
+  const int wps = warps_per_segment(n_rows, n_seg);
+  const unsigned blocks = (unsigned)((n_seg * wps + kSegWarps - 1) / kSegWarps);
+  cudaStream_t s = (cudaStream_t)stream;
+  T2H_DISPATCH_ROWSHAPE(C, {
+    if (wps == 1) seg_reduce_fwd_kernel<RS, 1><<<blocks, kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane);
+    else if (wps == 2) seg_reduce_fwd_kernel<RS, 2><<<blocks, kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane);
+    else if (wps == 4) seg_reduce_fwd_kernel<RS, 4><<<blocks, kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane);
+    else seg_reduce_fwd_kernel<RS, 8><<<blocks, kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane);
+  });
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }

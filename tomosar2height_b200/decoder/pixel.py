@@ -10,6 +10,7 @@ import torch.nn.functional as F
 
 from .. import functional as T
 from ..block import ResnetBlockFC
+from ..linear import linear
 
 
 class ConvDecoder(nn.Module):
@@ -38,7 +39,9 @@ class FCDecoder(nn.Module):
     def forward(self, x):
         for block in self.blocks:
             x = block(x)
-        return self.fc_out(self.act(x))
+        if self.act is F.relu:
+            return linear(x, self.fc_out.weight, self.fc_out.bias, relu_in=True)
+        return linear(self.act(x), self.fc_out.weight, self.fc_out.bias)
 
 
 class PixelwiseDecoder(nn.Module):

@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import functional as T
+from ..linear import linear
 from ..topology import Topology
 from .unet import conv3x3, conv1x1, upconv2x2, check_modes, xavier_normal_convs
 
@@ -40,9 +41,10 @@ class _Exchange:
         return T.plane_to_nchw(T.seg_mean(c, level), p.B, reso_plane)
 
     def exchange(self, p, plane, c_last):
-        c = self.fc_comm(self.sample_plane_feature(p, plane))
-        if c_last is not None:
-            c = c + self.fc_c(c_last)
+        sampled = self.sample_plane_feature(p, plane)
+        hidden = linear(sampled, self.fc_comm[0].weight, self.fc_comm[0].bias)
+        carry = None if c_last is None else linear(c_last, self.fc_c.weight, self.fc_c.bias)
+        c = linear(hidden, self.fc_comm[2].weight, self.fc_comm[2].bias, relu_in=True, residual=carry)
         return self.generate_plane_features(p, c, plane.shape[1], plane.shape[2]), c
 
 

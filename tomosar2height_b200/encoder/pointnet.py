@@ -13,6 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import functional as T
+from ..linear import linear
 from .. import scatter as S
 from ..block import ResnetBlockFC
 from ..topology import Topology
@@ -47,14 +48,17 @@ class LocalPoolPointnet(nn.Module):
         """inputs (B, N, 3) fp32 CUDA, xy in the open unit square -> {'xy': (B, C, R, R)}."""
         topo = Topology(inputs, self.reso_plane)
         level = topo.level(self.reso_plane)
-        net = self.blocks[0](self.fc_pos(topo.xyz_sorted))
+        # xyz rows are zero-padded to 4 floats (16-byte rows for TMA); pad fc_pos.weight to match
+        pad = topo.xyz_sorted.shape[1] - self.fc_pos.weight.shape[1]
+        net = linear(topo.xyz_sorted, F.pad(self.fc_pos.weight, (0, pad)), self.fc_pos.bias)
+        net = self.blocks[0](net)
         for block in self.blocks[1:]:
             if self.scatter_type == 'max':
                 pooled = T.seg_max_pool(net, level)
             else:
                 pooled = T.seg_broadcast(T.seg_mean(net, level), level)
-            net = block(torch.cat([net, pooled], dim=1))
-        c = self.fc_c(F.relu(net))
+            net = block(net, pooled)  # [net | pooled] without the concat copy
+        c = linear(net, self.fc_c.weight, self.fc_c.bias, relu_in=True)
         plane = T.plane_to_nchw(T.seg_mean(c, level), topo.B, self.reso_plane)
         if self.unet_type == 'unet':
             return {'xy': self.unet(plane)}

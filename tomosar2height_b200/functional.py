@@ -92,7 +92,7 @@ class _SegReduce(torch.autograd.Function):
         rows = _rows(rows, "seg_reduce")
         C = rows.shape[1]
         plane = torch.empty(level.n_seg, C, dtype=torch.float32, device=rows.device)
-        call("t2h_seg_reduce_fwd", ptr(rows), *_geom(level), C, level.morton, level.reso, int(mean), ptr(plane))
+        call("t2h_seg_reduce_fwd", ptr(rows), rows.shape[0], *_geom(level), C, level.morton, level.reso, int(mean), ptr(plane))
         ctx.level, ctx.mean, ctx.n_rows = level, mean, rows.shape[0]
         return plane
 
@@ -124,7 +124,7 @@ class _SegBroadcast(torch.autograd.Function):
         g_rows = g_rows.contiguous()
         C = g_rows.shape[1]
         g_plane = torch.empty(level.n_seg, C, dtype=torch.float32, device=g_rows.device)
-        call("t2h_seg_reduce_fwd", ptr(g_rows), *_geom(level), C, level.morton, level.reso, int(ctx.mean), ptr(g_plane))
+        call("t2h_seg_reduce_fwd", ptr(g_rows), g_rows.shape[0], *_geom(level), C, level.morton, level.reso, int(ctx.mean), ptr(g_plane))
         return g_plane, None, None, None
 
 
@@ -155,7 +155,7 @@ class _BilinearSample(torch.autograd.Function):
         C = g_rows.shape[1]
         g_plane = torch.empty(ctx.shape, dtype=torch.float32, device=g_rows.device)
         xyz = level.xyz_sorted
-        call("t2h_bilinear_sample_bwd", ptr(g_rows), level.reso, C, ptr(xyz), xyz.shape[1], ptr(level.perm),
+        call("t2h_bilinear_sample_bwd", ptr(g_rows), g_rows.shape[0], level.reso, C, ptr(xyz), xyz.shape[1], ptr(level.perm),
              ptr(level.cell_start), level.n_seg, level.shift, level.morton, ptr(g_plane))
         return g_plane, None
 

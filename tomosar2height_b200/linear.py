@@ -10,6 +10,7 @@ accumulation fused in the epilogue) and the weight gradient through the MN-major
 ordinary fp32 ``nn.Parameter``s; their TF32 hi/lo splits (and transposes) are derived caches keyed on
 the parameter's version counter.
 """
+import os
 import weakref
 
 import torch
@@ -43,6 +44,8 @@ class _SplitCache:
 
 
 _cache = _SplitCache()
+# ablation switch for benchmarks / debugging only: run the point MLPs as plain cuBLAS fp32 GEMMs
+USE_LIBRARY_GEMM = os.environ.get("T2H_LINEAR", "") == "cublas"
 
 
 def _rowmajor(t):
@@ -134,7 +137,7 @@ def linear(x, weight, bias=None, x2=None, relu_in=False, residual=None):
     if not x.is_cuda:
         raise RuntimeError("linear: expected a CUDA tensor (the B200 path has no CPU fallback)")
     lead = x.shape[:-1]
-    if not tc_eligible(x, weight, x2):
+    if USE_LIBRARY_GEMM or not tc_eligible(x, weight, x2):
         # odd widths (e.g. a 1-wide output head): plain library GEMM
         xin = x if x2 is None else torch.cat([x, x2], dim=-1)
         y = F.linear(F.relu(xin) if relu_in else xin, weight, bias)

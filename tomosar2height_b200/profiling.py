@@ -30,7 +30,11 @@ def _bytes(name, a):
         n_seg, C = a[4], a[6]
         rows = _bytes.n_rows
         return 4 * rows * C + 4 * n_seg * C + 4 * rows * C
-    if name in ("t2h_seg_reduce_fwd", "t2h_seg_broadcast"):
+    if name == "t2h_seg_reduce_fwd":
+        n_seg, C = a[4], a[6]
+        rows = _bytes.n_rows
+        return 4 * rows * C + 4 * rows + 4 * n_seg * C
+    if name == "t2h_seg_broadcast":
         n_seg, C = a[3], a[5]
         rows = _bytes.n_rows
         return 4 * rows * C + 4 * rows + 4 * n_seg * C
@@ -38,7 +42,7 @@ def _bytes(name, a):
         reso, C, n, n_per = a[1], a[2], a[6], a[7]
         return 4 * (n // n_per) * reso * reso * C + 8 * n + 4 * n * C
     if name == "t2h_bilinear_sample_bwd":
-        reso, C, n_seg = a[1], a[2], a[7]
+        reso, C, n_seg = a[2], a[3], a[8]
         rows = _bytes.n_rows
         return 4 * rows * C + 8 * rows + 4 * n_seg * C
     if name in ("t2h_upsample_bilinear_fwd", "t2h_upsample_bilinear_bwd"):
@@ -53,6 +57,23 @@ def _bytes(name, a):
         return 4 * 16 * a[1] + 4 * a[2]  # 4 radix passes x (key+value in, key+value out) + cell table
     if name == "t2h_cell_index":
         return 16 * a[1]
+    if name == "t2h_linear_fwd":  # x1, ld, k1, x2, ld, k2, rows, w_hi, w_lo, n_out, bias, relu, mask, ld, res, ld, out, ld
+        k, rows, n = a[2] + a[5], a[6], a[9]
+        return 4 * rows * (k + n + (n if a[12] else 0) + (n if a[14] else 0)) + 8 * k * n
+    if name == "t2h_linear_wgrad":  # g, ld, x, ld, rows, n_out, k_in, ...
+        rows, n, k = a[4], a[5], a[6]
+        return 4 * rows * (n + k) + 4 * n * k
+    if name == "t2h_colsum":
+        return 4 * a[2] * a[3]
+    return 0
+
+
+def _flops(name, a):
+    """algorithmic FLOPs (2*M*K*N, one pass; the three TF32 passes of the split are not counted)."""
+    if name == "t2h_linear_fwd":
+        return 2 * a[6] * (a[2] + a[5]) * a[9]
+    if name == "t2h_linear_wgrad":
+        return 2 * a[4] * a[5] * a[6]
     return 0
 
 
@@ -78,7 +99,7 @@ class KernelTimer:
             start.record()
             timer._orig(name, *args)
             stop.record()
-            timer.records.setdefault(name, []).append((start, stop, _bytes(name, args)))
+            timer.records.setdefault(name, []).append((start, stop, _bytes(name, args), _flops(name, args)))
 
         _lib.call = timed_call
         for mod in _patch_targets():
@@ -95,18 +116,20 @@ class KernelTimer:
         torch.cuda.synchronize()
         out = {}
         for name, recs in self.records.items():
-            ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-            nbytes = sum(b for _, _, b in recs)
+            ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+            nbytes = sum(r[2] for r in recs)
+            flops = sum(r[3] for r in recs)
             out[name] = {
                 "launches": len(recs),
                 "ms_total": ms,
                 "ms_avg": ms / len(recs),
                 "bytes_per_launch": nbytes / len(recs),
                 "gbs": (nbytes / 1e9) / (ms / 1e3) if ms > 0 else 0.0,
+                "tflops": (flops / 1e12) / (ms / 1e3) if ms > 0 else 0.0,
             }
         return out
 
 
 def _patch_targets():
     from . import functional
-    return [functional]
+    return [functional]  # modules that bound `call` by name; the others go through _lib.call

@@ -44,7 +44,8 @@ class Topology:
     """Sort the points of a (B, N, 3) tile batch by (tile, cell) once.
 
     Attributes
-      xyz_sorted  (B*N, 3) fp32 : coordinates in sorted order
+      xyz_sorted  (B*N, 4) fp32 : coordinates in sorted order, zero-padded to 16-byte rows
+                                  (vector loads in the sampling kernels, TMA-loadable for fc_pos)
       perm        (B*N,) int32  : sorted position -> flat input index  (b*N + n)
       cell_start  (B*R*R + 1,) int32
       morton      bool          : Morton keys (power-of-two R) -> coarser levels share the sort
@@ -54,6 +55,10 @@ class Topology:
         _lib.require_cuda_f32(xyz, "Topology(xyz)")
         if xyz.dim() != 3 or xyz.shape[2] < 2:
             raise RuntimeError(f"Topology: expected (B, N, >=2) points, got {tuple(xyz.shape)}")
+        if xyz.shape[2] > 4:
+            raise RuntimeError("Topology: at most 4 coordinates per point are supported")
+        if xyz.shape[2] != 4:
+            xyz = torch.nn.functional.pad(xyz, (0, 4 - xyz.shape[2]))
         xyz = xyz.contiguous()
         self.B, self.N, self.D = xyz.shape
         self.reso = int(reso)
