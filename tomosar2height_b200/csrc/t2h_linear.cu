@@ -43,22 +43,30 @@ struct LinearArgs {
   int64_t ld_out;
 };
 
-template <int BLOCK_N>
+// A_TMEM: the split x operand is written to tensor memory (tcgen05.st) and consumed from there, so the
+// three MMAs of a k-step only read the WEIGHT tiles from shared memory.  In SS mode the 128x256 tile is
+// shared-memory-bandwidth bound (each MMA re-reads 4 KB of A and 8 KB of B per 134 cycles).
+template <int BLOCK_N, bool A_TMEM>
 struct Smem {
   static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int STAGES = (BLOCK_N <= 64) ? 2 : ((BLOCK_N == 128) ? 3 : 2);
+  static constexpr int STAGE_BYTES = (A_TMEM ? 1 : 2) * A_BYTES + 2 * W_BYTES;
+  static constexpr int STAGES = A_TMEM ? 2 : ((BLOCK_N == 128) ? 3 : 2);  // A_TMEM/128: 96 KB + 256 TMEM cols -> 2 CTAs per SM
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  // TMEM columns: accumulator + (hi, lo) x 32 columns per stage when A lives in TMEM
+  static constexpr int TMEM_USED = (BLOCK_N < 32 ? 32 : BLOCK_N) + (A_TMEM ? STAGES * 64 : 0);
+  static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : (TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512)));
+  static constexpr int W_OFF = (A_TMEM ? 1 : 2) * A_BYTES;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool A_TMEM>
 __global__ void __launch_bounds__(kThreads)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                      const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
                      const LinearArgs p) {
-  using S = Smem<BLOCK_N>;
+  using S = Smem<BLOCK_N, A_TMEM>;
   constexpr int STAGES = S::STAGES;
+  constexpr int W_OFF = S::W_OFF;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -73,6 +81,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BLOCK_M;
   const int n0 = blockIdx.y * BLOCK_N;
+  constexpr uint32_t A_TMEM_COL0 = (BLOCK_N < 32 ? 32 : BLOCK_N);  // A stages follow the accumulator columns
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -86,7 +95,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
     tma_prefetch_desc(&tm_whi);
     tma_prefetch_desc(&tm_wlo);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N < 32 ? 32 : BLOCK_N);
+  if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -102,8 +111,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
         mbar_arrive_expect_tx(full_tma(s), A_BYTES + 2 * S::W_BYTES);
         if (kc < p.k1_chunks) tma_load_2d(stage, &tm_x1, full_tma(s), kc * BLOCK_K, m0);
         else                  tma_load_2d(stage, &tm_x2, full_tma(s), (kc - p.k1_chunks) * BLOCK_K, m0);
-        tma_load_2d(stage + 2 * A_BYTES, &tm_whi, full_tma(s), kc * BLOCK_K, n0);
-        tma_load_2d(stage + 2 * A_BYTES + S::W_BYTES, &tm_wlo, full_tma(s), kc * BLOCK_K, n0);
+        tma_load_2d(stage + W_OFF, &tm_whi, full_tma(s), kc * BLOCK_K, n0);
+        tma_load_2d(stage + W_OFF + S::W_BYTES, &tm_wlo, full_tma(s), kc * BLOCK_K, n0);
       }
     }
   } else if (warp == 1) {
@@ -119,13 +128,21 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
           const uint32_t koff = k * UMMA_K * 4;  // 32 bytes along the swizzled 128-byte row
-          const uint64_t a_hi = make_smem_desc(stage + koff, 16, 1024);
-          const uint64_t a_lo = make_smem_desc(stage + A_BYTES + koff, 16, 1024);
-          const uint64_t b_hi = make_smem_desc(stage + 2 * A_BYTES + koff, 16, 1024);
-          const uint64_t b_lo = make_smem_desc(stage + 2 * A_BYTES + S::W_BYTES + koff, 16, 1024);
-          mma_tf32(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
-          mma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
-          mma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
+          const uint64_t b_hi = make_smem_desc(stage + W_OFF + koff, 16, 1024);
+          const uint64_t b_lo = make_smem_desc(stage + W_OFF + S::W_BYTES + koff, 16, 1024);
+          if (A_TMEM) {
+            const uint32_t a_hi = tmem_d + A_TMEM_COL0 + s * 64 + k * UMMA_K;
+            const uint32_t a_lo = a_hi + 32;
+            mma_tf32_ts(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
+            mma_tf32_ts(tmem_d, a_hi, b_lo, idesc, 1);
+            mma_tf32_ts(tmem_d, a_hi, b_hi, idesc, 1);
+          } else {
+            const uint64_t a_hi = make_smem_desc(stage + koff, 16, 1024);
+            const uint64_t a_lo = make_smem_desc(stage + A_BYTES + koff, 16, 1024);
+            mma_tf32(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
+            mma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
+            mma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
+          }
         }
         mma_commit(empty(s));  // slot reusable once these MMAs have read their operands
       }
@@ -133,12 +150,31 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
     }
   } else {
     // ---- operand transform: thread t owns row t of the 128 x 32 chunk ------------------------
-    const int t = threadIdx.x - 64;
+    // (a warp may only touch TMEM lanes [32*(warp%4), +32), so rows follow the same quarters)
+    const int t = (warp & 3) * 32 + lane;
     for (int kc = 0; kc < p.k_chunks; ++kc) {
       const int s = kc % STAGES;
       const uint32_t ph = (kc / STAGES) & 1;
       mbar_wait(full_tma(s), ph);
       float* hi_row = reinterpret_cast<float*>(base_ptr + s * S::STAGE_BYTES + t * 128);
+      if (A_TMEM) {
+        // TMA placed logical 16-byte chunk j of row t at chunk j ^ (t & 7) (SWIZZLE_128B)
+        float hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v = *reinterpret_cast<const float4*>(hi_row + ((j ^ (t & 7)) * 4));
+          if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          split_tf32(v.x, hi[4 * j], lo[4 * j]); split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+          split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+        }
+        const uint32_t a_dst = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + A_TMEM_COL0 + s * 64;
+        tmem_st_32x32(a_dst, hi);
+        tmem_st_32x32(a_dst + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(full_ab(s));
+        continue;
+      }
       float* lo_row = reinterpret_cast<float*>(base_ptr + s * S::STAGE_BYTES + A_BYTES + t * 128);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -187,7 +223,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_d, BLOCK_N < 32 ? 32 : BLOCK_N);
+  if (warp == 1) tmem_dealloc(tmem_d, S::TMEM_COLS);
 }
 
 
@@ -442,23 +478,23 @@ static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool A_TMEM>
 static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const float* w_hi, const float* w_lo, int k_total,
                          const LinearArgs& args, cudaStream_t stream) {
   CUtensorMap whi, wlo;
   if (!make_map(&whi, w_hi, k_total, args.n_out, k_total, BLOCK_K, BLOCK_N)) return T2H_ERR_CUDA;
   if (!make_map(&wlo, w_lo, k_total, args.n_out, k_total, BLOCK_K, BLOCK_N)) return T2H_ERR_CUDA;
-  auto kern = linear_tf32x3_kernel<BLOCK_N>;
+  auto kern = linear_tf32x3_kernel<BLOCK_N, A_TMEM>;
   static bool configured = false;  // idempotent attribute, racing threads set the same value
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BLOCK_N>::TOTAL) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BLOCK_N, A_TMEM>::TOTAL) != cudaSuccess) {
       (void)cudaGetLastError();
       return T2H_ERR_CUDA;
     }
     configured = true;
   }
   dim3 grid((unsigned)((args.rows + BLOCK_M - 1) / BLOCK_M), (unsigned)((args.n_out + BLOCK_N - 1) / BLOCK_N));
-  kern<<<grid, kThreads, Smem<BLOCK_N>::TOTAL, stream>>>(x1, x2, whi, wlo, args);
+  kern<<<grid, kThreads, Smem<BLOCK_N, A_TMEM>::TOTAL, stream>>>(x1, x2, whi, wlo, args);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
@@ -503,10 +539,16 @@ extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const floa
   a.residual = residual; a.ld_res = ld_res; a.out = out; a.ld_out = ld_out;
   const int k_total = k1 + k2;
   cudaStream_t s = (cudaStream_t)stream;
-  if (n_out <= 32) return launch_linear<32>(m1, m2, w_hi, w_lo, k_total, a, s);
-  if (n_out <= 64) return launch_linear<64>(m1, m2, w_hi, w_lo, k_total, a, s);
-  if (n_out <= 128) return launch_linear<128>(m1, m2, w_hi, w_lo, k_total, a, s);
-  return launch_linear<256>(m1, m2, w_hi, w_lo, k_total, a, s);
+  static const int ss_only = []() { const char* e = getenv("T2H_LINEAR_SS"); return e ? atoi(e) : 0; }();  // ablation
+  if (n_out <= 32) return launch_linear<32, false>(m1, m2, w_hi, w_lo, k_total, a, s);
+  if (n_out <= 64) return launch_linear<64, false>(m1, m2, w_hi, w_lo, k_total, a, s);
+  if (ss_only) {
+    if (n_out <= 128) return launch_linear<128, false>(m1, m2, w_hi, w_lo, k_total, a, s);
+    return launch_linear<256, false>(m1, m2, w_hi, w_lo, k_total, a, s);
+  }
+  static const int wide = []() { const char* e = getenv("T2H_LINEAR_BN256"); return e ? atoi(e) : 0; }();  // ablation
+  if (n_out <= 128 || !wide) return launch_linear<128, true>(m1, m2, w_hi, w_lo, k_total, a, s);
+  return launch_linear<256, true>(m1, m2, w_hi, w_lo, k_total, a, s);
 }
 
 // ---- weight / bias gradient -----------------------------------------------------------------------
