@@ -41,6 +41,7 @@ struct LinearArgs {
   int64_t ld_res;
   float* out;              // [rows, ld_out]
   int64_t ld_out;
+  int aux_kind;            // which of mask (1) / residual (2) is staged through shared memory by TMA (0: none)
 };
 
 // A_TMEM: the split x operand is written to tensor memory (tcgen05.st) and consumed from there, so the
@@ -63,6 +64,7 @@ template <int BLOCK_N, bool A_TMEM>
 __global__ void __launch_bounds__(kThreads)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                      const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_aux,
                      const LinearArgs p) {
   using S = Smem<BLOCK_N, A_TMEM>;
   constexpr int STAGES = S::STAGES;
@@ -79,8 +81,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * S::STAGE_BYTES + 8 * (3 * STAGES + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * BLOCK_N;
+  // 1-D grid, N-tile fastest: the CTAs that share an x tile are co-scheduled, so the tile is fetched
+  // from DRAM once and re-read from L2 (an M-fastest raster re-read x from DRAM once per N-tile)
+  const int n_tiles = (p.n_out + BLOCK_N - 1) / BLOCK_N;
+  const int m0 = (int)(blockIdx.x / n_tiles) * BLOCK_M;
+  const int n0 = (int)(blockIdx.x % n_tiles) * BLOCK_N;
   constexpr uint32_t A_TMEM_COL0 = (BLOCK_N < 32 ? 32 : BLOCK_N);  // A stages follow the accumulator columns
 
   if (threadIdx.x == 0) {
@@ -90,10 +95,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
       mbar_init(empty(s), 1);
     }
     mbar_init(tmem_full, 1);
+    mbar_init(bars + 8u * (3 * STAGES + 2), 1);  // aux (mask / residual) tile landed
     fence_barrier_init();
     tma_prefetch_desc(&tm_x1);
     tma_prefetch_desc(&tm_whi);
     tma_prefetch_desc(&tm_wlo);
+    tma_prefetch_desc(&tm_out);
   }
   if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
   tc_fence_before();
@@ -190,35 +197,63 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
       mbar_arrive(full_ab(s));
     }
     // ---- epilogue ------------------------------------------------------------------------------
+    // TMEM -> registers -> bias / ReLU-mask / residual -> shared memory (128-byte swizzled rows) -> one
+    // TMA store per 32-column block: global writes (and the mask / residual reads, which arrive by
+    // TMA into the same staging rows) are full coalesced lines instead of 16-byte pieces per thread.
+    // The pipeline stages are free by now (all TMA loads consumed, all MMAs complete) and are reused.
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int64_t row = (int64_t)m0 + quarter * 32 + lane;
+    const int64_t row = (int64_t)m0 + t;
     const bool row_ok = row < p.rows;
+    const uint32_t aux_bar = bars + 8u * (3 * STAGES + 2);
+    const int n_blocks = min(BLOCK_N / 32, (p.n_out - n0 + 31) / 32);
+    static_assert((BLOCK_N / 32) * A_BYTES <= STAGES * S::STAGE_BYTES, "staging does not fit");
+    if (p.aux_kind) {
+      if (t == 0) {
+        mbar_arrive_expect_tx(aux_bar, (uint32_t)n_blocks * A_BYTES);
+        const CUtensorMap* aux = &tm_aux;
+        for (int cb = 0; cb < n_blocks; ++cb) tma_load_2d(base + cb * A_BYTES, aux, aux_bar, n0 + cb * 32, m0);
+      }
+      mbar_wait(aux_bar, 0);
+    }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int cb = 0; cb < n_blocks; ++cb) {
       float v[32];
       __syncwarp();
-      tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32), v);
+      float* srow = reinterpret_cast<float*>(base_ptr + cb * A_BYTES + t * 128);
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const int n = n0 + c0 + g * 4;
-        if (n >= p.n_out || !row_ok) continue;
+        const int n = n0 + cb * 32 + g * 4;
+        float4* slot = reinterpret_cast<float4*>(srow + ((g ^ (t & 7)) * 4));  // SWIZZLE_128B placement
         float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        if (p.bias) {
-          const float4 b = ld4(p.bias + n);
-          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        if (n < p.n_out) {
+          if (p.bias) {
+            const float4 b = ld4(p.bias + n);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (p.mask) {
+            float4 m;
+            if (p.aux_kind == 1) m = *slot;
+            else m = row_ok ? ld4(p.mask + row * p.ld_mask + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+          }
+          if (p.residual) {
+            float4 r;
+            if (p.aux_kind == 2) r = *slot;
+            else r = row_ok ? *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+          }
         }
-        if (p.mask) {
-          const float4 m = ld4(p.mask + row * p.ld_mask + n);
-          o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
-        }
-        if (p.residual) {
-          const float4 r = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + n);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
-        st4(p.out + row * p.ld_out + n, o);
+        *slot = o;
       }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+    if (t == 0) {
+      for (int cb = 0; cb < n_blocks; ++cb) tma_store_2d(&tm_out, base + cb * A_BYTES, n0 + cb * 32, m0);
+      tma_store_commit_and_wait();
     }
   }
   tc_fence_before();
@@ -481,9 +516,13 @@ static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_
 template <int BLOCK_N, bool A_TMEM>
 static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const float* w_hi, const float* w_lo, int k_total,
                          const LinearArgs& args, cudaStream_t stream) {
-  CUtensorMap whi, wlo;
+  CUtensorMap whi, wlo, mout, maux;
   if (!make_map(&whi, w_hi, k_total, args.n_out, k_total, BLOCK_K, BLOCK_N)) return T2H_ERR_CUDA;
   if (!make_map(&wlo, w_lo, k_total, args.n_out, k_total, BLOCK_K, BLOCK_N)) return T2H_ERR_CUDA;
+  if (!make_map(&mout, args.out, args.n_out, args.rows, args.ld_out, 32, BLOCK_M)) return T2H_ERR_CUDA;
+  maux = mout;
+  if (args.aux_kind == 1 && !make_map(&maux, args.mask, args.n_out, args.rows, args.ld_mask, 32, BLOCK_M)) return T2H_ERR_CUDA;
+  if (args.aux_kind == 2 && !make_map(&maux, args.residual, args.n_out, args.rows, args.ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
   auto kern = linear_tf32x3_kernel<BLOCK_N, A_TMEM>;
   static bool configured = false;  // idempotent attribute, racing threads set the same value
   if (!configured) {
@@ -493,8 +532,9 @@ static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const flo
     }
     configured = true;
   }
-  dim3 grid((unsigned)((args.rows + BLOCK_M - 1) / BLOCK_M), (unsigned)((args.n_out + BLOCK_N - 1) / BLOCK_N));
-  kern<<<grid, kThreads, Smem<BLOCK_N, A_TMEM>::TOTAL, stream>>>(x1, x2, whi, wlo, args);
+  const int64_t tiles = ((args.rows + BLOCK_M - 1) / BLOCK_M) * ((args.n_out + BLOCK_N - 1) / BLOCK_N);
+  if (tiles > 0x7fffffffLL) return T2H_ERR_UNSUPPORTED_SHAPE;
+  kern<<<(unsigned)tiles, kThreads, Smem<BLOCK_N, A_TMEM>::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
@@ -537,6 +577,7 @@ extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const floa
   a.k_chunks = a.k1_chunks + (k2 + BLOCK_K - 1) / BLOCK_K;
   a.relu_in = relu_in; a.bias = bias; a.mask = mask; a.ld_mask = ld_mask;
   a.residual = residual; a.ld_res = ld_res; a.out = out; a.ld_out = ld_out;
+  a.aux_kind = mask ? 1 : (residual ? 2 : 0);
   const int k_total = k1 + k2;
   cudaStream_t s = (cudaStream_t)stream;
   static const int ss_only = []() { const char* e = getenv("T2H_LINEAR_SS"); return e ? atoi(e) : 0; }();  // ablation
