@@ -131,12 +131,14 @@ int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const float* x2, int6
                    int relu_in, const float* mask, int64_t ld_mask, const float* residual,
                    int64_t ld_res, float* out, int64_t ld_out, t2h_stream_t stream);
 
-/* weight gradient grad_w[n, k] = sum_r grad_out[r, n] * act(x[r, k]) (autograd backward of nn.Linear):
- * 3xTF32 tcgen05 GEMM over MN-major operands, split over the rows, partials summed in a fixed order */
+/* weight gradient grad_w[n, k] = sum_r grad_out[r, n] * act(x[r, k]) and (grad_b nullable) bias gradient
+ * grad_b[n] = sum_r grad_out[r, n] (autograd backward of nn.Linear): 3xTF32 tcgen05 GEMM over
+ * MN-major operands (grad_out^T through tensor memory), split over the rows, partials summed in a
+ * fixed order */
 size_t t2h_linear_wgrad_workspace_bytes(int64_t rows, int n_out, int k_in);
 int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float* x, int64_t ld_x, int64_t rows,
                      int n_out, int k_in, int relu_in, void* workspace, size_t workspace_bytes,
-                     float* grad_w, int64_t ld_w, t2h_stream_t stream);
+                     float* grad_w, int64_t ld_w, float* grad_b, t2h_stream_t stream);
 /* bias gradient: out[c] = sum_r g[r, c], two-stage and deterministic */
 size_t t2h_colsum_workspace_bytes(int64_t rows, int n);
 int t2h_colsum(const float* g, int64_t ld_g, int64_t rows, int n, void* workspace,

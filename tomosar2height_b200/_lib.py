@@ -41,7 +41,7 @@ SIGNATURES = {
     "t2h_upsample_bilinear_bwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_split_tf32": [_p, _i64, _p, _p, _p],
     "t2h_linear_wgrad_workspace_bytes": [_i64, _i32, _i32],
-    "t2h_linear_wgrad": [_p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p, _i64, _p],
+    "t2h_linear_wgrad": [_p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _p, _sz, _p, _i64, _p, _p],
     "t2h_colsum_workspace_bytes": [_i64, _i32],
     "t2h_colsum": [_p, _i64, _i64, _i32, _p, _sz, _p, _p],
     "t2h_linear_fwd": [_p, _i64, _i32, _p, _i64, _i32, _i64, _p, _p, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p],

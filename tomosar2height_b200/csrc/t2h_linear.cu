@@ -262,14 +262,20 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
 }
 
 
-// ---- weight gradient: dW[n, k] = sum_r g[r, n] * act(x[r, k]) ------------------------------------
-// The reduction runs over the ROWS, so both operands are "MN-major": the row-major tiles
-// g[32 rows x 128 n] and x[32 rows x BLOCK_N k] are loaded by TMA as 32-float (128-byte) wide boxes
-// and fed to tcgen05.mma with MN-major descriptors (no transposes anywhere).  Each CTA owns one
-// 128 x BLOCK_N tile of dW for one slice of the rows and writes an fp32 partial; the partials are
-// summed in a fixed order by wgrad_reduce_kernel (deterministic, no atomics).
+// ---- weight gradient: dW[n, k] = sum_r g[r, n] * act(x[r, k]),  db[n] = sum_r g[r, n] ---------------
+// The reduction runs over the ROWS, so the operands are "MN-major".
+//   A = g^T: the row-major tile g[32 rows x 128 n] is TMA-loaded un-swizzled; thread n reads its column
+//       (conflict-free), splits it and writes it with tcgen05.st into TMEM lane n -- the transpose is
+//       free, the A operand never touches shared memory again, and the same thread accumulates the
+//       bias gradient (column sum) on the way.
+//   B = x:  row-major tile x[32 rows x BLOCK_N k] TMA-loaded as 32-float boxes with
+//       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and consumed with SWIZZLE_128B_BASE32B MN-major descriptors
+//       (the only tf32 MN-major layout); hi/lo split element-wise in place.
+// Each CTA owns one 128 x BLOCK_N tile of dW for one slice of the rows and writes an fp32 partial;
+// partials are summed in a fixed order by wgrad_reduce_kernel (deterministic, no atomics).
 constexpr int WG_ROWS = 32;                    // rows per pipeline stage (4 MMA k-steps of 8)
 constexpr int WG_GROUP_BYTES = WG_ROWS * 128;  // one 32-float-wide box
+constexpr int WG_A_BYTES = WG_ROWS * BLOCK_M * 4;
 
 struct WgradArgs {
   int64_t rows;
@@ -277,17 +283,18 @@ struct WgradArgs {
   int k_in;        // N extent (columns of x)
   int relu_in;
   int64_t rows_per_split;  // multiple of WG_ROWS
-  float* partial;  // [splits, n_out, k_in]
-  int debug;
+  float* partial;       // [splits, n_out, k_in]
+  float* partial_bias;  // [splits, n_out] or nullptr
 };
 
 template <int BLOCK_N>
 struct WgSmem {
-  static constexpr int A_B = 4 * WG_GROUP_BYTES;                 // 128 n-values
   static constexpr int B_B = (BLOCK_N / 32) * WG_GROUP_BYTES;
-  static constexpr int STAGE_BYTES = 2 * (A_B + B_B);            // raw/hi + lo
-  static constexpr int STAGES = (BLOCK_N <= 64) ? 3 : 2;
+  static constexpr int STAGE_BYTES = WG_A_BYTES + 2 * B_B;       // g raw | x hi | x lo
+  static constexpr int STAGES = 2;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int TMEM_USED = BLOCK_N + STAGES * 64;        // accumulator + (g hi, g lo) per stage
+  static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
 };
 
 template <int BLOCK_N>
@@ -295,7 +302,7 @@ __global__ void __launch_bounds__(kThreads)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, const WgradArgs p) {
   using S = WgSmem<BLOCK_N>;
   constexpr int STAGES = S::STAGES;
-  constexpr int A_B = S::A_B, B_B = S::B_B;
+  constexpr int B_B = S::B_B;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -325,7 +332,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
     tma_prefetch_desc(&tm_g);
     tma_prefetch_desc(&tm_x);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);
+  if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -339,68 +346,77 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
         mbar_wait(empty(s), ph ^ 1);
         const uint32_t stage = base + s * S::STAGE_BYTES;
         const int r = (int)(r_begin + (int64_t)it * WG_ROWS);
-        mbar_arrive_expect_tx(full_tma(s), A_B + B_B);
-        // rows past r_end of this split but inside the tensor would be double counted: the split size
-        // is a multiple of WG_ROWS, so only the global tail is partial and TMA zero-fills it
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) tma_load_2d(stage + gq * WG_GROUP_BYTES, &tm_g, full_tma(s), n0 + gq * 32, r);
+        mbar_arrive_expect_tx(full_tma(s), WG_A_BYTES + B_B);
+        // the split size is a multiple of WG_ROWS, so only the global tail is partial; TMA zero-fills it
+        tma_load_2d(stage, &tm_g, full_tma(s), n0, r);
 #pragma unroll
         for (int gq = 0; gq < BLOCK_N / 32; ++gq)
-          tma_load_2d(stage + A_B + gq * WG_GROUP_BYTES, &tm_x, full_tma(s), k0 + gq * 32, r);
+          tma_load_2d(stage + WG_A_BYTES + gq * WG_GROUP_BYTES, &tm_x, full_tma(s), k0 + gq * 32, r);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 1, 1);
-      if (p.debug == 2) idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
-      if (p.debug == 3) idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 1, 0);
-      if (p.debug == 4) idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 1);
+      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 1);  // A from TMEM, B MN-major
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(full_tma(s), ph);
         mbar_wait(full_ab(s), ph);
         tc_fence_after();
-        const uint32_t a_hi0 = base + s * S::STAGE_BYTES, b_hi0 = a_hi0 + A_B;
-        const uint32_t a_lo0 = a_hi0 + A_B + B_B, b_lo0 = a_lo0 + A_B;
+        const uint32_t b_hi0 = base + s * S::STAGE_BYTES + WG_A_BYTES, b_lo0 = b_hi0 + B_B;
 #pragma unroll
         for (int k = 0; k < WG_ROWS / UMMA_K; ++k) {
           const uint32_t koff = k * 1024;  // 8 rows x 128 bytes
-          const uint64_t a_hi = make_smem_desc(a_hi0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
-          const uint64_t a_lo = make_smem_desc(a_lo0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
+          const uint32_t a_hi = tmem_d + BLOCK_N + s * 64 + k * UMMA_K, a_lo = a_hi + 32;
           const uint64_t b_hi = make_smem_desc(b_hi0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
           const uint64_t b_lo = make_smem_desc(b_lo0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
-          mma_tf32(tmem_d, a_lo, b_hi, idesc, (it | k) != 0);
-          mma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
-          mma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
+          mma_tf32_ts(tmem_d, a_lo, b_hi, idesc, (it | k) != 0);
+          mma_tf32_ts(tmem_d, a_hi, b_lo, idesc, 1);
+          mma_tf32_ts(tmem_d, a_hi, b_hi, idesc, 1);
         }
         mma_commit(empty(s));
       }
       mma_commit(tmem_full);
     }
   } else {
-    const int t = threadIdx.x - 64;
+    const int quarter = warp & 3;
+    const int t = quarter * 32 + lane;  // column n0 + t of g  <->  TMEM lane t
+    float bias_acc = 0.f;
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(full_tma(s), ph);
-      float4* hi = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES);
-      float4* lo = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES + A_B + B_B);
-      // the split is element-wise, hence independent of the swizzled placement
-#pragma unroll 4
-      for (int c = t; c < (A_B + B_B) / 16; c += 128) {
-        float4 v = hi[c];
-        if (p.relu_in && c >= A_B / 16) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      // A: column t of the [32 rows][128 n] tile -> TMEM lane t (hi | lo), plus the bias gradient
+      const float* gcol = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES) + t;
+      float hi[32], lo[32];
+#pragma unroll
+      for (int r = 0; r < WG_ROWS; ++r) {
+        const float v = gcol[r * BLOCK_M];
+        bias_acc += v;
+        split_tf32(v, hi[r], lo[r]);
+      }
+      const uint32_t a_dst = tmem_d + ((uint32_t)(quarter * 32) << 16) + BLOCK_N + s * 64;
+      tmem_st_32x32(a_dst, hi);
+      tmem_st_32x32(a_dst + 32, lo);
+      // B: element-wise split in place (independent of the swizzled placement)
+      float4* bhi = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES + WG_A_BYTES);
+      float4* blo = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES + WG_A_BYTES + B_B);
+#pragma unroll
+      for (int c = t; c < B_B / 16; c += 128) {
+        float4 v = bhi[c];
+        if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         float4 h, l;
         split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-        hi[c] = h;
-        lo[c] = l;
+        bhi[c] = h;
+        blo[c] = l;
       }
+      tmem_st_wait();
+      tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(full_ab(s));
     }
-    const int quarter = warp & 3;
-    const int n = n0 + quarter * 32 + lane;
+    const int n = n0 + t;
+    if (p.partial_bias && blockIdx.y == 0 && n < p.n_out) p.partial_bias[(int64_t)blockIdx.z * p.n_out + n] = bias_acc;
     float* dst = p.partial + ((int64_t)blockIdx.z * p.n_out + n) * p.k_in;
     if (n_iter > 0) {
       mbar_wait(tmem_full, 0);
@@ -412,10 +428,6 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
       if (n_iter > 0) {
         __syncwarp();
         tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-        if (p.debug == 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 1.f;
-        }
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -429,14 +441,20 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_d, BLOCK_N);
+  if (warp == 1) tmem_dealloc(tmem_d, S::TMEM_COLS);
 }
 
 // dst[n, k] (ld) = sum over splits of partial[s, n, k], fixed order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int n_out, int k_in,
-                                    float* __restrict__ dst, int64_t ld) {
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_bias,
+                                    int splits, int n_out, int k_in, float* __restrict__ dst, int64_t ld,
+                                    float* __restrict__ dst_bias) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
   const int64_t total4 = (int64_t)n_out * k_in / 4;
+  if (dst_bias && i < n_out) {
+    float b = 0.f;
+    for (int s = 0; s < splits; ++s) b += partial_bias[(int64_t)s * n_out + i];
+    dst_bias[i] = b;
+  }
   if (i >= total4) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < splits; ++s) {
@@ -593,8 +611,10 @@ extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const floa
 }
 
 // ---- weight / bias gradient -----------------------------------------------------------------------
+static inline int wgrad_bn(int k_in) { return k_in <= 32 ? 32 : (k_in <= 64 ? 64 : 128); }
+
 static int wgrad_splits(int64_t rows, int tiles) {
-  int64_t want = (2 * kSMs + tiles - 1) / tiles;              // ~2 CTAs per SM in flight
+  int64_t want = (4 * kSMs + tiles - 1) / tiles;              // ~2 waves of 2 CTAs per SM
   int64_t max_splits = (rows + WG_ROWS - 1) / WG_ROWS;
   if (want > max_splits) want = max_splits;
   if (want > 512) want = 512;
@@ -603,16 +623,16 @@ static int wgrad_splits(int64_t rows, int tiles) {
 
 extern "C" size_t t2h_linear_wgrad_workspace_bytes(int64_t rows, int n_out, int k_in) {
   if (rows <= 0 || n_out <= 0 || k_in <= 0) return 256;
-  const int bn = k_in <= 32 ? 32 : (k_in <= 64 ? 64 : (k_in <= 128 ? 128 : 256));
+  const int bn = wgrad_bn(k_in);
   const int tiles = ((n_out + BLOCK_M - 1) / BLOCK_M) * ((k_in + bn - 1) / bn);
-  return (size_t)wgrad_splits(rows, tiles) * n_out * k_in * sizeof(float) + 256;
+  return (size_t)wgrad_splits(rows, tiles) * n_out * (k_in + 1) * sizeof(float) + 256;
 }
 
 template <int BLOCK_N>
 static int launch_wgrad(const float* g, int64_t ld_g, const float* x, int64_t ld_x, WgradArgs a, int splits,
                         cudaStream_t stream) {
   CUtensorMap mg, mx;
-  if (!make_map(&mg, g, a.n_out, a.rows, ld_g, 32, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
+  if (!make_map(&mg, g, a.n_out, a.rows, ld_g, BLOCK_M, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
   if (!make_map(&mx, x, a.k_in, a.rows, ld_x, 32, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
   auto kern = wgrad_tf32x3_kernel<BLOCK_N>;
   static bool configured = false;
@@ -631,13 +651,13 @@ static int launch_wgrad(const float* g, int64_t ld_g, const float* x, int64_t ld
 
 extern "C" int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float* x, int64_t ld_x, int64_t rows,
                                 int n_out, int k_in, int relu_in, void* workspace, size_t workspace_bytes,
-                                float* grad_w, int64_t ld_w, t2h_stream_t stream) {
+                                float* grad_w, int64_t ld_w, float* grad_b, t2h_stream_t stream) {
   if (!grad_out || !x || !grad_w || !workspace || rows < 0 || n_out <= 0 || k_in <= 0) return T2H_ERR_INVALID_ARGUMENT;
   if ((n_out % 4) || (k_in % 4) || (ld_g % 4) || (ld_x % 4) || (ld_w % 4)) return T2H_ERR_UNSUPPORTED_SHAPE;
   if (((uintptr_t)grad_out | (uintptr_t)x | (uintptr_t)grad_w | (uintptr_t)workspace) & 15) return T2H_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < t2h_linear_wgrad_workspace_bytes(rows, n_out, k_in)) return T2H_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t s = (cudaStream_t)stream;
-  const int bn = k_in <= 32 ? 32 : (k_in <= 64 ? 64 : (k_in <= 128 ? 128 : 256));
+  const int bn = wgrad_bn(k_in);
   const int tiles = ((n_out + BLOCK_M - 1) / BLOCK_M) * ((k_in + bn - 1) / bn);
   const int splits = rows > 0 ? wgrad_splits(rows, tiles) : 1;
   WgradArgs a;
@@ -646,17 +666,18 @@ extern "C" int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float
   a.rows_per_split = ((per + WG_ROWS - 1) / WG_ROWS) * WG_ROWS;
   if (a.rows_per_split < WG_ROWS) a.rows_per_split = WG_ROWS;
   a.partial = (float*)workspace;
-  { const char* e = getenv("T2H_WGRAD_DEBUG"); a.debug = e ? atoi(e) : 0; }
+  a.partial_bias = grad_b ? a.partial + (size_t)splits * n_out * k_in : nullptr;
   int st = T2H_OK;
   if (rows > 0) {
     if (bn == 32) st = launch_wgrad<32>(grad_out, ld_g, x, ld_x, a, splits, s);
     else if (bn == 64) st = launch_wgrad<64>(grad_out, ld_g, x, ld_x, a, splits, s);
-    else if (bn == 128) st = launch_wgrad<128>(grad_out, ld_g, x, ld_x, a, splits, s);
-    else st = launch_wgrad<256>(grad_out, ld_g, x, ld_x, a, splits, s);
+    else st = launch_wgrad<128>(grad_out, ld_g, x, ld_x, a, splits, s);
     if (st) return st;
   }
   const int64_t total4 = (int64_t)n_out * k_in / 4;
-  wgrad_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(a.partial, rows > 0 ? splits : 0, n_out, k_in, grad_w, ld_w);
+  const int64_t threads = total4 > n_out ? total4 : n_out;
+  wgrad_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a.partial, a.partial_bias, rows > 0 ? splits : 0,
+                                                                       n_out, k_in, grad_w, ld_w, grad_b);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }

@@ -63,14 +63,14 @@ def _launch_fwd(x1, x2, w_hi, w_lo, n_out, bias, relu_in, mask, residual, out):
               ptr(residual), 0 if residual is None else residual.stride(0), ptr(out), out.stride(0))
 
 
-def _launch_wgrad(gy, x, relu_in, grad_w_view):
+def _launch_wgrad(gy, x, relu_in, grad_w_view, grad_b=None):
     rows, n_out = gy.shape
     k_in = x.shape[1]
     lib = _lib.load()
     ws_bytes = int(lib.t2h_linear_wgrad_workspace_bytes(rows, n_out, k_in))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gy.device)
     _lib.call("t2h_linear_wgrad", ptr(gy), gy.stride(0), ptr(x), x.stride(0), rows, n_out, k_in, int(relu_in), ptr(ws),
-              ws_bytes, ptr(grad_w_view), grad_w_view.stride(0))
+              ws_bytes, ptr(grad_w_view), grad_w_view.stride(0), ptr(grad_b))
 
 
 def colsum(g):
@@ -114,12 +114,15 @@ class _LinearTC(torch.autograd.Function):
             t_hi, t_lo = _cache.get(weight, k1, k_total, transposed=True)
             d_x2 = torch.empty_like(x2)
             _launch_fwd(gy, None, t_hi, t_lo, k_total - k1, None, False, x2 if ctx.relu_in else None, None, d_x2)
+        want_bias = ctx.has_bias and need[3]
         if need[2]:
             d_w = torch.empty(n_out, k_total, dtype=torch.float32, device=gy.device)
-            _launch_wgrad(gy, x1, ctx.relu_in, d_w[:, :k1])
+            if want_bias:  # the bias gradient (column sum of gy) rides along with the first wgrad launch
+                d_b = torch.empty(n_out, dtype=torch.float32, device=gy.device)
+            _launch_wgrad(gy, x1, ctx.relu_in, d_w[:, :k1], d_b)
             if x2 is not None:
                 _launch_wgrad(gy, x2, ctx.relu_in, d_w[:, k1:])
-        if ctx.has_bias and need[3]:
+        elif want_bias:
             d_b = colsum(gy)
         if need[4]:
             d_res = gy

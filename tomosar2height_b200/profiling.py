@@ -60,7 +60,7 @@ def _bytes(name, a):
     if name == "t2h_linear_fwd":  # x1, ld, k1, x2, ld, k2, rows, w_hi, w_lo, n_out, bias, relu, mask, ld, res, ld, out, ld
         k, rows, n = a[2] + a[5], a[6], a[9]
         return 4 * rows * (k + n + (n if a[12] else 0) + (n if a[14] else 0)) + 8 * k * n
-    if name == "t2h_linear_wgrad":  # g, ld, x, ld, rows, n_out, k_in, ...
+    if name == "t2h_linear_wgrad":  # g, ld, x, ld, rows, n_out, k_in, relu, ws, ws_bytes, gw, ld, gb
         rows, n, k = a[4], a[5], a[6]
         return 4 * rows * (n + k) + 4 * n * k
     if name == "t2h_colsum":
