@@ -117,3 +117,22 @@ def test_weight_split_cache_tracks_updates():
         w.mul_(2.0)  # optimizer-style in-place update bumps the version counter
     y1 = linear(x, w)
     assert (y1 - 2 * y0).abs().max().item() < 1e-5 * y0.abs().max().item()
+
+
+def test_linear_odd_widths_are_padded():
+    """1-wide output head (pixel.py:51) and a K that is not a multiple of 4 still run on the tensor cores."""
+    from tomosar2height_b200.linear import linear
+    from tomosar2height_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 50, 50, 30, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(1, 30, generator=g) / 5).cuda().requires_grad_(True)
+    b = torch.randn(1, generator=g).cuda().requires_grad_(True)
+    before = _lib.launch_count
+    y = linear(x, w, b, relu_in=True)
+    assert y.shape == (2, 50, 50, 1) and _lib.launch_count > before
+    y.square().sum().backward()
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yd = xd.relu() @ wd.t() + bd
+    yd.square().sum().backward()
+    for got, ref in ((y, yd), (x.grad, xd.grad), (w.grad, wd.grad), (b.grad, bd.grad)):
+        assert (got.double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()

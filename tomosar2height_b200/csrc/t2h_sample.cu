@@ -83,7 +83,7 @@ template <class RS, int WPS>
 __global__ void __launch_bounds__(kSampleWarps * kWarp)
 sample_bwd_kernel(const float* __restrict__ grad_rows, int reso, const float* __restrict__ xyz, int64_t stride,
                   const int32_t* __restrict__ perm, const int32_t* __restrict__ cell_start, int64_t n_seg, int shift,
-                  int morton, float* __restrict__ grad_plane) {
+                  int morton, int log2_cells, float* __restrict__ grad_plane) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
   constexpr int SEGS = kSampleWarps / WPS;
   __shared__ float4 part_sum[WPS > 1 ? kSampleWarps * (C / 4) : 1];
@@ -93,9 +93,17 @@ sample_bwd_kernel(const float* __restrict__ grad_rows, int reso, const float* __
   const int part = warp % WPS;
   const bool valid = seg < n_seg;
   const int64_t cells = (int64_t)reso * reso;
-  const int64_t b = valid ? seg / cells : 0;
+  // Morton levels have power-of-two cell counts: split tile / cell with shifts (no 64-bit division)
+  const int64_t b = !valid ? 0 : (morton ? (seg >> log2_cells) : seg / cells);
   int cx = 0, cy = 0;
   if (valid) cell_decode((uint32_t)(seg - b * cells), reso, morton, cx, cy);
+  // Morton bits of the three candidate columns / rows, computed once instead of per neighbour cell
+  uint32_t mx[3], my[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    mx[d] = part1by1((uint32_t)(cx + d - 1));
+    my[d] = part1by1((uint32_t)(cy + d - 1)) << 1;
+  }
 
   float4 acc[CH];
 #pragma unroll
@@ -108,7 +116,7 @@ sample_bwd_kernel(const float* __restrict__ grad_rows, int reso, const float* __
       for (int dx = -1; dx <= 1; ++dx) {
         const int nx = cx + dx;
         if (nx < 0 || nx >= reso) continue;
-        const int64_t key = b * cells + cell_code((uint32_t)nx, (uint32_t)ny, reso, morton);
+        const int64_t key = b * cells + (morton ? (mx[dx + 1] | my[dy + 1]) : (uint32_t)(nx + reso * ny));
         int beg = cell_start[key << shift], end = cell_start[(key + 1) << shift];
         if (WPS > 1) {
           const int slice = (end - beg + WPS - 1) / WPS;
@@ -290,8 +298,11 @@ extern "C" int t2h_bilinear_sample_bwd(const float* grad_rows, int64_t n_points,
   while (wps < kSampleWarps && avg >= 4 * wps) wps *= 2;
   const unsigned blocks = (unsigned)((n_seg * wps + kSampleWarps - 1) / kSampleWarps);
   cudaStream_t s = (cudaStream_t)stream;
+  int log2_cells = 0;
+  while ((1 << log2_cells) < reso) ++log2_cells;
+  log2_cells *= 2;
 #define T2H_SBWD(W) sample_bwd_kernel<RS, W><<<blocks, kSampleWarps * kWarp, 0, s>>>( \
-      grad_rows, reso, xyz_sorted, point_stride, perm, cell_start, n_seg, shift, morton, grad_plane)
+      grad_rows, reso, xyz_sorted, point_stride, perm, cell_start, n_seg, shift, morton, log2_cells, grad_plane)
   T2H_DISPATCH_ROWSHAPE(C, {
     if (wps == 1) T2H_SBWD(1); else if (wps == 2) T2H_SBWD(2); else if (wps == 4) T2H_SBWD(4); else T2H_SBWD(8);
   });

@@ -20,16 +20,16 @@ struct SegGeom {
   int shift;   // 2k for level r = R >> k
   int morton;
   int reso;    // resolution r of THIS level
+  int log2_cells;  // log2(r*r) when morton (r is a power of two): tile / cell split by shifts, no 64-bit division
 };
 
 // plane row (row-major (b, y, x)) of segment `seg` (key order of this level)
 __device__ __forceinline__ int64_t plane_row(const SegGeom& g, int64_t seg) {
   if (!g.morton) return seg;
-  const int64_t cells = (int64_t)g.reso * g.reso;
-  int64_t b = seg / cells;
-  int ix, iy;
-  cell_decode((uint32_t)(seg - b * cells), g.reso, 1, ix, iy);
-  return b * cells + (int64_t)iy * g.reso + ix;
+  const int64_t b = seg >> g.log2_cells;
+  const uint32_t code = (uint32_t)(seg - (b << g.log2_cells));
+  const int ix = (int)compact1by1(code), iy = (int)compact1by1(code >> 1);
+  return (b << g.log2_cells) + (int64_t)iy * g.reso + ix;
 }
 
 template <class RS>
@@ -173,38 +173,17 @@ seg_max_bwd_kernel(const float* __restrict__ grad_pooled, const float* __restric
   }
 }
 
-// WPS warps cooperate on one segment (coarse levels hold hundreds of points per cell): each warp
-// reduces a contiguous slice of the segment's rows, the slices are combined through shared memory
-// in slice order, so the summation order stays fixed.
-template <class RS, int WPS>
-__global__ void __launch_bounds__(kSegWarps * kWarp)
-seg_reduce_fwd_kernel(const float* __restrict__ rows, SegGeom g, int mean, float* __restrict__ plane) {
-  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  constexpr int SEGS = kSegWarps / WPS;  // segments per CTA
-  __shared__ float4 part_sum[WPS > 1 ? kSegWarps * (C / 4) : 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t seg = (int64_t)blockIdx.x * SEGS + warp / WPS;
-  const int part = warp % WPS;
-  const bool valid = seg < g.n_seg;
-  const int sub = lane / LPR, l = lane % LPR;
-  int beg = 0, end = 0;
-  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
-  const int len = end - beg;
-  int my_beg = beg, my_end = end;
-  if (WPS > 1) {
-    const int slice = (len + WPS - 1) / WPS;
-    my_beg = min(beg + part * slice, end);
-    my_end = min(my_beg + slice, end);
-  }
+constexpr int kHeavy = 64;  // rows; longer segments are processed by the whole CTA (skewed tiles)
 
-  float4 acc[CH];
-#pragma unroll
-  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int i = my_beg + sub;
-  // two rows in flight per lane
-  for (; i + RPI < my_end; i += 2 * RPI) {
-    const int64_t r0 = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
-    const int64_t r1 = g.perm ? (int64_t)g.perm[i + RPI] : (int64_t)(i + RPI);
+// acc += rows[beg + sub, beg + sub + RPI, ...) ; two rows in flight per lane
+template <class RS>
+__device__ __forceinline__ void accum_range(const float* __restrict__ rows, const int32_t* __restrict__ perm, int beg, int end,
+                                            int sub, int l, float4 (&acc)[RS::CH]) {
+  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
+  int i = beg + sub;
+  for (; i + RPI < end; i += 2 * RPI) {
+    const int64_t r0 = perm ? (int64_t)perm[i] : (int64_t)i;
+    const int64_t r1 = perm ? (int64_t)perm[i + RPI] : (int64_t)(i + RPI);
     float4 v0[CH], v1[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -217,45 +196,110 @@ seg_reduce_fwd_kernel(const float* __restrict__ rows, SegGeom g, int mean, float
       acc[c].x += v1[c].x; acc[c].y += v1[c].y; acc[c].z += v1[c].z; acc[c].w += v1[c].w;
     }
   }
-  for (; i < my_end; i += RPI) {
-    const int64_t r0 = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+  for (; i < end; i += RPI) {
+    const int64_t r0 = perm ? (int64_t)perm[i] : (int64_t)i;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       float4 v = ld4(rows + r0 * C + (c * LPR + l) * 4);
       acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
     }
   }
+}
+
+// sum the RPI sub-rows of a warp (fixed xor tree)
+template <class RS>
+__device__ __forceinline__ void warp_combine(float4 (&acc)[RS::CH]) {
 #pragma unroll
-  for (int off = LPR; off < kWarp; off <<= 1)
+  for (int off = RS::LPR; off < kWarp; off <<= 1)
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
+    for (int c = 0; c < RS::CH; ++c) {
       float4 o = shfl_xor4(acc[c], off);
       acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
     }
-  if (WPS > 1) {
-    if (sub == 0 && part > 0) {
+}
+
+// Segment sum / mean.  WPS warps cooperate on one segment (coarse levels hold hundreds of points per
+// cell): each warp reduces a contiguous slice of the segment's rows, the slices are combined through
+// shared memory in slice order, so the summation order stays fixed.  With WPS == 1 (fine levels) a
+// segment longer than kHeavy rows -- a facade in a clustered tile -- is deferred and reduced by all
+// eight warps of the CTA the same way.
+template <class RS, int WPS>
+__global__ void __launch_bounds__(kSegWarps * kWarp)
+seg_reduce_fwd_kernel(const float* __restrict__ rows, SegGeom g, int mean, float* __restrict__ plane) {
+  constexpr int LPR = RS::LPR, CH = RS::CH, C = RS::C;
+  constexpr int SEGS = kSegWarps / WPS;  // segments per CTA
+  __shared__ float4 part_sum[kSegWarps * (C / 4)];
+  __shared__ int hv_beg[kSegWarps], hv_len[kSegWarps];
+  __shared__ long long hv_row[kSegWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t seg = (int64_t)blockIdx.x * SEGS + warp / WPS;
+  const int part = warp % WPS;
+  const bool valid = seg < g.n_seg;
+  const int sub = lane / LPR, l = lane % LPR;
+  int beg = 0, end = 0;
+  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
+  const int len = end - beg;
+
+  auto finish = [&](float4 (&acc)[CH], int n_rows, int64_t prow) {
+    const float inv = mean ? __fdiv_rn(1.0f, (float)max(n_rows, 1)) : 1.0f;  // one division, <= 1 ulp from sum / count
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 v = acc[c];
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      st4(plane + prow * C + (c * LPR + l) * 4, v);
+    }
+  };
+  // slices of `n_parts` warps -> part 0, in slice order
+  auto combine_parts = [&](float4 (&acc)[CH], int first_warp, int n_parts, int my_part) {
+    if (sub == 0 && my_part > 0) {
 #pragma unroll
       for (int c = 0; c < CH; ++c) part_sum[warp * (C / 4) + c * LPR + l] = acc[c];
     }
     __syncthreads();
-    if (part == 0 && sub == 0) {
-      for (int q = 1; q < WPS; ++q)
+    if (my_part == 0 && sub == 0) {
+      for (int q = 1; q < n_parts; ++q)
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          const float4 o = part_sum[(warp + q) * (C / 4) + c * LPR + l];
+          const float4 o = part_sum[(first_warp + q) * (C / 4) + c * LPR + l];
           acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
         }
     }
-  }
-  if (valid && part == 0 && sub == 0) {
-    const float cnt = (float)max(len, 1);
-    const int64_t prow = plane_row(g, seg);
+  };
+
+  float4 acc[CH];
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      float4 v = acc[c];
-      if (mean) { v.x = __fdiv_rn(v.x, cnt); v.y = __fdiv_rn(v.y, cnt); v.z = __fdiv_rn(v.z, cnt); v.w = __fdiv_rn(v.w, cnt); }
-      st4(plane + prow * C + (c * LPR + l) * 4, v);
-    }
+  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // light segments: the WPS warps of the group; heavy ones (skewed tiles): deferred to the whole CTA
+  const int group = warp / WPS;
+  const bool heavy = WPS < kSegWarps && valid && len > kHeavy * WPS;
+  if (lane == 0 && part == 0) {
+    hv_len[group] = heavy ? len : 0;
+    hv_beg[group] = beg;
+    hv_row[group] = valid ? plane_row(g, seg) : 0;
+  }
+  if (valid && !heavy) {
+    const int slice = (len + WPS - 1) / WPS;
+    const int my_beg = min(beg + part * slice, end), my_end = min(my_beg + slice, end);
+    accum_range<RS>(rows, g.perm, my_beg, my_end, sub, l, acc);
+    warp_combine<RS>(acc);
+  }
+  if (WPS > 1) combine_parts(acc, warp - part, WPS, part);  // contains the CTA barrier
+  else __syncthreads();
+  if (valid && !heavy && part == 0 && sub == 0) finish(acc, len, plane_row(g, seg));
+  if (WPS == kSegWarps) return;
+  for (int w = 0; w < SEGS; ++w) {
+    const int hl = hv_len[w];
+    if (hl == 0) continue;  // uniform across the CTA
+    const int hb = hv_beg[w], slice = (hl + kSegWarps - 1) / kSegWarps;
+    const int my_beg = min(hb + warp * slice, hb + hl), my_end = min(my_beg + slice, hb + hl);
+    __syncthreads();        // part_sum is free again
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    accum_range<RS>(rows, g.perm, my_beg, my_end, sub, l, acc);
+    warp_combine<RS>(acc);
+    combine_parts(acc, 0, kSegWarps, warp);
+    if (warp == 0 && sub == 0) finish(acc, hl, hv_row[w]);
   }
 }
 
@@ -269,13 +313,13 @@ seg_broadcast_kernel(const float* __restrict__ plane, SegGeom g, int mean, float
   const int sub = lane / LPR, l = lane % LPR;
   const int beg = g.cell_start[seg << g.shift], end = g.cell_start[(seg + 1) << g.shift];
   if (beg >= end) return;
-  const float cnt = (float)(end - beg);
+  const float inv = mean ? __fdiv_rn(1.0f, (float)(end - beg)) : 1.0f;
   const int64_t prow = plane_row(g, seg);
   float4 v[CH];
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     v[c] = ld4(plane + prow * C + (c * LPR + l) * 4);
-    if (mean) { v[c].x = __fdiv_rn(v[c].x, cnt); v[c].y = __fdiv_rn(v[c].y, cnt); v[c].z = __fdiv_rn(v[c].z, cnt); v[c].w = __fdiv_rn(v[c].w, cnt); }
+    v[c].x *= inv; v[c].y *= inv; v[c].z *= inv; v[c].w *= inv;
   }
   for (int i = beg + sub; i < end; i += RPI) {
     const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
@@ -291,13 +335,19 @@ static int check_geom(const int32_t* cell_start, int64_t n_seg, int shift, int C
   return T2H_OK;
 }
 
+static inline int log2_cells_of(int reso) {
+  int l = 0;
+  while ((1 << l) < reso) ++l;
+  return 2 * l;
+}
+
 static inline unsigned seg_blocks(int64_t n_seg) { return (unsigned)((n_seg + kSegWarps - 1) / kSegWarps); }
 
 // warps per segment from the mean segment length: ~8+ rows per warp, at most the whole CTA
 static inline int warps_per_segment(int64_t n_rows, int64_t n_seg) {
   const int64_t avg = n_seg > 0 ? n_rows / n_seg : 0;
   int wps = 1;
-  while (wps < kSegWarps && avg >= 16 * wps) wps *= 2;
+  while (wps < kSegWarps && avg >= 8 * wps) wps *= 2;
   return wps;
 }
 
@@ -312,7 +362,7 @@ extern "C" int t2h_seg_max_fwd(const float* rows, const int32_t* perm, const int
   if (st) return st;
   if (!rows || !arg) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, tie_rank, cell_start, n_seg, shift, morton, reso};
+  SegGeom g{perm, tie_rank, cell_start, n_seg, shift, morton, reso, log2_cells_of(reso)};
   T2H_DISPATCH_ROWSHAPE(C, seg_max_fwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
                                rows, g, pooled, plane, arg));
   T2H_CHECK_LAUNCH();
@@ -326,7 +376,7 @@ extern "C" int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane
   if (st) return st;
   if (!arg || !grad_rows || (!grad_pooled && !grad_plane)) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso};
+  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso, log2_cells_of(reso)};
   T2H_DISPATCH_ROWSHAPE(C, seg_max_bwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
                                grad_pooled, grad_plane, g, arg, grad_rows));
   T2H_CHECK_LAUNCH();
@@ -340,7 +390,7 @@ extern "C" int t2h_seg_reduce_fwd(const float* rows, int64_t n_rows, const int32
   if (st) return st;
   if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso};
+  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso, log2_cells_of(reso)};
   const int wps = warps_per_segment(n_rows, n_seg);
   const unsigned blocks = (unsigned)((n_seg * wps + kSegWarps - 1) / kSegWarps);
   cudaStream_t s = (cudaStream_t)stream;
@@ -361,7 +411,7 @@ extern "C" int t2h_seg_broadcast(const float* plane, const int32_t* perm, const 
   if (st) return st;
   if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso};
+  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso, log2_cells_of(reso)};
   T2H_DISPATCH_ROWSHAPE(C, seg_broadcast_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
                                plane, g, mean, rows));
   T2H_CHECK_LAUNCH();

@@ -48,7 +48,7 @@ class LocalPoolPointnet(nn.Module):
         """inputs (B, N, 3) fp32 CUDA, xy in the open unit square -> {'xy': (B, C, R, R)}."""
         topo = Topology(inputs, self.reso_plane)
         level = topo.level(self.reso_plane)
-        # xyz rows are zero-padded to 4 floats (16-byte rows for TMA); pad fc_pos.weight to match
+        # xyz rows are stored zero-padded to 4 floats (16-byte rows for TMA); pad fc_pos.weight to match
         pad = topo.xyz_sorted.shape[1] - self.fc_pos.weight.shape[1]
         net = linear(topo.xyz_sorted, F.pad(self.fc_pos.weight, (0, pad)), self.fc_pos.bias)
         net = self.blocks[0](net)

@@ -129,24 +129,38 @@ class _LinearTC(torch.autograd.Function):
         return d_x1, d_x2, d_w, d_b, d_res, None
 
 
-def tc_eligible(x, weight, x2=None):
-    k1 = x.shape[-1]
-    return (x.is_cuda and x.dtype == torch.float32 and weight.shape[0] % 4 == 0 and k1 % 4 == 0
-            and (x2 is None or (k1 % 32 == 0 and x2.shape[-1] % 4 == 0)))
+def _pad_to(v, m):
+    return (m - v % m) % m
 
 
 def linear(x, weight, bias=None, x2=None, relu_in=False, residual=None):
-    """relu?([x | x2]) @ weight.T + bias + residual over the last dimension (any leading shape)."""
-    if not x.is_cuda:
-        raise RuntimeError("linear: expected a CUDA tensor (the B200 path has no CPU fallback)")
-    lead = x.shape[:-1]
-    if USE_LIBRARY_GEMM or not tc_eligible(x, weight, x2):
-        # odd widths (e.g. a 1-wide output head): plain library GEMM
+    """relu?([x | x2]) @ weight.T + bias + residual over the last dimension (any leading shape).
+
+    Widths that TMA cannot address directly (rows must be multiples of 16 bytes) are zero-padded to a
+    multiple of 4 -- e.g. the 1-wide ``fc_out`` head of the FC decoder (pixel.py:51) -- and the result
+    is sliced back; padding is differentiable, so gradients reach the original parameters.
+    """
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError("linear: expected a float32 CUDA tensor (the B200 path has no CPU fallback)")
+    if USE_LIBRARY_GEMM:  # ablation only (T2H_LINEAR=cublas)
         xin = x if x2 is None else torch.cat([x, x2], dim=-1)
         y = F.linear(F.relu(xin) if relu_in else xin, weight, bias)
         return y if residual is None else y + residual
+    n_out, k1 = weight.shape[0], x.shape[-1]
+    if x2 is not None and (k1 % 32 or x2.shape[-1] % 4):
+        x, x2, k1 = torch.cat([x, x2], dim=-1), None, k1 + x2.shape[-1]  # second source must start on a 32-wide chunk
+    pk, pn = _pad_to(k1, 4) if x2 is None else 0, _pad_to(n_out, 4)
+    if pk:
+        x = F.pad(x, (0, pk))
+        weight = F.pad(weight, (0, pk))
+    if pn:
+        weight = F.pad(weight, (0, 0, 0, pn))
+        bias = None if bias is None else F.pad(bias, (0, pn))
+        residual = None if residual is None else F.pad(residual, (0, pn))
+    lead = x.shape[:-1]
     x2d = x.reshape(-1, x.shape[-1])
     x22d = None if x2 is None else x2.reshape(-1, x2.shape[-1])
     res2d = None if residual is None else residual.reshape(-1, weight.shape[0])
     y = _LinearTC.apply(x2d, x22d, weight, bias, res2d, bool(relu_in))
-    return y.view(*lead, weight.shape[0])
+    y = y.view(*lead, weight.shape[0])
+    return y[..., :n_out] if pn else y
