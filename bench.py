@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--points", type=int, default=262144, help="points per tile")
     ap.add_argument("--micro-batch", type=int, default=4, help="tiles per forward/backward")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="skip cuDNN autotuning (use under ncu)")
+    ap.add_argument("--no-graph", action="store_true", help="issue every micro-batch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--conv-tf32", action="store_true", help="let the retained cuDNN convs use TF32 (reference GPU default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-points", type=int, default=262144, help="points of the CPU-baseline tile")
@@ -182,15 +183,26 @@ def run_b200(args):
     cloud_h, dsm_h = cloud_h.pin_memory(), dsm_h.pin_memory()
     cloud_d, dsm_d = cloud_h.to(dev), dsm_h.to(dev)
 
-    def train_step(cloud, dsm):
+    def micro_loss(m, cloud, dsm):
+        pa, _ = m(input_cloud=cloud)
+        # per-tile mean L1, summed over tiles: the reference accumulates un-normalised tile grads (trainer.py:63-79)
+        return (pa.squeeze(-1) - dsm).abs().mean(dim=(1, 2)).sum()
+
+    graphed = None
+    if not args.no_graph:
+        from tomosar2height_b200.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(model, micro_loss, cloud_d[:mb], dsm_d[:mb])
+
+    def train_step(cloud, dsm, eager=False):
         flat.zero_()
         total = torch.zeros((), device=dev)
         for i in range(0, T, mb):
-            pa, _ = model(input_cloud=cloud[i:i + mb])
-            # per-tile mean L1, summed over tiles: the reference accumulates un-normalised tile grads
-            loss = (pa.squeeze(-1) - dsm[i:i + mb]).abs().mean(dim=(1, 2)).sum()
-            loss.backward()
-            total += loss.detach()
+            if graphed is not None and not eager:
+                total += graphed(cloud[i:i + mb], dsm[i:i + mb])
+            else:
+                loss = micro_loss(model, cloud[i:i + mb], dsm[i:i + mb])
+                loss.backward()
+                total += loss.detach()
         flat.all_reduce()
         opt.step()
         return total
@@ -209,19 +221,25 @@ def run_b200(args):
     clocks.start()
     calls0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with KernelTimer(n_rows=mb * N) as kt:
-        barrier()
-        torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed steps
-        ev0.record()
-        for _ in range(args.steps):
-            train_step(cloud_d, dsm_d)
-        ev1.record()
-        barrier()
-        torch.cuda.profiler.stop()
+    barrier()
+    torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed steps
+    ev0.record()
+    for _ in range(args.steps):
+        train_step(cloud_d, dsm_d)
+    ev1.record()
+    barrier()
+    torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
     clock_info = clocks.stop()
-    launches = _lib.launch_count - calls0
+    # per-kernel device times (roofline): the same step issued eagerly with CUDA events around every
+    # C-ABI call -- a graph replay has no host-visible launch boundaries; kernel durations are the same
+    calls0 = _lib.launch_count
+    with KernelTimer(n_rows=mb * N) as kt:
+        train_step(cloud_d, dsm_d, eager=True)
+        barrier()
+    launches = (_lib.launch_count - calls0) * args.steps  # C-ABI calls replayed per timed step x steps
     kernels = kt.summary()
+    kernel_ms_per_step = sum(v["ms_total"] for v in kernels.values())
 
     # ---- timed region 2: end to end from pinned host buffers --------------------------------
     barrier()
@@ -262,7 +280,7 @@ def run_b200(args):
                 roofline = {"bound": "hbm", "kernel": top, "achieved": k["gbs"], "peak": hbm_peak, "unit": "GB/s",
                             "frac": k["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src}
             roofline.update({"launches": k["launches"], "ms_avg": k["ms_avg"], "bytes_per_launch": k["bytes_per_launch"],
-                             "share_of_step": k["ms_total"] / ms})
+                             "share_of_step": k["ms_total"] / (ms / args.steps)})
         line = {
             "metric": "fwd+bwd points/s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -270,7 +288,8 @@ def run_b200(args):
             "ndsm_px_per_s": world * T * 512 * 512 * args.steps / (ms / 1e3),
             "config": {"workload": "cloud-only training step (fwd+L1+bwd+AdamW), Berlin-shaped tiles, R=256, ALTO depth 5, conv decoder",
                        "tiles_per_step_per_gpu": T, "points_per_tile": N, "micro_batch_tiles": mb, "parallelism": f"dp{world}",
-                       "conv_tf32": bool(args.conv_tf32), "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)"},
+                       "conv_tf32": bool(args.conv_tf32), "cuda_graph": graphed is not None,
+                       "hand_written_kernel_ms_per_step": kernel_ms_per_step, "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)"},
             "e2e": {"value": pts / (ms_e2e / 1e3), "unit": "points/s", "h2d_bytes_per_step": cloud_h.numel() * 4 + dsm_h.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "loss": last},
             "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,

@@ -139,6 +139,20 @@ size_t t2h_linear_wgrad_workspace_bytes(int64_t rows, int n_out, int k_in);
 int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float* x, int64_t ld_x, int64_t rows,
                      int n_out, int k_in, int relu_in, void* workspace, size_t workspace_bytes,
                      float* grad_w, int64_t ld_w, float* grad_b, t2h_stream_t stream);
+/* ---- f3: 3x3 / padding 1 convolutions of the plane CNN (alto.py:59-61,98-99,177-182,226-227,
+ *      pixel.py:20-22) as implicit GEMM on the same tcgen05 3xTF32 pipeline.  Planes are channels-last
+ *      (B, H, W, C); the weight is passed as the matrix [cout, 9*cin] with k = (3*ky + kx)*cin + ci
+ *      (= the conv weight in torch.channels_last memory order), pre-split like a linear weight.
+ *      out = conv3x3(act(x)) + bias  (zeroed where mask <= 0)  (+ residual); the input gradient is the
+ *      same call with the spatially flipped, transposed weight.  Needs cin % 32 == 0, W % 16 == 0,
+ *      H % 8 == 0 (forward) / H % 2 == 0 (weight gradient). */
+int t2h_conv3x3_fwd(const float* x, int B, int H, int W, int cin, const float* w_hi, const float* w_lo,
+                    int cout, const float* bias, int relu_in, const float* mask, const float* residual,
+                    float* out, t2h_stream_t stream);
+size_t t2h_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int cin, int cout);
+int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, int H, int W, int cin, int cout,
+                      int relu_in, void* workspace, size_t workspace_bytes, float* grad_w, float* grad_b,
+                      t2h_stream_t stream);
 /* bias gradient: out[c] = sum_r g[r, c], two-stage and deterministic */
 size_t t2h_colsum_workspace_bytes(int64_t rows, int n);
 int t2h_colsum(const float* g, int64_t ld_g, int64_t rows, int n, void* workspace,

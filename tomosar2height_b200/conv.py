@@ -1,0 +1,123 @@
+"""Plane convolutions on the tcgen05 3xTF32 pipeline.
+
+The reference's plane CNN (alto.py:59-61,74,98-114,157-182,215-236,354,380) and ConvDecoder
+(pixel.py:17-32) are ``nn.Conv2d`` / ``nn.ConvTranspose2d`` modules on cuDNN.  With strict fp32 they run
+on SIMT kernels (~25 TFLOP/s on B200) and became the largest term of the step once the point path was
+on tensor cores, so the three shapes they use are mapped onto the GEMM kernels of ``t2h_linear.cu``:
+
+* 3x3 / padding 1  -> implicit GEMM, K chunk = (tap, 32-channel slice) fetched by 4-D TMA from the
+                      tap-shifted pixel patch (zero fill outside the plane = the padding)
+* 1x1              -> a linear layer over the pixels of the channels-last plane
+* transposed 2x2 / stride 2 -> a linear layer to 4*Cout followed by a pixel shuffle
+
+Parameters stay the modules' own fp32 ``weight`` / ``bias`` (checkpoints unchanged).  Tensors are the
+logical (B, C, H, W) views with channels_last strides used everywhere in the model.  Shapes the
+kernels do not cover (Cin or Cout not a multiple of 32, planes narrower than 16) fall back to cuDNN.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import ptr
+from .linear import _cache, linear, USE_LIBRARY_GEMM
+
+
+def _fwd_matrix(w):      # (Cout, Cin, 3, 3) -> [Cout, (ky, kx, ci)]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def _dgrad_matrix(w):    # -> [Cin, (ky', kx', co)] with the taps mirrored
+    return w.flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1)
+
+
+def _launch_conv(x, w_hi, w_lo, cout, bias, relu_in, mask, out):
+    B, H, W, cin = x.shape
+    _lib.call("t2h_conv3x3_fwd", ptr(x), B, H, W, cin, ptr(w_hi), ptr(w_lo), cout, ptr(bias), int(relu_in), ptr(mask),
+              None, ptr(out))
+
+
+class _Conv3x3TC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu_in):
+        """x: channels-last (B, H, W, Cin) contiguous; returns (B, H, W, Cout)."""
+        B, H, W, cin = x.shape
+        cout = weight.shape[0]
+        w_hi, w_lo = _cache.get_matrix(weight, "conv3x3_fwd", _fwd_matrix)
+        out = torch.empty(B, H, W, cout, dtype=torch.float32, device=x.device)
+        _launch_conv(x, w_hi, w_lo, cout, bias, relu_in, None, out)
+        ctx.save_for_backward(x, weight)
+        ctx.relu_in = relu_in
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        B, H, W, cin = x.shape
+        cout = weight.shape[0]
+        d_x = d_w = d_b = None
+        if ctx.needs_input_grad[0]:
+            t_hi, t_lo = _cache.get_matrix(weight, "conv3x3_dgrad", _dgrad_matrix)
+            d_x = torch.empty_like(x)
+            _launch_conv(g, t_hi, t_lo, cin, None, False, x if ctx.relu_in else None, d_x)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            lib = _lib.load()
+            ws_bytes = int(lib.t2h_conv3x3_wgrad_workspace_bytes(B, H, W, cin, cout))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+            d_wm = torch.empty(cout, 9 * cin, dtype=torch.float32, device=g.device)
+            if ctx.has_bias:
+                d_b = torch.empty(cout, dtype=torch.float32, device=g.device)
+            _lib.call("t2h_conv3x3_wgrad", ptr(g), ptr(x), B, H, W, cin, cout, int(ctx.relu_in), ptr(ws), ws_bytes,
+                      ptr(d_wm), ptr(d_b))
+            d_w = d_wm.view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+        return d_x, d_w, d_b, None
+
+
+def _tc_ok_3x3(x, weight):
+    B, C, H, W = x.shape
+    return (not USE_LIBRARY_GEMM and x.is_cuda and x.dtype == torch.float32 and weight.shape[2:] == (3, 3)
+            and C % 32 == 0 and weight.shape[0] % 32 == 0 and W % 16 == 0 and H % 8 == 0)
+
+
+def conv3x3(x, weight, bias=None, relu_in=False):
+    """F.conv2d(relu?(x), weight, bias, padding=1) on logical (B, C, H, W) tensors."""
+    if not _tc_ok_3x3(x, weight):
+        return F.conv2d(F.relu(x) if relu_in else x, weight, bias, padding=1)
+    y = _Conv3x3TC.apply(x.permute(0, 2, 3, 1).contiguous(), weight, bias, bool(relu_in))
+    return y.permute(0, 3, 1, 2)
+
+
+def conv1x1(x, weight, bias=None, relu_in=False):
+    """F.conv2d(relu?(x), weight, bias) for 1x1 kernels = a linear layer over the pixels."""
+    if USE_LIBRARY_GEMM or not x.is_cuda:
+        return F.conv2d(F.relu(x) if relu_in else x, weight, bias)
+    y = linear(x.permute(0, 2, 3, 1), weight.reshape(weight.shape[0], weight.shape[1]), bias, relu_in=relu_in)
+    return y.permute(0, 3, 1, 2)
+
+
+def conv_transpose2x2(x, weight, bias=None):
+    """F.conv_transpose2d(x, weight, bias, stride=2) for 2x2 kernels: out[2y+dy, 2x+dx] = x[y, x] @ W[:, :, dy, dx]."""
+    if USE_LIBRARY_GEMM or not x.is_cuda:
+        return F.conv_transpose2d(x, weight, bias, stride=2)
+    B, cin, H, W = x.shape
+    cout = weight.shape[1]
+    wm = weight.permute(2, 3, 1, 0).reshape(4 * cout, cin)           # rows ordered (dy, dx, co)
+    bm = None if bias is None else bias.repeat(4)
+    y = linear(x.permute(0, 2, 3, 1), wm, bm)                          # (B, H, W, 4*cout)
+    y = y.view(B, H, W, 2, 2, cout).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, cout)
+    return y.permute(0, 3, 1, 2)
+
+
+def apply_conv(module, x, relu_in=False):
+    """Run an ``nn.Conv2d`` / ``nn.ConvTranspose2d`` module of the plane CNN through the kernels above
+    (its parameters are used as they are); anything else is called as a module."""
+    if isinstance(module, torch.nn.Conv2d) and module.groups == 1 and module.stride == (1, 1) and module.dilation == (1, 1):
+        if module.kernel_size == (3, 3) and module.padding == (1, 1) and module.padding_mode == 'zeros':
+            return conv3x3(x, module.weight, module.bias, relu_in=relu_in)
+        if module.kernel_size == (1, 1) and module.padding == (0, 0):
+            return conv1x1(x, module.weight, module.bias, relu_in=relu_in)
+    if (isinstance(module, torch.nn.ConvTranspose2d) and module.kernel_size == (2, 2) and module.stride == (2, 2)
+            and module.padding == (0, 0) and module.output_padding == (0, 0) and module.groups == 1 and not relu_in):
+        return conv_transpose2x2(x, module.weight, module.bias)
+    return module(F.relu(x) if relu_in else x)

@@ -42,7 +42,15 @@ struct LinearArgs {
   float* out;              // [rows, ld_out]
   int64_t ld_out;
   int aux_kind;            // which of mask (1) / residual (2) is staged through shared memory by TMA (0: none)
+  // 3x3 convolution as implicit GEMM over channels-last planes (B, H, W, C): a 128-row tile is a
+  // CONV_TH x CONV_TW pixel patch, K chunk kc = (tap, 32-channel slice), loaded by 4-D TMA from the
+  // tap-shifted coordinates (zero fill outside the plane = padding 1)
+  int conv;                // 0: plain rows, 1: 3x3 convolution
+  int tiles_x;             // patches per plane row  (W / CONV_TW)
+  int tiles_per_img;       // patches per plane      ((H / CONV_TH) * tiles_x)
+  int cin_chunks;          // Cin / 32
 };
+constexpr int CONV_TW = 16, CONV_TH = 8;  // 16 x 8 pixels = 128 GEMM rows
 
 // A_TMEM: the split x operand is written to tensor memory (tcgen05.st) and consumed from there, so the
 // three MMAs of a k-step only read the WEIGHT tiles from shared memory.  In SS mode the 128x256 tile is
@@ -84,8 +92,16 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
   // 1-D grid, N-tile fastest: the CTAs that share an x tile are co-scheduled, so the tile is fetched
   // from DRAM once and re-read from L2 (an M-fastest raster re-read x from DRAM once per N-tile)
   const int n_tiles = (p.n_out + BLOCK_N - 1) / BLOCK_N;
-  const int m0 = (int)(blockIdx.x / n_tiles) * BLOCK_M;
+  const int m_idx = (int)(blockIdx.x / n_tiles);
+  const int m0 = m_idx * BLOCK_M;
   const int n0 = (int)(blockIdx.x % n_tiles) * BLOCK_N;
+  int img = 0, px0 = 0, py0 = 0;  // conv mode: image and top-left pixel of this patch
+  if (p.conv) {
+    img = m_idx / p.tiles_per_img;
+    const int rem = m_idx - img * p.tiles_per_img;
+    py0 = (rem / p.tiles_x) * CONV_TH;
+    px0 = (rem % p.tiles_x) * CONV_TW;
+  }
   constexpr uint32_t A_TMEM_COL0 = (BLOCK_N < 32 ? 32 : BLOCK_N);  // A stages follow the accumulator columns
 
   if (threadIdx.x == 0) {
@@ -116,7 +132,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
         mbar_wait(empty(s), ph ^ 1);
         const uint32_t stage = base + s * S::STAGE_BYTES;
         mbar_arrive_expect_tx(full_tma(s), A_BYTES + 2 * S::W_BYTES);
-        if (kc < p.k1_chunks) tma_load_2d(stage, &tm_x1, full_tma(s), kc * BLOCK_K, m0);
+        if (p.conv) {
+          const int tap = kc / p.cin_chunks, cc = kc - tap * p.cin_chunks;
+          tma_load_4d(stage, &tm_x1, full_tma(s), cc * BLOCK_K, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
+        } else if (kc < p.k1_chunks) tma_load_2d(stage, &tm_x1, full_tma(s), kc * BLOCK_K, m0);
         else                  tma_load_2d(stage, &tm_x2, full_tma(s), (kc - p.k1_chunks) * BLOCK_K, m0);
         tma_load_2d(stage + W_OFF, &tm_whi, full_tma(s), kc * BLOCK_K, n0);
         tma_load_2d(stage + W_OFF + S::W_BYTES, &tm_wlo, full_tma(s), kc * BLOCK_K, n0);
@@ -213,7 +232,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
       if (t == 0) {
         mbar_arrive_expect_tx(aux_bar, (uint32_t)n_blocks * A_BYTES);
         const CUtensorMap* aux = &tm_aux;
-        for (int cb = 0; cb < n_blocks; ++cb) tma_load_2d(base + cb * A_BYTES, aux, aux_bar, n0 + cb * 32, m0);
+        for (int cb = 0; cb < n_blocks; ++cb) {
+          if (p.conv) tma_load_4d(base + cb * A_BYTES, aux, aux_bar, n0 + cb * 32, px0, py0, img);
+          else tma_load_2d(base + cb * A_BYTES, aux, aux_bar, n0 + cb * 32, m0);
+        }
       }
       mbar_wait(aux_bar, 0);
     }
@@ -252,7 +274,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
     fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
     if (t == 0) {
-      for (int cb = 0; cb < n_blocks; ++cb) tma_store_2d(&tm_out, base + cb * A_BYTES, n0 + cb * 32, m0);
+      for (int cb = 0; cb < n_blocks; ++cb) {
+        if (p.conv) tma_store_4d(&tm_out, base + cb * A_BYTES, n0 + cb * 32, px0, py0, img);
+        else tma_store_2d(&tm_out, base + cb * A_BYTES, n0 + cb * 32, m0);
+      }
       tma_store_commit_and_wait();
     }
   }
@@ -285,6 +310,12 @@ struct WgradArgs {
   int64_t rows_per_split;  // multiple of WG_ROWS
   float* partial;       // [splits, n_out, k_in]
   float* partial_bias;  // [splits, n_out] or nullptr
+  // 3x3 convolution: "rows" are pixels taken 32 at a time as 2 x 16 patches of a channels-last plane,
+  // the x operand of k-group (tap, channel slice) is the tap-shifted patch (4-D TMA, zero fill = padding)
+  int conv;
+  int tiles_x;        // W / 16
+  int units_per_img;  // (H / 2) * tiles_x
+  int cin;
 };
 
 template <int BLOCK_N>
@@ -347,11 +378,24 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
         const uint32_t stage = base + s * S::STAGE_BYTES;
         const int r = (int)(r_begin + (int64_t)it * WG_ROWS);
         mbar_arrive_expect_tx(full_tma(s), WG_A_BYTES + B_B);
-        // the split size is a multiple of WG_ROWS, so only the global tail is partial; TMA zero-fills it
-        tma_load_2d(stage, &tm_g, full_tma(s), n0, r);
+        if (p.conv) {
+          const int u = r >> 5, img = u / p.units_per_img, rem = u - img * p.units_per_img;
+          const int y0 = (rem / p.tiles_x) * 2, x0 = (rem % p.tiles_x) * 16;
+          tma_load_4d(stage, &tm_g, full_tma(s), n0, x0, y0, img);
 #pragma unroll
-        for (int gq = 0; gq < BLOCK_N / 32; ++gq)
-          tma_load_2d(stage + WG_A_BYTES + gq * WG_GROUP_BYTES, &tm_x, full_tma(s), k0 + gq * 32, r);
+          for (int gq = 0; gq < BLOCK_N / 32; ++gq) {
+            const int k = k0 + gq * 32;
+            int tap = k / p.cin, ci0 = k - tap * p.cin;
+            if (tap >= 9) { tap = 4; ci0 = p.cin; }  // beyond the 9 taps: out-of-range channel -> zero fill
+            tma_load_4d(stage + WG_A_BYTES + gq * WG_GROUP_BYTES, &tm_x, full_tma(s), ci0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+          }
+        } else {
+          // the split size is a multiple of WG_ROWS, so only the global tail is partial; TMA zero-fills it
+          tma_load_2d(stage, &tm_g, full_tma(s), n0, r);
+#pragma unroll
+          for (int gq = 0; gq < BLOCK_N / 32; ++gq)
+            tma_load_2d(stage + WG_A_BYTES + gq * WG_GROUP_BYTES, &tm_x, full_tma(s), k0 + gq * 32, r);
+        }
       }
     }
   } else if (warp == 1) {
@@ -531,16 +575,39 @@ static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// channels-last plane (B, H, W, C) as a 4-D tensor (C, W, H, B); box = 32 channels x bw x bh pixels of one image
+static bool make_map_4d(CUtensorMap* map, const float* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B,
+                        uint32_t box_c, uint32_t bw, uint32_t bh, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * sizeof(float), W * C * sizeof(float), H * W * C * sizeof(float)};
+  cuuint32_t box[4] = {box_c, bw, bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct PlaneGeom { int B, H, W; };  // conv mode only
+
 template <int BLOCK_N, bool A_TMEM>
 static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const float* w_hi, const float* w_lo, int k_total,
-                         const LinearArgs& args, cudaStream_t stream) {
+                         const LinearArgs& args, cudaStream_t stream, const PlaneGeom* pg = nullptr) {
   CUtensorMap whi, wlo, mout, maux;
   if (!make_map(&whi, w_hi, k_total, args.n_out, k_total, BLOCK_K, BLOCK_N)) return T2H_ERR_CUDA;
   if (!make_map(&wlo, w_lo, k_total, args.n_out, k_total, BLOCK_K, BLOCK_N)) return T2H_ERR_CUDA;
-  if (!make_map(&mout, args.out, args.n_out, args.rows, args.ld_out, 32, BLOCK_M)) return T2H_ERR_CUDA;
-  maux = mout;
-  if (args.aux_kind == 1 && !make_map(&maux, args.mask, args.n_out, args.rows, args.ld_mask, 32, BLOCK_M)) return T2H_ERR_CUDA;
-  if (args.aux_kind == 2 && !make_map(&maux, args.residual, args.n_out, args.rows, args.ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
+  if (pg) {
+    if (!make_map_4d(&mout, args.out, args.n_out, pg->W, pg->H, pg->B, 32, CONV_TW, CONV_TH)) return T2H_ERR_CUDA;
+    maux = mout;
+    if (args.aux_kind == 1 && !make_map_4d(&maux, args.mask, args.n_out, pg->W, pg->H, pg->B, 32, CONV_TW, CONV_TH)) return T2H_ERR_CUDA;
+    if (args.aux_kind == 2 && !make_map_4d(&maux, args.residual, args.n_out, pg->W, pg->H, pg->B, 32, CONV_TW, CONV_TH)) return T2H_ERR_CUDA;
+  } else {
+    if (!make_map(&mout, args.out, args.n_out, args.rows, args.ld_out, 32, BLOCK_M)) return T2H_ERR_CUDA;
+    maux = mout;
+    if (args.aux_kind == 1 && !make_map(&maux, args.mask, args.n_out, args.rows, args.ld_mask, 32, BLOCK_M)) return T2H_ERR_CUDA;
+    if (args.aux_kind == 2 && !make_map(&maux, args.residual, args.n_out, args.rows, args.ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
+  }
   auto kern = linear_tf32x3_kernel<BLOCK_N, A_TMEM>;
   static bool configured = false;  // idempotent attribute, racing threads set the same value
   if (!configured) {
@@ -596,6 +663,7 @@ extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const floa
   a.relu_in = relu_in; a.bias = bias; a.mask = mask; a.ld_mask = ld_mask;
   a.residual = residual; a.ld_res = ld_res; a.out = out; a.ld_out = ld_out;
   a.aux_kind = mask ? 1 : (residual ? 2 : 0);
+  a.conv = 0; a.tiles_x = a.tiles_per_img = a.cin_chunks = 0;
   const int k_total = k1 + k2;
   cudaStream_t s = (cudaStream_t)stream;
   static const int ss_only = []() { const char* e = getenv("T2H_LINEAR_SS"); return e ? atoi(e) : 0; }();  // ablation
@@ -608,6 +676,35 @@ extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const floa
   static const int wide = []() { const char* e = getenv("T2H_LINEAR_BN256"); return e ? atoi(e) : 0; }();  // ablation
   if (n_out <= 128 || !wide) return launch_linear<128, true>(m1, m2, w_hi, w_lo, k_total, a, s);
   return launch_linear<256, true>(m1, m2, w_hi, w_lo, k_total, a, s);
+}
+
+
+extern "C" int t2h_conv3x3_fwd(const float* x, int B, int H, int W, int cin, const float* w_hi, const float* w_lo,
+                               int cout, const float* bias, int relu_in, const float* mask, const float* residual,
+                               float* out, t2h_stream_t stream) {
+  if (!x || !w_hi || !w_lo || !out || B < 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) return T2H_ERR_INVALID_ARGUMENT;
+  if ((cin % BLOCK_K) || (cout % 4) || (W % CONV_TW) || (H % CONV_TH)) return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)x | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)out | (uintptr_t)bias | (uintptr_t)mask |
+       (uintptr_t)residual) & 15)
+    return T2H_ERR_INVALID_ARGUMENT;
+  if (B == 0) return T2H_OK;
+  CUtensorMap mx;
+  if (!make_map_4d(&mx, x, cin, W, H, B, BLOCK_K, CONV_TW, CONV_TH)) return T2H_ERR_CUDA;
+  LinearArgs a;
+  a.rows = (int64_t)B * H * W; a.n_out = cout;
+  a.cin_chunks = cin / BLOCK_K;
+  a.k_chunks = a.k1_chunks = 9 * a.cin_chunks;
+  a.relu_in = relu_in; a.bias = bias; a.mask = mask; a.ld_mask = cout; a.residual = residual; a.ld_res = cout;
+  a.out = out; a.ld_out = cout;
+  a.aux_kind = mask ? 1 : (residual ? 2 : 0);
+  if (mask && residual) return T2H_ERR_UNSUPPORTED_SHAPE;  // only one epilogue operand is staged in conv mode
+  a.conv = 1; a.tiles_x = W / CONV_TW; a.tiles_per_img = (H / CONV_TH) * a.tiles_x;
+  PlaneGeom pg{B, H, W};
+  cudaStream_t s = (cudaStream_t)stream;
+  const int k_total = 9 * cin;
+  if (cout <= 32) return launch_linear<32, false>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
+  if (cout <= 64) return launch_linear<64, false>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
+  return launch_linear<128, true>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
 }
 
 // ---- weight / bias gradient -----------------------------------------------------------------------
@@ -629,11 +726,7 @@ extern "C" size_t t2h_linear_wgrad_workspace_bytes(int64_t rows, int n_out, int 
 }
 
 template <int BLOCK_N>
-static int launch_wgrad(const float* g, int64_t ld_g, const float* x, int64_t ld_x, WgradArgs a, int splits,
-                        cudaStream_t stream) {
-  CUtensorMap mg, mx;
-  if (!make_map(&mg, g, a.n_out, a.rows, ld_g, BLOCK_M, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
-  if (!make_map(&mx, x, a.k_in, a.rows, ld_x, 32, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
+static int launch_wgrad(const CUtensorMap& mg, const CUtensorMap& mx, WgradArgs a, int splits, cudaStream_t stream) {
   auto kern = wgrad_tf32x3_kernel<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
@@ -667,17 +760,65 @@ extern "C" int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float
   if (a.rows_per_split < WG_ROWS) a.rows_per_split = WG_ROWS;
   a.partial = (float*)workspace;
   a.partial_bias = grad_b ? a.partial + (size_t)splits * n_out * k_in : nullptr;
+  a.conv = 0; a.tiles_x = a.units_per_img = a.cin = 0;
   int st = T2H_OK;
   if (rows > 0) {
-    if (bn == 32) st = launch_wgrad<32>(grad_out, ld_g, x, ld_x, a, splits, s);
-    else if (bn == 64) st = launch_wgrad<64>(grad_out, ld_g, x, ld_x, a, splits, s);
-    else st = launch_wgrad<128>(grad_out, ld_g, x, ld_x, a, splits, s);
+    CUtensorMap mg, mx;
+    if (!make_map(&mg, grad_out, n_out, rows, ld_g, BLOCK_M, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
+    if (!make_map(&mx, x, k_in, rows, ld_x, 32, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
+    if (bn == 32) st = launch_wgrad<32>(mg, mx, a, splits, s);
+    else if (bn == 64) st = launch_wgrad<64>(mg, mx, a, splits, s);
+    else st = launch_wgrad<128>(mg, mx, a, splits, s);
     if (st) return st;
   }
   const int64_t total4 = (int64_t)n_out * k_in / 4;
   const int64_t threads = total4 > n_out ? total4 : n_out;
   wgrad_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a.partial, a.partial_bias, rows > 0 ? splits : 0,
                                                                        n_out, k_in, grad_w, ld_w, grad_b);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+
+extern "C" size_t t2h_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int cin, int cout) {
+  return t2h_linear_wgrad_workspace_bytes((int64_t)B * H * W, cout, 9 * cin);
+}
+
+extern "C" int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, int H, int W, int cin, int cout,
+                                 int relu_in, void* workspace, size_t workspace_bytes, float* grad_w, float* grad_b,
+                                 t2h_stream_t stream) {
+  if (!grad_out || !x || !grad_w || !workspace || B < 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) return T2H_ERR_INVALID_ARGUMENT;
+  if ((cin % 32) || (cout % 4) || (W % 16) || (H % 2)) return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)grad_out | (uintptr_t)x | (uintptr_t)grad_w | (uintptr_t)workspace) & 15) return T2H_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < t2h_conv3x3_wgrad_workspace_bytes(B, H, W, cin, cout)) return T2H_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t rows = (int64_t)B * H * W;
+  const int k_in = 9 * cin;
+  const int bn = wgrad_bn(k_in);
+  const int tiles = ((cout + BLOCK_M - 1) / BLOCK_M) * ((k_in + bn - 1) / bn);
+  const int splits = rows > 0 ? wgrad_splits(rows, tiles) : 1;
+  WgradArgs a;
+  a.rows = rows; a.n_out = cout; a.k_in = k_in; a.relu_in = relu_in;
+  int64_t per = (rows + splits - 1) / splits;
+  a.rows_per_split = ((per + WG_ROWS - 1) / WG_ROWS) * WG_ROWS;
+  if (a.rows_per_split < WG_ROWS) a.rows_per_split = WG_ROWS;
+  a.partial = (float*)workspace;
+  a.partial_bias = grad_b ? a.partial + (size_t)splits * cout * k_in : nullptr;
+  a.conv = 1; a.tiles_x = W / 16; a.units_per_img = (H / 2) * a.tiles_x; a.cin = cin;
+  if (rows > 0) {
+    CUtensorMap mg, mx;
+    if (!make_map_4d(&mg, grad_out, cout, W, H, B, BLOCK_M, 16, 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
+    if (!make_map_4d(&mx, x, cin, W, H, B, 32, 16, 2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
+    int st;
+    if (bn == 32) st = launch_wgrad<32>(mg, mx, a, splits, s);
+    else if (bn == 64) st = launch_wgrad<64>(mg, mx, a, splits, s);
+    else st = launch_wgrad<128>(mg, mx, a, splits, s);
+    if (st) return st;
+  }
+  const int64_t total4 = (int64_t)cout * k_in / 4;
+  const int64_t threads = total4 > cout ? total4 : cout;
+  wgrad_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a.partial, a.partial_bias, rows > 0 ? splits : 0,
+                                                                       cout, k_in, grad_w, k_in, grad_b);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }

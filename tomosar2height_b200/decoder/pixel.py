@@ -1,7 +1,7 @@
 """PixelwiseDecoder (reference: tomosar2height/decoder/pixel.py:8-125).
 
 The plane is bilinearly up-sampled to the output raster (t2h_upsample_bilinear_*, channels-last,
-align_corners=True), the image plane is added, and a conv head (cuDNN, untouched) or an FC head of
+align_corners=True), the image plane is added, and a conv head (implicit GEMM, conv.py) or an FC head of
 ResnetBlockFC blocks produces heights (+ optional footprint logits).
 """
 import torch
@@ -9,6 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import functional as T
+from ..conv import apply_conv
 from ..block import ResnetBlockFC
 from ..linear import linear
 
@@ -23,10 +24,10 @@ class ConvDecoder(nn.Module):
         self.act = F.leaky_relu if leaky else F.relu
 
     def forward(self, x):
-        x1 = self.act(self.conv1(x))
-        x2 = self.act(self.conv2(x1))
-        x3 = self.act(self.conv3(x2))
-        return self.conv4(torch.cat([x, x1, x2, x3], dim=1))
+        x1 = self.act(apply_conv(self.conv1, x))
+        x2 = self.act(apply_conv(self.conv2, x1))
+        x3 = self.act(apply_conv(self.conv3, x2))
+        return apply_conv(self.conv4, torch.cat([x, x1, x2, x3], dim=1))
 
 
 class FCDecoder(nn.Module):

@@ -1,7 +1,7 @@
 """ALTO U-Net: plane CNN alternating with point <-> plane exchanges
 (reference: tomosar2height/encoder/alto.py:48-382).
 
-Per level: 2x conv3x3+ReLU on the plane (cuDNN, untouched) -> residual 1x1 from the previous
+Per level: 2x conv3x3+ReLU on the plane (implicit GEMM on the tcgen05 pipeline, conv.py) -> residual 1x1 from the previous
 level -> bilinear SAMPLE of the plane at the points (t2h_bilinear_sample_*) -> per-point
 ``fc_comm`` (C -> 2C -> C) + ``fc_c(c_last)`` -> cell-wise MEAN back onto the plane
 (t2h_seg_reduce_*), which REPLACES the conv output.
@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import functional as T
+from ..conv import apply_conv
 from ..linear import linear
 from ..topology import Topology
 from .unet import conv3x3, conv1x1, upconv2x2, check_modes, xavier_normal_convs
@@ -63,12 +64,13 @@ class DownConv(nn.Module, _Exchange):
             self.conv1x1 = conv1x1(in_channels, out_channels)
 
     def forward(self, p, x, x_after_conv=None, c_last=None):
-        plane = F.relu(self.conv2(F.relu(self.conv1(x['xy']))))
+        # conv3x3 -> ReLU -> conv3x3 -> ReLU; the first ReLU is applied on load by the second conv
+        plane = F.relu(apply_conv(self.conv2, apply_conv(self.conv1, x['xy']), relu_in=True))
         if x_after_conv is not None:
             side = x_after_conv['xy']
             if 2 <= self.downsample < self.depth:  # alto.py:108-110: levels >= 2 see a pooled residual
                 side = self.pool(side)
-            plane = plane + self.conv1x1(side)
+            plane = plane + apply_conv(self.conv1x1, side)
         x_after_conv = {'xy': plane}
         scattered, c = self.exchange(p, plane, c_last)
         before_pool = {'xy': scattered}
@@ -95,11 +97,11 @@ class UpConv(nn.Module, _Exchange):
 
     def forward(self, p, from_down, from_up, x_after_conv, c_last, i):
         last = i == self.depth - 2
-        up = self.upconv_noup(from_up['xy']) if last else self.upconv(from_up['xy'])
+        up = apply_conv(self.upconv_noup, from_up['xy']) if last else apply_conv(self.upconv, from_up['xy'])
         merged = torch.cat((up, from_down['xy']), 1) if self.merge_mode == 'concat' else up + from_down['xy']
-        plane = F.relu(self.conv2(F.relu(self.conv1(merged))))
+        plane = F.relu(apply_conv(self.conv2, apply_conv(self.conv1, merged), relu_in=True))
         if x_after_conv is not None:
-            plane = plane + self.conv1x1(x_after_conv['xy'])
+            plane = plane + apply_conv(self.conv1x1, x_after_conv['xy'])
         x_after_conv = {'xy': plane}
         if last:  # alto.py:241-242: the last block has no point exchange
             return {'xy': plane}, x_after_conv, c_last
@@ -141,4 +143,4 @@ class UNet(nn.Module):
             skips.append(before_pool)
         for i, up in enumerate(self.up_convs):
             x, x_after_conv, c = up(p, skips[-(i + 2)], x, x_after_conv, c, i)
-        return self.conv_final(x['xy'])
+        return apply_conv(self.conv_final, x['xy'])

@@ -29,7 +29,7 @@ class _SplitCache:
     def get(self, weight, c0=0, c1=None, transposed=False):
         c1 = weight.shape[1] if c1 is None else c1
         key = (id(weight), c0, c1, transposed)
-        hit = self._store.get(key)
+        hit = None if capture_mode else self._store.get(key)
         if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
             return hit[3], hit[4]
         with torch.no_grad():
@@ -37,6 +37,25 @@ class _SplitCache:
             w = w.t().contiguous() if transposed else w.contiguous()
             hi, lo = torch.empty_like(w), torch.empty_like(w)
             _lib.call("t2h_split_tf32", ptr(w), w.numel(), ptr(hi), ptr(lo))
+        if capture_mode:
+            return hi, lo  # lives in the graph's private pool; not a cache entry
+        if len(self._store) > 4096:
+            self._store.clear()
+        self._store[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), hi, lo)
+        return hi, lo
+
+    def get_matrix(self, weight, tag, builder):
+        """(hi, lo) split of ``builder(weight.detach())`` (a 2-D fp32 matrix), cached per parameter version."""
+        key = (id(weight), tag)
+        hit = None if capture_mode else self._store.get(key)
+        if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+            return hit[3], hit[4]
+        with torch.no_grad():
+            w = builder(weight.detach()).contiguous()
+            hi, lo = torch.empty_like(w), torch.empty_like(w)
+            _lib.call("t2h_split_tf32", ptr(w), w.numel(), ptr(hi), ptr(lo))
+        if capture_mode:
+            return hi, lo
         if len(self._store) > 4096:
             self._store.clear()
         self._store[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), hi, lo)
@@ -44,6 +63,9 @@ class _SplitCache:
 
 
 _cache = _SplitCache()
+# True while a CUDA graph is being captured (graph.py): splits are recomputed inside the graph, because the
+# weights change between replays
+capture_mode = False
 # ablation switch for benchmarks / debugging only: run the point MLPs as plain cuBLAS fp32 GEMMs
 USE_LIBRARY_GEMM = os.environ.get("T2H_LINEAR", "") == "cublas"
 
