@@ -55,11 +55,14 @@ constexpr int CONV_TW = 16, CONV_TH = 8;  // 16 x 8 pixels = 128 GEMM rows
 // A_TMEM: the split x operand is written to tensor memory (tcgen05.st) and consumed from there, so the
 // three MMAs of a k-step only read the WEIGHT tiles from shared memory.  In SS mode the 128x256 tile is
 // shared-memory-bandwidth bound (each MMA re-reads 4 KB of A and 8 KB of B per 134 cycles).
-template <int BLOCK_N, bool A_TMEM>
+// STAGES_: pipeline depth.  Narrow layers have only 1-2 K chunks; with a single stage a CTA needs 40-48 KB
+// of shared memory and 4-5 CTAs share an SM, which hides the serial load -> split -> MMA -> store chain
+// of one CTA behind the others (these layers are HBM-bound).
+template <int BLOCK_N, bool A_TMEM, int STAGES_>
 struct Smem {
   static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = (A_TMEM ? 1 : 2) * A_BYTES + 2 * W_BYTES;
-  static constexpr int STAGES = A_TMEM ? 2 : ((BLOCK_N == 128) ? 3 : 2);  // A_TMEM/128: 96 KB + 256 TMEM cols -> 2 CTAs per SM
+  static constexpr int STAGES = STAGES_;  // A_TMEM/128 with 2 stages: 96 KB + 256 TMEM cols -> 2 CTAs per SM
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
   // TMEM columns: accumulator + (hi, lo) x 32 columns per stage when A lives in TMEM
@@ -68,13 +71,13 @@ struct Smem {
   static constexpr int W_OFF = (A_TMEM ? 1 : 2) * A_BYTES;
 };
 
-template <int BLOCK_N, bool A_TMEM>
+template <int BLOCK_N, bool A_TMEM, int STAGES_>
 __global__ void __launch_bounds__(kThreads)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                      const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
                      const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_aux,
                      const LinearArgs p) {
-  using S = Smem<BLOCK_N, A_TMEM>;
+  using S = Smem<BLOCK_N, A_TMEM, STAGES_>;
   constexpr int STAGES = S::STAGES;
   constexpr int W_OFF = S::W_OFF;
   extern __shared__ uint8_t smem_raw[];
@@ -316,13 +319,14 @@ struct WgradArgs {
   int tiles_x;        // W / 16
   int units_per_img;  // (H / 2) * tiles_x
   int cin;
+  int a_cols;         // columns of g actually loaded per tile: min(128, n_out rounded up to 32)
 };
 
 template <int BLOCK_N>
 struct WgSmem {
   static constexpr int B_B = (BLOCK_N / 32) * WG_GROUP_BYTES;
   static constexpr int STAGE_BYTES = WG_A_BYTES + 2 * B_B;       // g raw | x hi | x lo
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = BLOCK_N <= 64 ? 3 : 2;           // narrow tiles: 24-32 KB stages, deeper prefetch
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
   static constexpr int TMEM_USED = BLOCK_N + STAGES * 64;        // accumulator + (g hi, g lo) per stage
   static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
@@ -377,7 +381,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
         mbar_wait(empty(s), ph ^ 1);
         const uint32_t stage = base + s * S::STAGE_BYTES;
         const int r = (int)(r_begin + (int64_t)it * WG_ROWS);
-        mbar_arrive_expect_tx(full_tma(s), WG_A_BYTES + B_B);
+        mbar_arrive_expect_tx(full_tma(s), (uint32_t)(WG_ROWS * p.a_cols * 4) + B_B);
         if (p.conv) {
           const int u = r >> 5, img = u / p.units_per_img, rem = u - img * p.units_per_img;
           const int y0 = (rem / p.tiles_x) * 2, x0 = (rem % p.tiles_x) * 16;
@@ -425,23 +429,36 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
   } else {
     const int quarter = warp & 3;
     const int t = quarter * 32 + lane;  // column n0 + t of g  <->  TMEM lane t
+    const bool a_live = quarter * 32 < p.a_cols;  // warp-uniform: this quarter holds real columns of g
     float bias_acc = 0.f;
+    if (!a_live) {  // lanes beyond the loaded columns: zero operand rows, written once for every stage
+      float z[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) z[r] = 0.f;
+      for (int s = 0; s < STAGES; ++s) {
+        tmem_st_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + BLOCK_N + s * 64, z);
+        tmem_st_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + BLOCK_N + s * 64 + 32, z);
+      }
+      tmem_st_wait();
+    }
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(full_tma(s), ph);
-      // A: column t of the [32 rows][128 n] tile -> TMEM lane t (hi | lo), plus the bias gradient
-      const float* gcol = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES) + t;
-      float hi[32], lo[32];
+      if (a_live) {
+        // A: column t of the [32 rows][a_cols] tile -> TMEM lane t (hi | lo), plus the bias gradient
+        const float* gcol = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES) + t;
+        float hi[32], lo[32];
 #pragma unroll
-      for (int r = 0; r < WG_ROWS; ++r) {
-        const float v = gcol[r * BLOCK_M];
-        bias_acc += v;
-        split_tf32(v, hi[r], lo[r]);
+        for (int r = 0; r < WG_ROWS; ++r) {
+          const float v = gcol[r * p.a_cols];
+          bias_acc += v;
+          split_tf32(v, hi[r], lo[r]);
+        }
+        const uint32_t a_dst = tmem_d + ((uint32_t)(quarter * 32) << 16) + BLOCK_N + s * 64;
+        tmem_st_32x32(a_dst, hi);
+        tmem_st_32x32(a_dst + 32, lo);
       }
-      const uint32_t a_dst = tmem_d + ((uint32_t)(quarter * 32) << 16) + BLOCK_N + s * 64;
-      tmem_st_32x32(a_dst, hi);
-      tmem_st_32x32(a_dst + 32, lo);
       // B: element-wise split in place (independent of the swizzled placement)
       float4* bhi = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES + WG_A_BYTES);
       float4* blo = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES + WG_A_BYTES + B_B);
@@ -591,7 +608,7 @@ static bool make_map_4d(CUtensorMap* map, const float* ptr, uint64_t C, uint64_t
 
 struct PlaneGeom { int B, H, W; };  // conv mode only
 
-template <int BLOCK_N, bool A_TMEM>
+template <int BLOCK_N, bool A_TMEM, int STAGES_>
 static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const float* w_hi, const float* w_lo, int k_total,
                          const LinearArgs& args, cudaStream_t stream, const PlaneGeom* pg = nullptr) {
   CUtensorMap whi, wlo, mout, maux;
@@ -608,10 +625,10 @@ static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const flo
     if (args.aux_kind == 1 && !make_map(&maux, args.mask, args.n_out, args.rows, args.ld_mask, 32, BLOCK_M)) return T2H_ERR_CUDA;
     if (args.aux_kind == 2 && !make_map(&maux, args.residual, args.n_out, args.rows, args.ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
   }
-  auto kern = linear_tf32x3_kernel<BLOCK_N, A_TMEM>;
+  auto kern = linear_tf32x3_kernel<BLOCK_N, A_TMEM, STAGES_>;
   static bool configured = false;  // idempotent attribute, racing threads set the same value
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BLOCK_N, A_TMEM>::TOTAL) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BLOCK_N, A_TMEM, STAGES_>::TOTAL) != cudaSuccess) {
       (void)cudaGetLastError();
       return T2H_ERR_CUDA;
     }
@@ -619,7 +636,7 @@ static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const flo
   }
   const int64_t tiles = ((args.rows + BLOCK_M - 1) / BLOCK_M) * ((args.n_out + BLOCK_N - 1) / BLOCK_N);
   if (tiles > 0x7fffffffLL) return T2H_ERR_UNSUPPORTED_SHAPE;
-  kern<<<(unsigned)tiles, kThreads, Smem<BLOCK_N, A_TMEM>::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args);
+  kern<<<(unsigned)tiles, kThreads, Smem<BLOCK_N, A_TMEM, STAGES_>::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
@@ -667,15 +684,14 @@ extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const floa
   const int k_total = k1 + k2;
   cudaStream_t s = (cudaStream_t)stream;
   static const int ss_only = []() { const char* e = getenv("T2H_LINEAR_SS"); return e ? atoi(e) : 0; }();  // ablation
-  if (n_out <= 32) return launch_linear<32, false>(m1, m2, w_hi, w_lo, k_total, a, s);
-  if (n_out <= 64) return launch_linear<64, false>(m1, m2, w_hi, w_lo, k_total, a, s);
-  if (ss_only) {
-    if (n_out <= 128) return launch_linear<128, false>(m1, m2, w_hi, w_lo, k_total, a, s);
-    return launch_linear<256, false>(m1, m2, w_hi, w_lo, k_total, a, s);
-  }
-  static const int wide = []() { const char* e = getenv("T2H_LINEAR_BN256"); return e ? atoi(e) : 0; }();  // ablation
-  if (n_out <= 128 || !wide) return launch_linear<128, true>(m1, m2, w_hi, w_lo, k_total, a, s);
-  return launch_linear<256, true>(m1, m2, w_hi, w_lo, k_total, a, s);
+  static const int deep = []() { const char* e = getenv("T2H_LINEAR_DEEP"); return e ? atoi(e) : 0; }();  // ablation
+  const bool shallow = a.k_chunks <= 2 && !deep;
+  if (n_out <= 32) return shallow ? launch_linear<32, false, 1>(m1, m2, w_hi, w_lo, k_total, a, s)
+                                  : launch_linear<32, false, 2>(m1, m2, w_hi, w_lo, k_total, a, s);
+  if (n_out <= 64) return shallow ? launch_linear<64, false, 1>(m1, m2, w_hi, w_lo, k_total, a, s)
+                                  : launch_linear<64, false, 2>(m1, m2, w_hi, w_lo, k_total, a, s);
+  if (ss_only) return launch_linear<128, false, 3>(m1, m2, w_hi, w_lo, k_total, a, s);
+  return launch_linear<128, true, 2>(m1, m2, w_hi, w_lo, k_total, a, s);
 }
 
 
@@ -702,9 +718,9 @@ extern "C" int t2h_conv3x3_fwd(const float* x, int B, int H, int W, int cin, con
   PlaneGeom pg{B, H, W};
   cudaStream_t s = (cudaStream_t)stream;
   const int k_total = 9 * cin;
-  if (cout <= 32) return launch_linear<32, false>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
-  if (cout <= 64) return launch_linear<64, false>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
-  return launch_linear<128, true>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
+  if (cout <= 32) return launch_linear<32, false, 2>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
+  if (cout <= 64) return launch_linear<64, false, 2>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
+  return launch_linear<128, true, 2>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
 }
 
 // ---- weight / bias gradient -----------------------------------------------------------------------
@@ -761,10 +777,11 @@ extern "C" int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float
   a.partial = (float*)workspace;
   a.partial_bias = grad_b ? a.partial + (size_t)splits * n_out * k_in : nullptr;
   a.conv = 0; a.tiles_x = a.units_per_img = a.cin = 0;
+  a.a_cols = n_out >= BLOCK_M ? BLOCK_M : ((n_out + 31) / 32) * 32;
   int st = T2H_OK;
   if (rows > 0) {
     CUtensorMap mg, mx;
-    if (!make_map(&mg, grad_out, n_out, rows, ld_g, BLOCK_M, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
+    if (!make_map(&mg, grad_out, n_out, rows, ld_g, a.a_cols, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
     if (!make_map(&mx, x, k_in, rows, ld_x, 32, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
     if (bn == 32) st = launch_wgrad<32>(mg, mx, a, splits, s);
     else if (bn == 64) st = launch_wgrad<64>(mg, mx, a, splits, s);
@@ -805,9 +822,10 @@ extern "C" int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, i
   a.partial = (float*)workspace;
   a.partial_bias = grad_b ? a.partial + (size_t)splits * cout * k_in : nullptr;
   a.conv = 1; a.tiles_x = W / 16; a.units_per_img = (H / 2) * a.tiles_x; a.cin = cin;
+  a.a_cols = cout >= BLOCK_M ? BLOCK_M : ((cout + 31) / 32) * 32;
   if (rows > 0) {
     CUtensorMap mg, mx;
-    if (!make_map_4d(&mg, grad_out, cout, W, H, B, BLOCK_M, 16, 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
+    if (!make_map_4d(&mg, grad_out, cout, W, H, B, a.a_cols, 16, 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
     if (!make_map_4d(&mx, x, cin, W, H, B, 32, 16, 2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
     int st;
     if (bn == 32) st = launch_wgrad<32>(mg, mx, a, splits, s);

@@ -65,6 +65,12 @@ def _bytes(name, a):
         return 4 * rows * (n + k) + 4 * n * k
     if name == "t2h_colsum":
         return 4 * a[2] * a[3]
+    if name == "t2h_conv3x3_fwd":
+        px = a[1] * a[2] * a[3]
+        return 4 * px * (a[4] + a[7] + (a[7] if a[10] else 0) + (a[7] if a[11] else 0)) + 8 * 9 * a[4] * a[7]
+    if name == "t2h_conv3x3_wgrad":
+        px = a[2] * a[3] * a[4]
+        return 4 * px * (a[5] + a[6]) + 4 * 9 * a[5] * a[6]
     return 0
 
 
@@ -74,6 +80,10 @@ def _flops(name, a):
         return 2 * a[6] * (a[2] + a[5]) * a[9]
     if name == "t2h_linear_wgrad":
         return 2 * a[4] * a[5] * a[6]
+    if name == "t2h_conv3x3_fwd":   # x, B, H, W, cin, w_hi, w_lo, cout, ...
+        return 2 * a[1] * a[2] * a[3] * 9 * a[4] * a[7]
+    if name == "t2h_conv3x3_wgrad":  # g, x, B, H, W, cin, cout, ...
+        return 2 * a[2] * a[3] * a[4] * 9 * a[5] * a[6]
     return 0
 
 
@@ -86,6 +96,7 @@ class KernelTimer:
     def __init__(self, n_rows):
         self.n_rows = n_rows
         self.records = {}
+        self.shapes = {}
         self._orig = None
 
     def __enter__(self):
@@ -100,6 +111,8 @@ class KernelTimer:
             timer._orig(name, *args)
             stop.record()
             timer.records.setdefault(name, []).append((start, stop, _bytes(name, args), _flops(name, args)))
+            if name in ("t2h_linear_fwd", "t2h_linear_wgrad", "t2h_conv3x3_fwd", "t2h_conv3x3_wgrad"):
+                timer.shapes.setdefault((name, _shape(name, args)), []).append((start, stop, _flops(name, args)))
 
         _lib.call = timed_call
         for mod in _patch_targets():
@@ -128,6 +141,29 @@ class KernelTimer:
                 "tflops": (flops / 1e12) / (ms / 1e3) if ms > 0 else 0.0,
             }
         return out
+
+
+def _shape(name, a):
+    if name == "t2h_linear_fwd":
+        return (a[6], a[2] + a[5], a[9])            # rows, K, N
+    if name == "t2h_linear_wgrad":
+        return (a[4], a[6], a[5])                   # rows, K, N
+    if name == "t2h_conv3x3_fwd":
+        return (a[1] * a[2] * a[3], 9 * a[4], a[7])  # pixels, 9*cin, cout
+    if name == "t2h_conv3x3_wgrad":
+        return (a[2] * a[3] * a[4], 9 * a[5], a[6])
+    return ()
+
+
+def shape_table(timer):
+    """[(name, (rows, K, N), launches, ms_total, TFLOP/s)] sorted by time."""
+    torch.cuda.synchronize()
+    out = []
+    for (name, shp), recs in timer.shapes.items():
+        ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+        fl = sum(r[2] for r in recs)
+        out.append((name, shp, len(recs), ms, fl / 1e9 / ms if ms > 0 else 0.0))
+    return sorted(out, key=lambda r: -r[3])
 
 
 def _patch_targets():
