@@ -67,9 +67,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
                ::"l"((uint64_t)map), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// commit the stores and wait until shared memory has been READ (the CTA may then exit / reuse the buffer;
+// the global writes themselves complete asynchronously, before the grid is reported finished)
 __device__ __forceinline__ void tma_store_commit_and_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
