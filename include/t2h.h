@@ -105,11 +105,16 @@ int t2h_seg_broadcast(const float* plane, const int32_t* perm, const int32_t* ce
 int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, const float* xyz_sorted,
                             int64_t point_stride, const int32_t* perm, int64_t n_points,
                             int64_t n_per_batch, float* out_rows, t2h_stream_t stream);
-/* grad_plane (B, r, r, C): atomic-free gather over the 3x3 neighbour cells of every plane cell */
+/* grad_plane (B, r, r, C), atomic-free and deterministic.  With Morton keys and C in {32..1024} (and a
+ * workspace): shared-memory-staged scatter, one CTA per 8x8 block of cells with a one-cell halo, single
+ * writer per accumulator, block tiles merged in a fixed order.  Otherwise (workspace NULL, row-major keys,
+ * odd C): gather over the 3x3 neighbour cells of every plane cell. */
+size_t t2h_bilinear_sample_bwd_workspace_bytes(int reso, int C, int64_t n_seg, int morton);
 int t2h_bilinear_sample_bwd(const float* grad_rows, int64_t n_points, int reso, int C,
                             const float* xyz_sorted, int64_t point_stride, const int32_t* perm,
                             const int32_t* cell_start, int64_t n_seg, int shift, int morton,
-                            float* grad_plane, t2h_stream_t stream);
+                            void* workspace, size_t workspace_bytes, float* grad_plane,
+                            t2h_stream_t stream);
 
 /* ---- a5: pixel.py:105-111 F.interpolate(bilinear, align_corners=True) ----------------------- */
 int t2h_upsample_bilinear_fwd(const float* in, int B, int h, int w, int C, int out_h, int out_w,

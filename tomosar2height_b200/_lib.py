@@ -36,7 +36,8 @@ SIGNATURES = {
     "t2h_seg_reduce_fwd": [_p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_seg_broadcast": [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_bilinear_sample_fwd": [_p, _i32, _i32, _p, _i64, _p, _i64, _i64, _p, _p],
-    "t2h_bilinear_sample_bwd": [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _p],
+    "t2h_bilinear_sample_bwd_workspace_bytes": [_i32, _i32, _i64, _i32],
+    "t2h_bilinear_sample_bwd": [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _sz, _p, _p],
     "t2h_upsample_bilinear_fwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_upsample_bilinear_bwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_split_tf32": [_p, _i64, _p, _p, _p],
@@ -51,7 +52,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"t2h_status_string": ctypes.c_char_p, "t2h_sort_workspace_bytes": _sz,
             "t2h_linear_wgrad_workspace_bytes": _sz, "t2h_colsum_workspace_bytes": _sz,
-            "t2h_conv3x3_wgrad_workspace_bytes": _sz}
+            "t2h_conv3x3_wgrad_workspace_bytes": _sz, "t2h_bilinear_sample_bwd_workspace_bytes": _sz}
 
 _lib = None
 _lock = threading.Lock()
@@ -81,7 +82,8 @@ def build_library(verbose: bool = False) -> str:
         out, _ = proc.communicate()
         if proc.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
-    if procs or not os.path.exists(LIB_PATH):
+    stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objects)
+    if procs or stale:
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objects]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if res.returncode != 0:

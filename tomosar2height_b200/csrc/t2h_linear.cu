@@ -505,25 +505,51 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_d, S::TMEM_COLS);
 }
 
-// dst[n, k] (ld) = sum over splits of partial[s, n, k], fixed order
+// dst[n, k] (ld) = sum over splits of partial[s, n, k]; TPO threads share one float4 of the output
+// (narrow layers have few outputs but hundreds of row splits), fixed strided order + xor tree
+template <int TPO>
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_bias,
                                     int splits, int n_out, int k_in, float* __restrict__ dst, int64_t ld,
                                     float* __restrict__ dst_bias) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = gid / TPO;  // float4 index
+  const int part = (int)(gid % TPO);
   const int64_t total4 = (int64_t)n_out * k_in / 4;
-  if (dst_bias && i < n_out) {
-    float b = 0.f;
-    for (int s = 0; s < splits; ++s) b += partial_bias[(int64_t)s * n_out + i];
-    dst_bias[i] = b;
-  }
-  if (i >= total4) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < splits; ++s) {
-    const float4 v = ld4(partial + ((int64_t)s * n_out * k_in) + i * 4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  float b = 0.f;
+  const bool has_w = i < total4, has_b = dst_bias && i < n_out;
+  for (int s = part; s < splits; s += TPO) {
+    if (has_w) {
+      const float4 v = ld4(partial + ((int64_t)s * n_out * k_in) + i * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (has_b) b += partial_bias[(int64_t)s * n_out + i];
   }
-  const int64_t e = i * 4;
-  st4(dst + (e / k_in) * ld + (e % k_in), acc);
+#pragma unroll
+  for (int off = 1; off < TPO; off <<= 1) {
+    const float4 o = shfl_xor4(acc, off);
+    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+  }
+  if (part != 0) return;
+  if (has_b) dst_bias[i] = b;
+  if (has_w) {
+    const int64_t e = i * 4;
+    st4(dst + (e / k_in) * ld + (e % k_in), acc);
+  }
+}
+
+static void launch_wgrad_reduce(const float* partial, const float* partial_bias, int splits, int n_out, int k_in,
+                                float* dst, int64_t ld, float* dst_bias, cudaStream_t s) {
+  const int64_t total4 = (int64_t)n_out * k_in / 4;
+  const int64_t outs = total4 > n_out ? total4 : n_out;
+  if (splits >= 64) {
+    wgrad_reduce_kernel<32><<<(unsigned)((outs * 32 + 255) / 256), 256, 0, s>>>(partial, partial_bias, splits, n_out, k_in, dst, ld, dst_bias);
+  } else if (splits >= 16) {
+    wgrad_reduce_kernel<8><<<(unsigned)((outs * 8 + 255) / 256), 256, 0, s>>>(partial, partial_bias, splits, n_out, k_in, dst, ld, dst_bias);
+  } else {
+    wgrad_reduce_kernel<1><<<(unsigned)((outs + 255) / 256), 256, 0, s>>>(partial, partial_bias, splits, n_out, k_in, dst, ld, dst_bias);
+  }
 }
 
 // column sums (bias gradient): partial[b, c] = sum of rows [b*rpb, (b+1)*rpb) of g[:, c]
@@ -788,10 +814,7 @@ extern "C" int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float
     else st = launch_wgrad<128>(mg, mx, a, splits, s);
     if (st) return st;
   }
-  const int64_t total4 = (int64_t)n_out * k_in / 4;
-  const int64_t threads = total4 > n_out ? total4 : n_out;
-  wgrad_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a.partial, a.partial_bias, rows > 0 ? splits : 0,
-                                                                       n_out, k_in, grad_w, ld_w, grad_b);
+  launch_wgrad_reduce(a.partial, a.partial_bias, rows > 0 ? splits : 0, n_out, k_in, grad_w, ld_w, grad_b, s);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
@@ -833,10 +856,7 @@ extern "C" int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, i
     else st = launch_wgrad<128>(mg, mx, a, splits, s);
     if (st) return st;
   }
-  const int64_t total4 = (int64_t)cout * k_in / 4;
-  const int64_t threads = total4 > cout ? total4 : cout;
-  wgrad_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a.partial, a.partial_bias, rows > 0 ? splits : 0,
-                                                                       cout, k_in, grad_w, k_in, grad_b);
+  launch_wgrad_reduce(a.partial, a.partial_bias, rows > 0 ? splits : 0, cout, k_in, grad_w, k_in, grad_b, s);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }

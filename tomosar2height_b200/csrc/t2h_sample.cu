@@ -10,6 +10,7 @@
 // order (grid_sample taps of a point in cell cx are always within {cx-1, cx, cx+1}, because the
 // corner-aligned coordinate p*(r-1) lies in (cx-1, cx+1) when p*r is in [cx, cx+1)).
 #include "t2h_common.cuh"
+#include <cstdlib>
 
 namespace t2h {
 
@@ -35,6 +36,9 @@ __device__ __forceinline__ Taps make_taps(float px, float py, int reso) {
   return t;
 }
 
+// Forward: a warp owns 32 consecutive sorted points.  Lane j computes the taps of point j ONCE (the
+// coordinate arithmetic is ~40 instructions and these kernels are issue-bound, not bandwidth-bound);
+// the RPI sub-groups then walk the points and fetch (offset, weights, row) by shuffle.
 template <class RS>
 __global__ void __launch_bounds__(kSampleWarps * kWarp)
 sample_fwd_kernel(const float* __restrict__ plane, int reso, const float* __restrict__ xyz, int64_t stride,
@@ -44,23 +48,43 @@ sample_fwd_kernel(const float* __restrict__ plane, int reso, const float* __rest
   const int sub = lane / LPR, l = lane % LPR;
   const int64_t warp = (int64_t)blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
   const int64_t first = warp * kPointsPerWarp;
-  const int64_t last = min(first + kPointsPerWarp, n);
-  for (int64_t i = first + sub; i < last; i += RPI) {
-    const int64_t row = perm ? (int64_t)perm[i] : i;
-    const int64_t b = row / n_per_batch;
+  if (first >= n) return;
+  const int npts = (int)min((int64_t)kPointsPerWarp, n - first);
+
+  // ---- per-lane tap setup for point first + lane -------------------------------------------------
+  int64_t my_row = 0, my_off = 0;
+  int my_dx = 0, my_dy = 0;
+  float my_nw = 0.f, my_ne = 0.f, my_sw = 0.f, my_se = 0.f;
+  if (lane < npts) {
+    const int64_t i = first + lane;
+    my_row = perm ? (int64_t)perm[i] : i;
+    const int64_t b = my_row / n_per_batch;
     const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + i * stride));
     const Taps t = make_taps(pxy.x, pxy.y, reso);
     // taps beyond the last row/column carry zero weight (ix == r-1 exactly); clamp the address
-    const int x1 = min(t.x0 + 1, reso - 1), y1 = min(t.y0 + 1, reso - 1);
-    const float w_nw = __fmul_rn(t.wx0, t.wy0);
-    const float w_ne = (t.x0 + 1 < reso) ? __fmul_rn(t.wx1, t.wy0) : 0.f;
-    const float w_sw = (t.y0 + 1 < reso) ? __fmul_rn(t.wx0, t.wy1) : 0.f;
-    const float w_se = (t.x0 + 1 < reso && t.y0 + 1 < reso) ? __fmul_rn(t.wx1, t.wy1) : 0.f;
-    const float* base = plane + (b * reso * (int64_t)reso) * C + l * 4;
-    const float* p_nw = base + ((int64_t)t.y0 * reso + t.x0) * C;
-    const float* p_ne = base + ((int64_t)t.y0 * reso + x1) * C;
-    const float* p_sw = base + ((int64_t)y1 * reso + t.x0) * C;
-    const float* p_se = base + ((int64_t)y1 * reso + x1) * C;
+    my_dx = (t.x0 + 1 < reso) ? 1 : 0;
+    my_dy = (t.y0 + 1 < reso) ? 1 : 0;
+    my_nw = __fmul_rn(t.wx0, t.wy0);
+    my_ne = my_dx ? __fmul_rn(t.wx1, t.wy0) : 0.f;
+    my_sw = my_dy ? __fmul_rn(t.wx0, t.wy1) : 0.f;
+    my_se = (my_dx && my_dy) ? __fmul_rn(t.wx1, t.wy1) : 0.f;
+    my_off = (b * reso + t.y0) * (int64_t)reso + t.x0;  // pixel index of the north-west tap
+  }
+  const int my_flags = my_dx | (my_dy << 1);
+  for (int t0 = 0; t0 < npts; t0 += RPI) {
+    const int j = t0 + sub;
+    const bool act = j < npts;
+    const int src = act ? j : 0;
+    const int64_t row = __shfl_sync(0xffffffffu, my_row, src);
+    const int64_t off = __shfl_sync(0xffffffffu, my_off, src);
+    const int flags = __shfl_sync(0xffffffffu, my_flags, src);
+    const float w_nw = __shfl_sync(0xffffffffu, my_nw, src), w_ne = __shfl_sync(0xffffffffu, my_ne, src);
+    const float w_sw = __shfl_sync(0xffffffffu, my_sw, src), w_se = __shfl_sync(0xffffffffu, my_se, src);
+    if (!act) continue;
+    const float* p_nw = plane + off * C + l * 4;
+    const float* p_ne = p_nw + (flags & 1) * C;
+    const float* p_sw = p_nw + (int64_t)(flags >> 1) * reso * C;
+    const float* p_se = p_sw + (flags & 1) * C;
     float* dst = out + row * C + l * 4;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -123,19 +147,35 @@ sample_bwd_kernel(const float* __restrict__ grad_rows, int reso, const float* __
           beg = min(beg + part * slice, end);
           end = min(beg + slice, end);
         }
-        for (int i = beg + sub; i < end; i += RPI) {
-          const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + (int64_t)i * stride));
-          const Taps t = make_taps(pxy.x, pxy.y, reso);
-          const float wx = (t.x0 == cx) ? t.wx0 : ((t.x0 + 1 == cx) ? t.wx1 : 0.f);
-          const float wy = (t.y0 == cy) ? t.wy0 : ((t.y0 + 1 == cy) ? t.wy1 : 0.f);
-          const float w = __fmul_rn(wx, wy);
-          if (w != 0.f) {
-            const int64_t row = perm ? (int64_t)perm[i] : (int64_t)i;
-            const float* src = grad_rows + row * C + l * 4;
+        // 32 candidates at a time: lane j evaluates the tap weights of candidate j once, the ballot keeps
+        // only the contributing ones, and the RPI sub-groups share them out in rank order (fixed order)
+        for (int base_i = beg; base_i < end; base_i += kWarp) {
+          const int i = base_i + lane;
+          float w = 0.f;
+          int row = 0;
+          if (i < end) {
+            const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + (int64_t)i * stride));
+            const Taps t = make_taps(pxy.x, pxy.y, reso);
+            const float wx = (t.x0 == cx) ? t.wx0 : ((t.x0 + 1 == cx) ? t.wx1 : 0.f);
+            const float wy = (t.y0 == cy) ? t.wy0 : ((t.y0 + 1 == cy) ? t.wy1 : 0.f);
+            w = __fmul_rn(wx, wy);
+            row = perm ? perm[i] : i;
+          }
+          const unsigned hit = __ballot_sync(0xffffffffu, w != 0.f);
+          const int cnt = __popc(hit);
+          for (int t0 = 0; t0 < cnt; t0 += RPI) {
+            const int k = t0 + sub;
+            const bool act = k < cnt;
+            const int src = act ? (int)__fns(hit, 0, k + 1) : 0;
+            const float wk = __shfl_sync(0xffffffffu, w, src);
+            const int rk = __shfl_sync(0xffffffffu, row, src);
+            if (act) {
+              const float* srcp = grad_rows + (int64_t)rk * C + l * 4;
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-              const float4 gq = ld4(src + c * LPR * 4);
-              acc[c].x += w * gq.x; acc[c].y += w * gq.y; acc[c].z += w * gq.z; acc[c].w += w * gq.w;
+              for (int c = 0; c < CH; ++c) {
+                const float4 gq = ld4(srcp + c * LPR * 4);
+                acc[c].x += wk * gq.x; acc[c].y += wk * gq.y; acc[c].z += wk * gq.z; acc[c].w += wk * gq.w;
+              }
             }
           }
         }
@@ -169,6 +209,158 @@ sample_bwd_kernel(const float* __restrict__ grad_rows, int reso, const float* __
 #pragma unroll
     for (int c = 0; c < CH; ++c) st4(dst + c * LPR * 4, acc[c]);
   }
+}
+
+// ---- G2, tiled: shared-memory-staged, atomic-free, deterministic ------------------------------------
+// A CTA owns a T x T block of plane cells.  With Morton keys its points are ONE contiguous range of the
+// sorted order, so their gradient rows stream in coalesced and are read exactly once.  Every point
+// scatters its four weighted contributions into a (T+2) x (T+2) accumulator tile in shared memory
+// (taps of a point of cell cx lie in columns cx-1..cx+1, hence the one-cell halo).  Determinism without
+// atomics comes from ownership: the 8 warps form CG channel groups x PG point groups; a warp only ever
+// touches its own 32*V-channel slice of its point group's private tile, in point order, so each
+// accumulator has a single writer and a fixed summation order.  Private tiles are then summed in group
+// order into a per-block scratch tile; sample_bwd_merge_kernel adds the (<= 4) overlapping block tiles
+// of every plane cell in a fixed order.
+constexpr int kTileWarps = 8;
+
+template <int C, int T>
+struct TileCfg {
+  static constexpr int CG = (C / 32 < kTileWarps) ? C / 32 : kTileWarps;  // channel groups
+  static constexpr int V = C / (32 * CG);                                // floats per lane
+  static constexpr int PG = kTileWarps / CG;                             // point groups (private tiles)
+  static constexpr int TW = T + 2;
+  static constexpr int TILE_FLOATS = TW * TW * C;
+  static constexpr int SMEM = PG * TILE_FLOATS * 4;
+};
+
+template <int C, int T>
+__global__ void __launch_bounds__(kTileWarps * kWarp)
+sample_bwd_tiled_kernel(const float* __restrict__ grad_rows, int reso, const float* __restrict__ xyz, int64_t stride,
+                        const int32_t* __restrict__ perm, const int32_t* __restrict__ cell_start, int shift,
+                        int log2_cells, float* __restrict__ scratch) {
+  using Cfg = TileCfg<C, T>;
+  constexpr int CG = Cfg::CG, V = Cfg::V, PG = Cfg::PG, TW = Cfg::TW;
+  extern __shared__ float tile_smem[];
+  constexpr int LOG2_T2 = (T == 8) ? 6 : ((T == 4) ? 4 : ((T == 2) ? 2 : 0));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pg = warp / CG, cg = warp % CG;
+  // block index -> tile (image) and Morton block code -> origin
+  const int64_t blk = blockIdx.x;
+  const int blocks_log2 = log2_cells - LOG2_T2;
+  const int64_t img = blk >> blocks_log2;
+  const uint32_t bcode = (uint32_t)(blk - (img << blocks_log2));
+  const int bx0 = (int)compact1by1(bcode) * T, by0 = (int)compact1by1(bcode >> 1) * T;
+  const int64_t key0 = (img << log2_cells) + ((int64_t)bcode << LOG2_T2);
+  const int p0 = cell_start[key0 << shift], p1 = cell_start[(key0 + (1 << LOG2_T2)) << shift];
+
+  for (int f = threadIdx.x; f < PG * Cfg::TILE_FLOATS / 4; f += kTileWarps * kWarp)
+    reinterpret_cast<float4*>(tile_smem)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  // this point group's contiguous slice of the block's points
+  const int len = p1 - p0, chunk = (len + PG - 1) / PG;
+  const int q0 = min(p0 + pg * chunk, p1), q1 = min(q0 + chunk, p1);
+  float* priv = tile_smem + pg * Cfg::TILE_FLOATS + cg * 32 * V + lane * V;
+  const float* gbase = grad_rows + cg * 32 * V + lane * V;
+  for (int base_i = q0; base_i < q1; base_i += kWarp) {
+    const int nb = min(kWarp, q1 - base_i);
+    int my_cell = 0, my_row = 0;
+    float my_nw = 0.f, my_ne = 0.f, my_sw = 0.f, my_se = 0.f;
+    if (lane < nb) {
+      const int i = base_i + lane;
+      const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + (int64_t)i * stride));
+      const Taps t = make_taps(pxy.x, pxy.y, reso);
+      my_nw = __fmul_rn(t.wx0, t.wy0);
+      my_ne = (t.x0 + 1 < reso) ? __fmul_rn(t.wx1, t.wy0) : 0.f;
+      my_sw = (t.y0 + 1 < reso) ? __fmul_rn(t.wx0, t.wy1) : 0.f;
+      my_se = (t.x0 + 1 < reso && t.y0 + 1 < reso) ? __fmul_rn(t.wx1, t.wy1) : 0.f;
+      // local coordinates in the haloed tile; clamp defensively (a point is always within one cell)
+      const int lx = min(max(t.x0 - bx0 + 1, 0), T), ly = min(max(t.y0 - by0 + 1, 0), T);
+      my_cell = ly * TW + lx;
+      my_row = perm ? perm[i] : i;
+    }
+    // U points per trip: issue all row loads first (memory-level parallelism), then the shared-memory updates
+    constexpr int U = (V <= 2) ? 8 : 4;
+    for (int j0 = 0; j0 < nb; j0 += U) {
+      int cell[U];
+      float wq[U][4], g[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = min(j0 + u, nb - 1);
+        cell[u] = __shfl_sync(0xffffffffu, my_cell, j);
+        const int row = __shfl_sync(0xffffffffu, my_row, j);
+        wq[u][0] = __shfl_sync(0xffffffffu, my_nw, j); wq[u][1] = __shfl_sync(0xffffffffu, my_ne, j);
+        wq[u][2] = __shfl_sync(0xffffffffu, my_sw, j); wq[u][3] = __shfl_sync(0xffffffffu, my_se, j);
+        const float* gp = gbase + (int64_t)row * C;
+        if constexpr (V == 1) {
+          g[u][0] = __ldg(gp);
+        } else if constexpr (V == 2) {
+          const float2 t2 = __ldg(reinterpret_cast<const float2*>(gp));
+          g[u][0] = t2.x; g[u][1] = t2.y;
+        } else {
+          const float4 t4 = ld4(gp);
+          g[u][0] = t4.x; g[u][1] = t4.y; g[u][2] = t4.z; g[u][3] = t4.w;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j0 + u >= nb) break;
+        float* a = priv + cell[u] * C;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          a[v] += wq[u][0] * g[u][v];
+          a[C + v] += wq[u][1] * g[u][v];
+          a[TW * C + v] += wq[u][2] * g[u][v];
+          a[TW * C + C + v] += wq[u][3] * g[u][v];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // private tiles -> scratch, summed in point-group order
+  float* dst = scratch + blk * (int64_t)Cfg::TILE_FLOATS;
+  for (int f = threadIdx.x; f < Cfg::TILE_FLOATS / 4; f += kTileWarps * kWarp) {
+    float4 acc = reinterpret_cast<const float4*>(tile_smem)[f];
+#pragma unroll
+    for (int q = 1; q < PG; ++q) {
+      const float4 o = reinterpret_cast<const float4*>(tile_smem + q * Cfg::TILE_FLOATS)[f];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    st4(dst + f * 4, acc);
+  }
+}
+
+// grad_plane[b, y, x, :] = sum of the block tiles that cover (x, y): own block plus the left/upper or
+// right/lower neighbours when the cell lies on a block edge; fixed order (by, then bx)
+template <int T>
+__global__ void __launch_bounds__(256)
+sample_bwd_merge_kernel(const float* __restrict__ scratch, int reso, int C, int log2_cells, int64_t n_cells,
+                        float* __restrict__ grad_plane) {
+  constexpr int TW = T + 2;
+  constexpr int LOG2_T2 = (T == 8) ? 6 : ((T == 4) ? 4 : ((T == 2) ? 2 : 0));
+  const int c4 = C / 4;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_cells * c4) return;
+  const int64_t cellid = gid / c4;
+  const int ch = (int)(gid - cellid * c4) * 4;
+  const int64_t cells = (int64_t)reso * reso;
+  const int64_t img = cellid / cells;
+  const int rem = (int)(cellid - img * cells);
+  const int y = rem / reso, x = rem - y * reso;
+  const int nblk = reso / T;
+  const int blocks_log2 = log2_cells - LOG2_T2;
+  const int bx_lo = max((x - 1 + T) / T - 1, 0) , bx_hi = min((x + 1) / T, nblk - 1);
+  const int by_lo = max((y - 1 + T) / T - 1, 0) , by_hi = min((y + 1) / T, nblk - 1);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int by = by_lo; by <= by_hi; ++by)
+    for (int bx = bx_lo; bx <= bx_hi; ++bx) {
+      const int lx = x - bx * T + 1, ly = y - by * T + 1;
+      if (lx < 0 || lx >= TW || ly < 0 || ly >= TW) continue;
+      const int64_t blk = (img << blocks_log2) + (part1by1((uint32_t)bx) | (part1by1((uint32_t)by) << 1));
+      const float4 v = ld4(scratch + (blk * (TW * TW) + ly * TW + lx) * (int64_t)C + ch);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  st4(grad_plane + cellid * C + ch, acc);
 }
 
 // ---- regular-grid bilinear resize, align_corners=True (ATen UpSampleBilinear2d semantics) -----
@@ -282,17 +474,89 @@ extern "C" int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, cons
   return T2H_OK;
 }
 
+// Block edge T for the tiled backward: the largest of {8, 4, 2, 1} that keeps ~<= 512 points per block
+// (coarse levels hold hundreds of points per cell; small blocks keep thousands of CTAs in flight)
+static inline int tiled_T(int reso, int C, int morton, int64_t n_points, int64_t n_seg) {
+  if (!morton || C < 32 || (C & (C - 1)) || C > 1024 || n_seg <= 0) return 0;   // C in {32, 64, ..., 1024}
+  const int64_t avg = n_points / n_seg > 0 ? n_points / n_seg : 1;
+  int T = C <= 512 ? 8 : 4;
+  while (T > 1 && ((int64_t)T * T * avg > 512 || T > reso)) T >>= 1;
+  return T;
+}
+
+extern "C" size_t t2h_bilinear_sample_bwd_workspace_bytes(int reso, int C, int64_t n_seg, int morton) {
+  if (!morton || n_seg <= 0) return 256;
+  return (size_t)n_seg * 9 * C * sizeof(float) + 256;  // worst case T = 1: a 3 x 3 tile per cell
+}
+
+template <int C, int T>
+static int launch_tiled(const float* grad_rows, int reso, const float* xyz, int64_t stride, const int32_t* perm,
+                        const int32_t* cell_start, int64_t n_seg, int shift, int log2_cells, float* scratch,
+                        float* grad_plane, cudaStream_t s) {
+  using Cfg = TileCfg<C, T>;
+  auto kern = sample_bwd_tiled_kernel<C, T>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return T2H_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t blocks = n_seg / (T * T);
+  kern<<<(unsigned)blocks, kTileWarps * kWarp, Cfg::SMEM, s>>>(grad_rows, reso, xyz, stride, perm, cell_start, shift, log2_cells, scratch);
+  T2H_CHECK_LAUNCH();
+  const int64_t threads = n_seg * (C / 4);
+  sample_bwd_merge_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(scratch, reso, C, log2_cells, n_seg, grad_plane);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
 extern "C" int t2h_bilinear_sample_bwd(const float* grad_rows, int64_t n_points, int reso, int C,
                                        const float* xyz_sorted, int64_t point_stride, const int32_t* perm,
                                        const int32_t* cell_start, int64_t n_seg, int shift, int morton,
-                                       float* grad_plane, t2h_stream_t stream) {
+                                       void* workspace, size_t workspace_bytes, float* grad_plane,
+                                       t2h_stream_t stream) {
   if (!grad_rows || !xyz_sorted || !cell_start || !grad_plane || reso <= 0 || point_stride < 2 || (point_stride & 1) ||
       n_points < 0 || n_seg < 0 ||
       shift < 0 || (shift & 1) || (shift && !morton) || n_seg % ((int64_t)reso * reso))
     return T2H_ERR_INVALID_ARGUMENT;
   if (morton && (reso & (reso - 1))) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  // ~9 neighbour cells are scanned per plane cell: split the scan over several warps on coarse levels
+  {
+    const int T = tiled_T(reso, C, morton, n_points, n_seg);
+    static const int force_gather = []() { const char* e = getenv("T2H_SAMPLE_BWD_GATHER"); return e ? atoi(e) : 0; }();
+    // measured (profiles/): the scatter tile wins on the fine levels (few points per cell, T = 8); on coarser
+    // levels its serial shared-memory updates lose to the gather kernel, which is used there
+    if (T == 8 && workspace && !force_gather) {
+      if (workspace_bytes < t2h_bilinear_sample_bwd_workspace_bytes(reso, C, n_seg, morton)) return T2H_ERR_WORKSPACE_TOO_SMALL;
+      int l2c = 0;
+      while ((1 << l2c) < reso) ++l2c;
+      l2c *= 2;
+      cudaStream_t st = (cudaStream_t)stream;
+      float* scr = (float*)workspace;
+#define T2H_TILED(CC, TT) return launch_tiled<CC, TT>(grad_rows, reso, xyz_sorted, point_stride, perm, cell_start, n_seg, shift, l2c, scr, grad_plane, st)
+#define T2H_TILED_C(CC)                                             \
+  case CC:                                                          \
+    if (T == 8) { if constexpr (CC <= 512) T2H_TILED(CC, 8); }     \
+    if (T == 4) T2H_TILED(CC, 4);                                   \
+    if (T == 2) T2H_TILED(CC, 2);                                   \
+    T2H_TILED(CC, 1);
+      switch (C) {
+        T2H_TILED_C(32)
+        T2H_TILED_C(64)
+        T2H_TILED_C(128)
+        T2H_TILED_C(256)
+        T2H_TILED_C(512)
+        T2H_TILED_C(1024)
+        default: break;
+      }
+#undef T2H_TILED_C
+#undef T2H_TILED
+    }
+  }
+  // gather fallback (row-major keys, odd channel counts): ~9 neighbour cells are scanned per plane cell;
+  // split the scan over several warps on coarse levels
   const int64_t avg = n_points / n_seg;
   int wps = 1;
   while (wps < kSampleWarps && avg >= 4 * wps) wps *= 2;

@@ -155,8 +155,10 @@ class _BilinearSample(torch.autograd.Function):
         C = g_rows.shape[1]
         g_plane = torch.empty(ctx.shape, dtype=torch.float32, device=g_rows.device)
         xyz = level.xyz_sorted
+        ws_bytes = int(_lib.load().t2h_bilinear_sample_bwd_workspace_bytes(level.reso, C, level.n_seg, level.morton))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g_rows.device)
         call("t2h_bilinear_sample_bwd", ptr(g_rows), g_rows.shape[0], level.reso, C, ptr(xyz), xyz.shape[1], ptr(level.perm),
-             ptr(level.cell_start), level.n_seg, level.shift, level.morton, ptr(g_plane))
+             ptr(level.cell_start), level.n_seg, level.shift, level.morton, ptr(ws), ws_bytes, ptr(g_plane))
         return g_plane, None
 
 

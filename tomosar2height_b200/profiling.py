@@ -42,7 +42,7 @@ def _bytes(name, a):
         reso, C, n, n_per = a[1], a[2], a[6], a[7]
         return 4 * (n // n_per) * reso * reso * C + 8 * n + 4 * n * C
     if name == "t2h_bilinear_sample_bwd":
-        reso, C, n_seg = a[2], a[3], a[8]
+        reso, C, n_seg = a[2], a[3], a[8]  # (workspace args follow)
         rows = _bytes.n_rows
         return 4 * rows * C + 8 * rows + 4 * n_seg * C
     if name in ("t2h_upsample_bilinear_fwd", "t2h_upsample_bilinear_bwd"):
