@@ -330,11 +330,186 @@ sample_bwd_tiled_kernel(const float* __restrict__ grad_rows, int reso, const flo
   }
 }
 
+// ---- G2, cell-parallel: register accumulation of the 3x3 target partials ------------------------------
+// All points of one own cell (cx, cy) contribute to the same 3x3 target cells (cx-1..cx+1, cy-1..cy+1),
+// so a warp that walks a cell's (contiguous) rows keeps nine partial sums in REGISTERS -- no per-point
+// shared-memory traffic, rows are read once, coalesced.  A CTA owns a T x T Morton block of cells; per
+// round its 8 warps are split into (cells x row slices x 128-channel groups).  Slice partials are combined
+// through shared memory in slice order, every own cell's nine partials are staged in shared memory, and
+// the block's haloed (T+2) x (T+2) output tile is assembled from them in a fixed order and written to
+// scratch; sample_bwd_merge_kernel adds the overlapping block tiles.  No atomics, fixed summation order.
+template <int C, int T>
+struct CellCfg {
+  static constexpr int CW = C < 128 ? C : 128;   // channels per warp
+  static constexpr int CGN = C / CW;             // channel groups
+  static constexpr int RF = kTileWarps / CGN;    // warps per channel group = cells per round x slices
+  static constexpr int LPR = CW / 4, RPI = 32 / LPR;
+  static constexpr int NC = T * T, TW = T + 2;
+  static constexpr int PARTS_FLOATS = kTileWarps * 9 * CW;
+  static constexpr int STAGE_FLOATS = NC * 9 * C;
+  static constexpr int SMEM = (PARTS_FLOATS + STAGE_FLOATS) * 4;
+  static constexpr int LOG2_T2 = (T == 8) ? 6 : ((T == 4) ? 4 : ((T == 2) ? 2 : 0));
+};
+
+template <int C, int T>
+__global__ void __launch_bounds__(kTileWarps * kWarp)
+sample_bwd_cell_kernel(const float* __restrict__ grad_rows, int reso, const float* __restrict__ xyz, int64_t stride,
+                       const int32_t* __restrict__ perm, const int32_t* __restrict__ cell_start, int shift,
+                       int log2_cells, int slices, float* __restrict__ scratch) {
+  // gridDim.y = ZS: on coarse levels (hundreds of rows per cell) the rows of every cell are additionally
+  // split over ZS CTAs, each writing its own scratch tile; the merge kernel adds them in z order
+  using Cfg = CellCfg<C, T>;
+  constexpr int CW = Cfg::CW, CGN = Cfg::CGN, RF = Cfg::RF, LPR = Cfg::LPR, RPI = Cfg::RPI, NC = Cfg::NC, TW = Cfg::TW;
+  extern __shared__ float cell_smem[];
+  float* parts = cell_smem;                       // [warp][9][CW]
+  float* stage = cell_smem + Cfg::PARTS_FLOATS;   // [own cell][9][C]
+  __shared__ int cell_heavy[NC];
+  constexpr int kHeavyRows = 96;                  // rows per slice beyond which a cell counts as heavy
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int cg = warp % CGN, rest = warp / CGN;
+  const int sl = rest % slices, cr = rest / slices;
+  const int cells_per_round = RF / slices;
+
+  const int64_t blk = blockIdx.x;
+  const int blocks_log2 = log2_cells - Cfg::LOG2_T2;
+  const int64_t img = blk >> blocks_log2;
+  const uint32_t bcode = (uint32_t)(blk - (img << blocks_log2));
+  const int bx0 = (int)compact1by1(bcode) * T, by0 = (int)compact1by1(bcode >> 1) * T;
+  const int64_t key0 = (img << log2_cells) + ((int64_t)bcode << Cfg::LOG2_T2);
+  const float* gbase = grad_rows + cg * CW + l * 4;
+
+  // rows of own cell q, slice my_sl of n_sl  ->  nine partial sums in registers  ->  parts[warp]
+  auto reduce_cell = [&](int q, int my_sl, int n_sl) {
+    float4 acc[9];
+#pragma unroll
+    for (int d = 0; d < 9; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cx = bx0 + (int)compact1by1((uint32_t)q), cy = by0 + (int)compact1by1((uint32_t)q >> 1);
+    const int beg = cell_start[(key0 + q) << shift], end = cell_start[(key0 + q + 1) << shift];
+    const int zs = gridDim.y, tot_sl = n_sl * zs, g_sl = blockIdx.y * n_sl + my_sl;
+    const int len = end - beg, chunk = (len + tot_sl - 1) / tot_sl;
+    const int r0 = min(beg + g_sl * chunk, end), r1 = min(r0 + chunk, end);
+    for (int base_i = r0; base_i < r1; base_i += kWarp) {
+      const int nb = min(kWarp, r1 - base_i);
+      // lane j: the 3 + 3 separable target weights of row base_i + j (the tap arithmetic runs once per row)
+      float wx_m = 0.f, wx_0 = 0.f, wx_p = 0.f, wy_m = 0.f, wy_0 = 0.f, wy_p = 0.f;
+      int my_row = 0;
+      if (lane < nb) {
+        const int i = base_i + lane;
+        const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + (int64_t)i * stride));
+        const Taps t = make_taps(pxy.x, pxy.y, reso);
+        const float wx1 = (t.x0 + 1 < reso) ? t.wx1 : 0.f, wy1 = (t.y0 + 1 < reso) ? t.wy1 : 0.f;
+        if (t.x0 < cx) { wx_m = t.wx0; wx_0 = wx1; } else { wx_0 = t.wx0; wx_p = wx1; }
+        if (t.y0 < cy) { wy_m = t.wy0; wy_0 = wy1; } else { wy_0 = t.wy0; wy_p = wy1; }
+        my_row = perm ? perm[i] : i;
+      }
+      // U rows per sub-group per trip: all U row loads are issued before the FMAs (memory-level parallelism)
+      constexpr int U = (RPI > 1) ? 1 : 4;  // narrow rows already cover RPI rows per trip; fine cells hold ~4 rows
+      for (int t0 = 0; t0 < nb; t0 += RPI * U) {
+        float4 g[U];
+        float wx[U][3], wy[U][3];
+        bool act[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = t0 + u * RPI + sub;
+          act[u] = j < nb;
+          const int src = act[u] ? j : 0;
+          const int row = __shfl_sync(0xffffffffu, my_row, src);
+          wx[u][0] = __shfl_sync(0xffffffffu, wx_m, src); wx[u][1] = __shfl_sync(0xffffffffu, wx_0, src); wx[u][2] = __shfl_sync(0xffffffffu, wx_p, src);
+          wy[u][0] = __shfl_sync(0xffffffffu, wy_m, src); wy[u][1] = __shfl_sync(0xffffffffu, wy_0, src); wy[u][2] = __shfl_sync(0xffffffffu, wy_p, src);
+          g[u] = act[u] ? ld4(gbase + (int64_t)row * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!act[u]) continue;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const float w = __fmul_rn(wx[u][dx], wy[u][dy]);
+              float4& a = acc[dy * 3 + dx];
+              a.x += w * g[u].x; a.y += w * g[u].y; a.z += w * g[u].z; a.w += w * g[u].w;
+            }
+        }
+      }
+    }
+    // fold the RPI sub-rows of the warp (fixed xor tree)
+#pragma unroll
+    for (int off = LPR; off < kWarp; off <<= 1)
+#pragma unroll
+      for (int d = 0; d < 9; ++d) {
+        const float4 o = shfl_xor4(acc[d], off);
+        acc[d].x += o.x; acc[d].y += o.y; acc[d].z += o.z; acc[d].w += o.w;
+      }
+    if (sub == 0) {
+#pragma unroll
+      for (int d = 0; d < 9; ++d) *reinterpret_cast<float4*>(parts + (warp * 9 + d) * CW + l * 4) = acc[d];
+    }
+  };
+  // parts of n_cells own cells (n_sl slices each) -> stage, in slice order; cells flagged `skip_heavy` are left out
+  auto combine = [&](int q_first, int n_cells, int n_sl, bool skip_heavy) {
+    for (int idx = threadIdx.x; idx < n_cells * 9 * (C / 4); idx += kTileWarps * kWarp) {
+      const int c4i = idx % (C / 4);
+      const int d = (idx / (C / 4)) % 9;
+      const int crr = idx / (9 * (C / 4));
+      if (skip_heavy && cell_heavy[q_first + crr]) continue;
+      const int cgi = (c4i * 4) / CW, within = (c4i * 4) % CW;
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s2 = 0; s2 < n_sl; ++s2) {
+        const int w2 = (crr * n_sl + s2) * CGN + cgi;
+        const float4 o = *reinterpret_cast<const float4*>(parts + (w2 * 9 + d) * CW + within);
+        sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+      }
+      *reinterpret_cast<float4*>(stage + ((q_first + crr) * 9 + d) * C + c4i * 4) = sum;
+    }
+  };
+
+  // heavy cells (a facade crossing the block) are deferred and then reduced by every warp of the CTA
+  if (threadIdx.x < NC) {
+    const int len = cell_start[(key0 + threadIdx.x + 1) << shift] - cell_start[(key0 + threadIdx.x) << shift];
+    cell_heavy[threadIdx.x] = (slices < RF && len > kHeavyRows * slices * (int)gridDim.y) ? 1 : 0;
+  }
+  __syncthreads();
+  for (int q0 = 0; q0 < NC; q0 += cells_per_round) {
+    const int q = q0 + cr;
+    if (q < NC && !cell_heavy[q]) reduce_cell(q, sl, slices);
+    __syncthreads();
+    combine(q0, min(cells_per_round, NC - q0), slices, true);
+    __syncthreads();
+  }
+  for (int q = 0; q < NC; ++q) {
+    if (!cell_heavy[q]) continue;  // uniform across the CTA
+    reduce_cell(q, rest, RF);
+    __syncthreads();
+    combine(q, 1, RF, false);
+    __syncthreads();
+  }
+  // haloed output tile of the block: target (ly, lx) collects partial d = (dy, dx) of own cell (ly-1-dy, lx-1-dx)
+  float* dst = scratch + ((int64_t)blockIdx.y * gridDim.x + blk) * (int64_t)(TW * TW * C);
+  for (int idx = threadIdx.x; idx < TW * TW * (C / 4); idx += kTileWarps * kWarp) {
+    const int c4i = idx % (C / 4), cellt = idx / (C / 4);
+    const int ly = cellt / TW, lx = cellt % TW;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int oy = ly - dy, ox = lx - dx;  // = (ly - 1) - (dy - 1)
+        if (ox >= 0 && ox < T && oy >= 0 && oy < T) {
+          const int qq = (int)(part1by1((uint32_t)ox) | (part1by1((uint32_t)oy) << 1));
+          const float4 o = *reinterpret_cast<const float4*>(stage + (qq * 9 + dy * 3 + dx) * C + c4i * 4);
+          sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+        }
+      }
+    st4(dst + (int64_t)cellt * C + c4i * 4, sum);
+  }
+}
+
 // grad_plane[b, y, x, :] = sum of the block tiles that cover (x, y): own block plus the left/upper or
 // right/lower neighbours when the cell lies on a block edge; fixed order (by, then bx)
 template <int T>
 __global__ void __launch_bounds__(256)
-sample_bwd_merge_kernel(const float* __restrict__ scratch, int reso, int C, int log2_cells, int64_t n_cells,
+sample_bwd_merge_kernel(const float* __restrict__ scratch, int reso, int C, int log2_cells, int64_t n_cells, int zs,
                         float* __restrict__ grad_plane) {
   constexpr int TW = T + 2;
   constexpr int LOG2_T2 = (T == 8) ? 6 : ((T == 4) ? 4 : ((T == 2) ? 2 : 0));
@@ -352,14 +527,16 @@ sample_bwd_merge_kernel(const float* __restrict__ scratch, int reso, int C, int 
   const int bx_lo = max((x - 1 + T) / T - 1, 0) , bx_hi = min((x + 1) / T, nblk - 1);
   const int by_lo = max((y - 1 + T) / T - 1, 0) , by_hi = min((y + 1) / T, nblk - 1);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int by = by_lo; by <= by_hi; ++by)
-    for (int bx = bx_lo; bx <= bx_hi; ++bx) {
-      const int lx = x - bx * T + 1, ly = y - by * T + 1;
-      if (lx < 0 || lx >= TW || ly < 0 || ly >= TW) continue;
-      const int64_t blk = (img << blocks_log2) + (part1by1((uint32_t)bx) | (part1by1((uint32_t)by) << 1));
-      const float4 v = ld4(scratch + (blk * (TW * TW) + ly * TW + lx) * (int64_t)C + ch);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
+  const int64_t n_blocks = n_cells >> LOG2_T2;
+  for (int z = 0; z < zs; ++z)
+    for (int by = by_lo; by <= by_hi; ++by)
+      for (int bx = bx_lo; bx <= bx_hi; ++bx) {
+        const int lx = x - bx * T + 1, ly = y - by * T + 1;
+        if (lx < 0 || lx >= TW || ly < 0 || ly >= TW) continue;
+        const int64_t blk = z * n_blocks + (img << blocks_log2) + (part1by1((uint32_t)bx) | (part1by1((uint32_t)by) << 1));
+        const float4 v = ld4(scratch + (blk * (TW * TW) + ly * TW + lx) * (int64_t)C + ch);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
   st4(grad_plane + cellid * C + ch, acc);
 }
 
@@ -486,7 +663,45 @@ static inline int tiled_T(int reso, int C, int morton, int64_t n_points, int64_t
 
 extern "C" size_t t2h_bilinear_sample_bwd_workspace_bytes(int reso, int C, int64_t n_seg, int morton) {
   if (!morton || n_seg <= 0) return 256;
-  return (size_t)n_seg * 9 * C * sizeof(float) + 256;  // worst case T = 1: a 3 x 3 tile per cell
+  // haloed block tiles: T = 1 blocks (C >= 512) carry a 3 x 3 tile per cell and up to 8 row splits;
+  // T >= 2 blocks at most 4 tile cells per cell
+  const size_t per_cell = C >= 512 ? 9 * 8 : (C >= 128 ? 4 * 8 : 36 * 8 / 16);
+  return (size_t)n_seg * per_cell * C * sizeof(float) + 256;
+}
+
+static inline int cell_zsplit(int64_t avg, int slices) {
+  int zs = 1;
+  while (zs < 8 && avg >= (int64_t)48 * slices * zs) zs *= 2;
+  return zs;
+}
+
+template <int C, int T>
+static int launch_cell(const float* grad_rows, int reso, const float* xyz, int64_t stride, const int32_t* perm,
+                       const int32_t* cell_start, int64_t n_points, int64_t n_seg, int shift, int log2_cells,
+                       float* scratch, float* grad_plane, cudaStream_t s) {
+  using Cfg = CellCfg<C, T>;
+  auto kern = sample_bwd_cell_kernel<C, T>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return T2H_ERR_CUDA;
+    }
+    configured = true;
+  }
+  // ~32 rows per warp on average: row slices inside the CTA first (bounded by the warps of a channel group),
+  // then ZS CTAs per block
+  const int64_t avg = n_points / n_seg;
+  int slices = 1;
+  while (slices < Cfg::RF && avg >= 48 * slices) slices *= 2;
+  const int zs = cell_zsplit(avg, slices);
+  const int64_t blocks = n_seg / (T * T);
+  kern<<<dim3((unsigned)blocks, (unsigned)zs), kTileWarps * kWarp, Cfg::SMEM, s>>>(grad_rows, reso, xyz, stride, perm, cell_start, shift, log2_cells, slices, scratch);
+  T2H_CHECK_LAUNCH();
+  const int64_t threads = n_seg * (C / 4);
+  sample_bwd_merge_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(scratch, reso, C, log2_cells, n_seg, zs, grad_plane);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
 }
 
 template <int C, int T>
@@ -507,7 +722,7 @@ static int launch_tiled(const float* grad_rows, int reso, const float* xyz, int6
   kern<<<(unsigned)blocks, kTileWarps * kWarp, Cfg::SMEM, s>>>(grad_rows, reso, xyz, stride, perm, cell_start, shift, log2_cells, scratch);
   T2H_CHECK_LAUNCH();
   const int64_t threads = n_seg * (C / 4);
-  sample_bwd_merge_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(scratch, reso, C, log2_cells, n_seg, grad_plane);
+  sample_bwd_merge_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(scratch, reso, C, log2_cells, n_seg, 1, grad_plane);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
@@ -526,9 +741,30 @@ extern "C" int t2h_bilinear_sample_bwd(const float* grad_rows, int64_t n_points,
   {
     const int T = tiled_T(reso, C, morton, n_points, n_seg);
     static const int force_gather = []() { const char* e = getenv("T2H_SAMPLE_BWD_GATHER"); return e ? atoi(e) : 0; }();
-    // measured (profiles/): the scatter tile wins on the fine levels (few points per cell, T = 8); on coarser
-    // levels its serial shared-memory updates lose to the gather kernel, which is used there
-    if (T == 8 && workspace && !force_gather) {
+    static const int mode = []() { const char* e = getenv("T2H_SAMPLE_BWD_MODE"); return e ? atoi(e) : 0; }();  // ablation
+    if (morton && workspace && !force_gather && mode != 1 && C >= 32 && !(C & (C - 1)) && C <= 1024) {
+      // cell-parallel register accumulation; block edge T with T*T*C <= 1024 floats x 9 partials of staging
+      if (workspace_bytes < t2h_bilinear_sample_bwd_workspace_bytes(reso, C, n_seg, morton)) return T2H_ERR_WORKSPACE_TOO_SMALL;
+      int l2c = 0;
+      while ((1 << l2c) < reso) ++l2c;
+      l2c *= 2;
+      cudaStream_t st = (cudaStream_t)stream;
+      float* scr = (float*)workspace;
+#define T2H_CELL(CC, TT) \
+  if (reso >= TT) return launch_cell<CC, TT>(grad_rows, reso, xyz_sorted, point_stride, perm, cell_start, n_points, n_seg, shift, l2c, scr, grad_plane, st)
+      switch (C) {
+        case 32: T2H_CELL(32, 4); break;
+        case 64: T2H_CELL(64, 4); break;
+        case 128: T2H_CELL(128, 2); break;
+        case 256: T2H_CELL(256, 2); break;
+        case 512: T2H_CELL(512, 1); break;
+        case 1024: T2H_CELL(1024, 1); break;
+        default: break;
+      }
+#undef T2H_CELL
+    }
+    // scatter tile with per-point shared-memory updates (kept for ablation: T2H_SAMPLE_BWD_MODE=1)
+    if (T == 8 && workspace && !force_gather && mode == 1) {
       if (workspace_bytes < t2h_bilinear_sample_bwd_workspace_bytes(reso, C, n_seg, morton)) return T2H_ERR_WORKSPACE_TOO_SMALL;
       int l2c = 0;
       while ((1 << l2c) < reso) ++l2c;
