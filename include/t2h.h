@@ -56,6 +56,10 @@ int t2h_cell_index(const float* xy, int64_t n_points, int64_t point_stride, int 
 /* keys[i] = b*reso^2 + code(ix,iy), cell coordinates clamped to [0, reso-1]; b = i / n_per_batch */
 int t2h_xy_keys(const float* xyz, int64_t n_points, int64_t point_stride, int64_t n_per_batch,
                 int reso, int morton, int32_t* keys, t2h_stream_t stream);
+/* ragged batches (tiles with different point counts, flat cloud + offsets[n_tiles + 1] on the device):
+ * b = the tile whose range [offsets[b], offsets[b+1]) holds point i */
+int t2h_xy_keys_ragged(const float* xyz, int64_t n_points, int64_t point_stride, const int64_t* offsets,
+                       int n_tiles, int reso, int morton, int32_t* keys, t2h_stream_t stream);
 /* keys[i] = b*dim_size + index[i]; *flag set non-zero if an index is outside [0, dim_size) */
 int t2h_index_keys(const int64_t* index, int64_t n_points, int64_t n_per_batch, int64_t dim_size,
                    int32_t* keys, int32_t* flag, t2h_stream_t stream);
@@ -101,10 +105,11 @@ int t2h_seg_broadcast(const float* plane, const int32_t* perm, const int32_t* ce
 
 /* ---- a4: alto.py:90-95,199-205 F.grid_sample(bilinear, border, align_corners=True) -----------
  * out_rows[row, :] = 4-tap bilinear sample of plane[b] at (x, y) = xyz_sorted[i, 0:2]
- * (point_stride, in floats, must be even: coordinates are fetched as one 8-byte load)         */
+ * (point_stride, in floats, must be even: coordinates are fetched as one 8-byte load);
+ * the tile of sorted point i is tile_ids[i] when given (ragged batches), else row / n_per_batch */
 int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, const float* xyz_sorted,
-                            int64_t point_stride, const int32_t* perm, int64_t n_points,
-                            int64_t n_per_batch, float* out_rows, t2h_stream_t stream);
+                            int64_t point_stride, const int32_t* perm, const int32_t* tile_ids,
+                            int64_t n_points, int64_t n_per_batch, float* out_rows, t2h_stream_t stream);
 /* grad_plane (B, r, r, C), atomic-free and deterministic.  With Morton keys and C in {32..1024} (and a
  * workspace): shared-memory-staged scatter, one CTA per 8x8 block of cells with a one-cell halo, single
  * writer per accumulator, block tiles merged in a fixed order.  Otherwise (workspace NULL, row-major keys,

@@ -10,6 +10,7 @@ from .decoder import decoder_dict  # noqa: F401
 from .encoder import encoder_dict  # noqa: F401
 from .block import ResnetBlockFC  # noqa: F401
 from .config import berlin_config, munich_config, Config, to_config  # noqa: F401
+from .topology import RaggedCloud  # noqa: F401
 
 
 def install_as_reference():

@@ -26,6 +26,7 @@ SIGNATURES = {
     "t2h_status_string": [_i32],
     "t2h_cell_index": [_p, _i64, _i64, _i32, _p, _p],
     "t2h_xy_keys": [_p, _i64, _i64, _i64, _i32, _i32, _p, _p],
+    "t2h_xy_keys_ragged": [_p, _i64, _i64, _p, _i32, _i32, _i32, _p, _p],
     "t2h_index_keys": [_p, _i64, _i64, _i64, _p, _p, _p],
     "t2h_sort_workspace_bytes": [_i64],
     "t2h_sort_by_cell": [_p, _i64, _i64, _p, _sz, _p, _p, _p, _p],
@@ -35,7 +36,7 @@ SIGNATURES = {
     "t2h_seg_max_bwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
     "t2h_seg_reduce_fwd": [_p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_seg_broadcast": [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
-    "t2h_bilinear_sample_fwd": [_p, _i32, _i32, _p, _i64, _p, _i64, _i64, _p, _p],
+    "t2h_bilinear_sample_fwd": [_p, _i32, _i32, _p, _i64, _p, _p, _i64, _i64, _p, _p],
     "t2h_bilinear_sample_bwd_workspace_bytes": [_i32, _i32, _i64, _i32],
     "t2h_bilinear_sample_bwd": [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _sz, _p, _p],
     "t2h_upsample_bilinear_fwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],

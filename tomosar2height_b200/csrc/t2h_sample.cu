@@ -42,7 +42,8 @@ __device__ __forceinline__ Taps make_taps(float px, float py, int reso) {
 template <class RS>
 __global__ void __launch_bounds__(kSampleWarps * kWarp)
 sample_fwd_kernel(const float* __restrict__ plane, int reso, const float* __restrict__ xyz, int64_t stride,
-                  const int32_t* __restrict__ perm, int64_t n, int64_t n_per_batch, float* __restrict__ out) {
+                  const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_ids, int64_t n, int64_t n_per_batch,
+                  float* __restrict__ out) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -58,7 +59,7 @@ sample_fwd_kernel(const float* __restrict__ plane, int reso, const float* __rest
   if (lane < npts) {
     const int64_t i = first + lane;
     my_row = perm ? (int64_t)perm[i] : i;
-    const int64_t b = my_row / n_per_batch;
+    const int64_t b = tile_ids ? (int64_t)tile_ids[i] : my_row / n_per_batch;  // ragged batches carry tile ids
     const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + i * stride));
     const Taps t = make_taps(pxy.x, pxy.y, reso);
     // taps beyond the last row/column carry zero weight (ix == r-1 exactly); clamp the address
@@ -637,8 +638,8 @@ upsample_bwd_kernel(const float* __restrict__ grad_out, int B, int h, int w, int
 using namespace t2h;
 
 extern "C" int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, const float* xyz_sorted,
-                                       int64_t point_stride, const int32_t* perm, int64_t n_points,
-                                       int64_t n_per_batch, float* out_rows, t2h_stream_t stream) {
+                                       int64_t point_stride, const int32_t* perm, const int32_t* tile_ids,
+                                       int64_t n_points, int64_t n_per_batch, float* out_rows, t2h_stream_t stream) {
   if (!plane || !xyz_sorted || !out_rows || reso <= 0 || point_stride < 2 || (point_stride & 1) || n_points < 0 ||
       n_per_batch <= 0)
     return T2H_ERR_INVALID_ARGUMENT;
@@ -646,7 +647,7 @@ extern "C" int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, cons
   const int64_t warps = (n_points + kPointsPerWarp - 1) / kPointsPerWarp;
   const unsigned blocks = (unsigned)((warps + kSampleWarps - 1) / kSampleWarps);
   T2H_DISPATCH_ROWSHAPE(C, sample_fwd_kernel<RS><<<blocks, kSampleWarps * kWarp, 0, (cudaStream_t)stream>>>(
-                               plane, reso, xyz_sorted, point_stride, perm, n_points, n_per_batch, out_rows));
+                               plane, reso, xyz_sorted, point_stride, perm, tile_ids, n_points, n_per_batch, out_rows));
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }

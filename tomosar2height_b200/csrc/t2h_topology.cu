@@ -33,6 +33,25 @@ __global__ void xy_keys_kernel(const float* __restrict__ xyz, int64_t n, int64_t
   keys[i] = (int32_t)(b * (int64_t)reso * reso + cell_code((uint32_t)ix, (uint32_t)iy, reso, morton));
 }
 
+// ragged batches: tile b owns the points [offsets[b], offsets[b+1]) of the flat cloud
+__global__ void xy_keys_ragged_kernel(const float* __restrict__ xyz, int64_t n, int64_t stride,
+                                      const int64_t* __restrict__ offsets, int n_tiles, int reso, int morton,
+                                      int32_t* __restrict__ keys) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = n_tiles;  // largest b with offsets[b] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (offsets[mid] <= i) lo = mid; else hi = mid;
+  }
+  const float r = (float)reso;
+  int ix = __float2int_rz(__fmul_rn(xyz[i * stride], r));
+  int iy = __float2int_rz(__fmul_rn(xyz[i * stride + 1], r));
+  ix = min(max(ix, 0), reso - 1);
+  iy = min(max(iy, 0), reso - 1);
+  keys[i] = (int32_t)((int64_t)lo * reso * reso + cell_code((uint32_t)ix, (uint32_t)iy, reso, morton));
+}
+
 __global__ void index_keys_kernel(const int64_t* __restrict__ index, int64_t n, int64_t n_per_batch,
                                   int64_t dim_size, int32_t* __restrict__ keys, int32_t* flag) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,6 +126,19 @@ extern "C" int t2h_xy_keys(const float* xyz, int64_t n_points, int64_t point_str
   if (n_batch * (int64_t)reso * reso > (int64_t)INT32_MAX) return T2H_ERR_UNSUPPORTED_SHAPE;
   if (n_points == 0) return T2H_OK;
   xy_keys_kernel<<<blocks_for(n_points, 256), 256, 0, (cudaStream_t)stream>>>(xyz, n_points, point_stride, n_per_batch, reso, morton, keys);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" int t2h_xy_keys_ragged(const float* xyz, int64_t n_points, int64_t point_stride, const int64_t* offsets,
+                                  int n_tiles, int reso, int morton, int32_t* keys, t2h_stream_t stream) {
+  if (!xyz || !keys || !offsets || n_points < 0 || point_stride < 2 || n_tiles <= 0 || reso <= 0 || reso > 32768)
+    return T2H_ERR_INVALID_ARGUMENT;
+  if (morton && (reso & (reso - 1))) return T2H_ERR_INVALID_ARGUMENT;
+  if ((int64_t)n_tiles * reso * reso > (int64_t)INT32_MAX) return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (n_points == 0) return T2H_OK;
+  xy_keys_ragged_kernel<<<blocks_for(n_points, 256), 256, 0, (cudaStream_t)stream>>>(xyz, n_points, point_stride, offsets,
+                                                                                    n_tiles, reso, morton, keys);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }

@@ -16,7 +16,7 @@ from .. import functional as T
 from ..linear import linear
 from .. import scatter as S
 from ..block import ResnetBlockFC
-from ..topology import Topology
+from ..topology import Topology, RaggedCloud
 from .unet import UNet
 from .alto import UNet as Alto
 
@@ -45,8 +45,12 @@ class LocalPoolPointnet(nn.Module):
         self.scatter = S.scatter_max if scatter_type == 'max' else S.scatter_mean
 
     def forward(self, inputs: torch.Tensor):
-        """inputs (B, N, 3) fp32 CUDA, xy in the open unit square -> {'xy': (B, C, R, R)}."""
-        topo = Topology(inputs, self.reso_plane)
+        """inputs (B, N, 3) fp32 CUDA (or a RaggedCloud of tiles with different point counts), xy in the
+        open unit square -> {'xy': (B, C, R, R)}."""
+        if isinstance(inputs, RaggedCloud):
+            topo = Topology(inputs.points, self.reso_plane, offsets=inputs.offsets)
+        else:
+            topo = Topology(inputs, self.reso_plane)
         level = topo.level(self.reso_plane)
         # xyz rows are stored zero-padded to 4 floats (16-byte rows for TMA); pad fc_pos.weight to match
         pad = topo.xyz_sorted.shape[1] - self.fc_pos.weight.shape[1]

@@ -140,10 +140,11 @@ class _BilinearSample(torch.autograd.Function):
             raise RuntimeError(f"bilinear_sample: unsupported channel count {plane.shape[3]}")
         plane = plane.contiguous()
         C = plane.shape[3]
-        n = level.B * level.N
+        n = level.n_points
         out = torch.empty(n, C, dtype=torch.float32, device=plane.device)
         xyz = level.xyz_sorted
-        call("t2h_bilinear_sample_fwd", ptr(plane), level.reso, C, ptr(xyz), xyz.shape[1], ptr(level.perm), n, level.N, ptr(out))
+        call("t2h_bilinear_sample_fwd", ptr(plane), level.reso, C, ptr(xyz), xyz.shape[1], ptr(level.perm),
+             ptr(level.tile_ids), n, level.N or 1, ptr(out))
         ctx.level = level
         ctx.shape = tuple(plane.shape)
         return out
@@ -211,7 +212,7 @@ def seg_sum(rows, level):
 
 def seg_broadcast(plane, level, mean=False):
     """rows[i] = plane[cell(i)] (divided by the cell count when mean=True)."""
-    return _SegBroadcast.apply(plane, level, mean, level.B * level.N)
+    return _SegBroadcast.apply(plane, level, mean, level.n_points)
 
 
 def bilinear_sample(plane_cl, level):

@@ -39,8 +39,8 @@ def _bytes(name, a):
         rows = _bytes.n_rows
         return 4 * rows * C + 4 * rows + 4 * n_seg * C
     if name == "t2h_bilinear_sample_fwd":
-        reso, C, n, n_per = a[1], a[2], a[6], a[7]
-        return 4 * (n // n_per) * reso * reso * C + 8 * n + 4 * n * C
+        reso, C, n, n_per = a[1], a[2], a[7], a[8]
+        return 4 * max(n // max(n_per, 1), 1) * reso * reso * C + 8 * n + 4 * n * C
     if name == "t2h_bilinear_sample_bwd":
         reso, C, n_seg = a[2], a[3], a[8]  # (workspace args follow)
         rows = _bytes.n_rows

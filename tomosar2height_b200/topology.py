@@ -12,6 +12,27 @@ def _is_pow2(v: int) -> bool:
     return v > 0 and (v & (v - 1)) == 0
 
 
+class RaggedCloud:
+    """A batch of tiles with DIFFERENT point counts: flat ``points`` (P, 3) fp32 + ``offsets`` (B+1,) int64,
+    tile b owning points[offsets[b]:offsets[b+1]] (xy normalised to the open unit square per tile).
+    The reference is stuck at batch 1 because its dense (B, N, 3) collate cannot hold such tiles
+    (conf/model/tomosar2height.yaml:40); every kernel here works on flat rows + cell keys, so ragged
+    batches cost nothing extra.  Pass it as ``input_cloud``."""
+
+    def __init__(self, points: torch.Tensor, offsets: torch.Tensor):
+        self.points, self.offsets = points, offsets
+
+    @classmethod
+    def from_list(cls, tiles):
+        sizes = torch.tensor([0] + [int(t.shape[0]) for t in tiles], dtype=torch.int64)
+        points = torch.cat([t.reshape(-1, t.shape[-1]) for t in tiles], 0).contiguous()
+        return cls(points, sizes.cumsum(0).to(points.device))
+
+    @property
+    def n_tiles(self):
+        return self.offsets.numel() - 1
+
+
 class CellLevel:
     """What the segment / sampling kernels need for one plane resolution ``reso``.
 
@@ -19,7 +40,8 @@ class CellLevel:
     otherwise it maps sorted position -> row.
     """
 
-    __slots__ = ("topo", "reso", "shift", "morton", "perm", "tie", "cell_start", "xyz_sorted", "B", "N", "n_seg")
+    __slots__ = ("topo", "reso", "shift", "morton", "perm", "tie", "cell_start", "xyz_sorted", "B", "N", "n_seg",
+                 "n_points", "tile_ids")
 
     def __init__(self, topo, reso, shift, perm, tie=None):
         self.topo = topo
@@ -34,10 +56,12 @@ class CellLevel:
         self.xyz_sorted = topo.xyz_sorted
         self.B, self.N = topo.B, topo.N
         self.n_seg = topo.B * reso * reso
+        self.n_points = topo.n_points
+        self.tile_ids = topo.tile_ids  # None for dense (B, N, 3) batches
 
     @property
     def n_rows(self):
-        return self.B * self.N
+        return self.n_points
 
 
 class Topology:
@@ -51,24 +75,40 @@ class Topology:
       morton      bool          : Morton keys (power-of-two R) -> coarser levels share the sort
     """
 
-    def __init__(self, xyz: torch.Tensor, reso: int):
+    def __init__(self, xyz: torch.Tensor, reso: int, offsets: torch.Tensor = None):
+        """xyz (B, N, >=2) for a dense batch, or -- with ``offsets`` (B+1,) int64 on the device -- the flat
+        (P, >=2) cloud of a RAGGED batch whose tile b owns the points [offsets[b], offsets[b+1])."""
         _lib.require_cuda_f32(xyz, "Topology(xyz)")
-        if xyz.dim() != 3 or xyz.shape[2] < 2:
-            raise RuntimeError(f"Topology: expected (B, N, >=2) points, got {tuple(xyz.shape)}")
-        if xyz.shape[2] > 4:
+        ragged = offsets is not None
+        if xyz.dim() != (2 if ragged else 3) or xyz.shape[-1] < 2:
+            raise RuntimeError(f"Topology: expected {'(P, >=2)' if ragged else '(B, N, >=2)'} points, got {tuple(xyz.shape)}")
+        if xyz.shape[-1] > 4:
             raise RuntimeError("Topology: at most 4 coordinates per point are supported")
-        if xyz.shape[2] != 4:
-            xyz = torch.nn.functional.pad(xyz, (0, 4 - xyz.shape[2]))
+        if xyz.shape[-1] != 4:
+            xyz = torch.nn.functional.pad(xyz, (0, 4 - xyz.shape[-1]))
         xyz = xyz.contiguous()
-        self.B, self.N, self.D = xyz.shape
+        self.D = 4
         self.reso = int(reso)
         self.morton = _is_pow2(self.reso)
-        n = self.B * self.N
-        n_keys = self.B * self.reso * self.reso
         dev = xyz.device
-        keys = torch.empty(n, dtype=torch.int32, device=dev)
-        _lib.call("t2h_xy_keys", _lib.ptr(xyz), n, self.D, self.N, self.reso, int(self.morton), _lib.ptr(keys))
+        if ragged:
+            if offsets.dtype != torch.int64 or not offsets.is_cuda or offsets.dim() != 1 or offsets.numel() < 2:
+                raise RuntimeError("Topology: offsets must be a CUDA int64 vector of length B + 1")
+            self.B, self.N = offsets.numel() - 1, None
+            n = xyz.shape[0]
+            keys = torch.empty(n, dtype=torch.int32, device=dev)
+            _lib.call("t2h_xy_keys_ragged", _lib.ptr(xyz), n, self.D, _lib.ptr(offsets.contiguous()), self.B, self.reso,
+                      int(self.morton), _lib.ptr(keys))
+        else:
+            self.B, self.N = xyz.shape[0], xyz.shape[1]
+            n = self.B * self.N
+            keys = torch.empty(n, dtype=torch.int32, device=dev)
+            _lib.call("t2h_xy_keys", _lib.ptr(xyz), n, self.D, self.N, self.reso, int(self.morton), _lib.ptr(keys))
+        self.n_points = n
+        n_keys = self.B * self.reso * self.reso
         self.keys_sorted, self.perm, self.cell_start = sort_keys(keys, n_keys)
+        self.tile_ids = (self.keys_sorted // (self.reso * self.reso)).to(torch.int32) if ragged else None
+        self.offsets = offsets
         self.xyz_sorted = torch.empty(n, self.D, dtype=torch.float32, device=dev)
         _lib.call("t2h_gather_rows", _lib.ptr(xyz.view(n, self.D)), _lib.ptr(self.perm), n, self.D,
                   _lib.ptr(self.xyz_sorted))
@@ -96,6 +136,8 @@ class Topology:
             return CellLevel(self, reso, shift, None if rows_sorted else self.perm)
         key = (reso, rows_sorted)
         if key not in self._sub:
+            if rows_sorted and self.N is None:
+                raise RuntimeError("Topology.level: ragged batches need power-of-two plane resolutions")
             if rows_sorted:
                 sub = Topology(self.xyz_sorted.view(self.B, self.N, self.D), reso)
             else:
@@ -149,7 +191,8 @@ def scatter_rows(rows: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
 class IndexLevel:
     """Level descriptor for an arbitrary (B, 1, N) int64 index (torch_scatter-style API)."""
 
-    __slots__ = ("reso", "shift", "morton", "perm", "tie", "cell_start", "xyz_sorted", "B", "N", "n_seg", "dim_size")
+    __slots__ = ("reso", "shift", "morton", "perm", "tie", "cell_start", "xyz_sorted", "B", "N", "n_seg", "dim_size",
+                 "n_points", "tile_ids")
 
     def __init__(self, index: torch.Tensor, dim_size: int, check: bool = True):
         if not index.is_cuda or index.dtype != torch.int64:
@@ -168,3 +211,4 @@ class IndexLevel:
         self.xyz_sorted, self.tie = None, None
         self.B, self.N, self.dim_size = B, N, dim_size
         self.n_seg = B * dim_size
+        self.n_points, self.tile_ids = n, None
