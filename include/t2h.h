@@ -141,6 +141,26 @@ int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const float* x2, int6
                    int relu_in, const float* mask, int64_t ld_mask, const float* residual,
                    int64_t ld_res, float* out, int64_t ld_out, t2h_stream_t stream);
 
+/* 3xFP16 flavour of the same GEMM for wide layers (n_out > 64): kind::f16 tensor-core passes run at twice
+ * the TF32 rate.  Both operands are scaled by a power of two taken from their maximum magnitude (scaled
+ * maximum in [2^14, 2^15), exact), split into fp16 hi = rn(v), lo = rn(v - hi), multiplied as
+ * lo*hi + hi*lo + hi*hi with fp32 accumulation and un-scaled in the epilogue: 2^-22 relative per product,
+ * plus an absolute floor of 2^-40 of the operand maximum for entries that are tiny against it.
+ *   t2h_absmax:     *slot = bit pattern of max |[x1 | x2]| (x2 nullable / k2 = 0), pre-activation
+ *   t2h_split_f16:  w (n fp32 values, n even) -> fp16 hi / lo under the scale of *absmax
+ *   t2h_linear_fwd_f16: as t2h_linear_fwd with the fp16 weight split, (k1 + k2) % 8 == 0; out_absmax
+ *                   (nullable) receives max |out|, i.e. the x_absmax of a following layer, for free */
+int t2h_absmax(const float* x1, int64_t ld_x1, int k1, const float* x2, int64_t ld_x2, int k2,
+               int64_t rows, uint32_t* slot, t2h_stream_t stream);
+int t2h_split_f16(const float* w, int64_t n, const uint32_t* absmax, uint16_t* hi, uint16_t* lo,
+                  t2h_stream_t stream);
+int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const float* x2, int64_t ld_x2, int k2,
+                       int64_t rows, const uint32_t* x_absmax, const uint16_t* w_hi,
+                       const uint16_t* w_lo, const uint32_t* w_absmax, int n_out, const float* bias,
+                       int relu_in, const float* mask, int64_t ld_mask, const float* residual,
+                       int64_t ld_res, float* out, int64_t ld_out, uint32_t* out_absmax,
+                       t2h_stream_t stream);
+
 /* weight gradient grad_w[n, k] = sum_r grad_out[r, n] * act(x[r, k]) and (grad_b nullable) bias gradient
  * grad_b[n] = sum_r grad_out[r, n] (autograd backward of nn.Linear): 3xTF32 tcgen05 GEMM over
  * MN-major operands (grad_out^T through tensor memory), split over the rows, partials summed in a

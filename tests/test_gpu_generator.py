@@ -41,4 +41,6 @@ def test_scene_generation_matches_oracle():
     from tomosar2height_b200.parallel import shard_tiles
     parts = [gen.generate(pts.cuda(), tile_range=shard_tiles(len(gen.anchors), rk, 2)) for rk in range(2)]
     merged = gen.finalize(parts[0][0] + parts[1][0], parts[0][1] + parts[1][1])
-    assert torch.allclose(merged[covered.cuda()], dsm[covered.cuda()], rtol=1e-9, atol=1e-9)
+    # not bitwise: the fp16x3 GEMMs scale their operands by the maximum of the whole batch, so a tile's result
+    # depends (at fp32 rounding level) on which other tiles share its batch
+    assert (merged[covered.cuda()] - dsm[covered.cuda()]).abs().max().item() <= 1e-5 * scale.item()

@@ -49,6 +49,11 @@ struct LinearArgs {
   int tiles_x;             // patches per plane row  (W / CONV_TW)
   int tiles_per_img;       // patches per plane      ((H / CONV_TH) * tiles_x)
   int cin_chunks;          // Cin / 32
+  // fp16x3 mode: device words holding the bit pattern of max|x| (pre-ReLU) and max|w| (t2h_absmax); both
+  // operands are scaled by a power of two that brings the maximum just below 2^15 before the fp16 split
+  const uint32_t* x_absmax;
+  const uint32_t* w_absmax;
+  uint32_t* out_absmax;    // nullable: max |out| is merged into this word (operand scale of the next fp16 GEMM)
 };
 constexpr int CONV_TW = 16, CONV_TH = 8;  // 16 x 8 pixels = 128 GEMM rows
 
@@ -289,6 +294,361 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_d, S::TMEM_COLS);
 }
 
+
+// ---- persistent variant (wide layers) ----------------------------------------------------------------
+// One CTA per SM walks the tile list (N-tile fastest, stride gridDim.x).  Roles: warp 0 TMA producer,
+// warp 1 MMA issuer, warps 2-9 operand transform (split x -> TMEM), warps 10-17 epilogue.  The fp32
+// accumulator is DOUBLE-BUFFERED in tensor memory (2 x 128 columns) and the stage ring runs across tile
+// boundaries, so tile i+1 is loaded, split and multiplied while the epilogue warps drain, post-process and
+// TMA-store tile i: the ~6 us of per-tile prologue/epilogue that the one-tile-per-CTA kernel exposes
+// (TMEM allocation, barrier setup, first-load latency, store drain) is paid once per SM or hidden.
+// TMEM: 2 x 128 (accumulators) + 4 x 64 (split A stages) = all 512 columns.
+constexpr int P_BLOCK_N = 128;
+constexpr int P_THREADS = 576;  // producer, MMA, 2 x 4 transform warps, 2 x 4 epilogue warps
+// F16 = false (3xTF32): a stage is one 32-wide K chunk (x fp32 16 KB | w hi 16 KB | w lo 16 KB), 4 stages; the
+//   two transform groups take alternate stages (even stage count: a waiter must see every phase of a barrier).
+// F16 = true (3xFP16): a stage is 64 K elements (two fp32 x boxes of 16 KB | w hi fp16 16 KB | w lo fp16 16 KB),
+//   3 stages; transform group g splits box g of every stage.  The split x operand is packed two fp16 per
+//   32-bit TMEM column, so a stage again occupies 64 columns (32 hi + 32 lo).
+template <bool F16>
+struct PSmem {
+  static constexpr int STAGES = F16 ? 3 : 4;
+  static constexpr int X_BYTES = (F16 ? 2 : 1) * A_BYTES;
+  static constexpr int W_BYTES = F16 ? P_BLOCK_N * 64 * 2 : P_BLOCK_N * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = X_BYTES + 2 * W_BYTES;        // x raw | w hi | w lo
+  static constexpr int STAGING_BYTES = 2 * A_BYTES;                // epilogue staging: two 32-column blocks at a time
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int A_COL0 = 2 * P_BLOCK_N;
+};
+
+// power-of-two operand scale from the bit pattern of max|v|: 2^e with e = 14 - floor(log2 max), so that the
+// scaled maximum lies in [2^14, 2^15) (fp16 overflows at 65504); |e| <= 63 (maxima between 2^-49 and 2^77)
+__device__ __forceinline__ int f16_scale_exp(uint32_t absmax_bits) {
+  const int biased = (int)((absmax_bits >> 23) & 0xFF);
+  if (biased == 0) return 0;  // zero / denormal maximum: nothing to scale
+  int e = 14 - (biased - 127);
+  return e > 63 ? 63 : (e < -63 ? -63 : e);  // two such scales multiply to a representable float
+}
+__device__ __forceinline__ float pow2f(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
+
+template <bool F16>
+__global__ void __launch_bounds__(P_THREADS, 1)
+linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
+                                const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                                const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_aux,
+                                const LinearArgs p, const int64_t n_tiles_total) {
+  using S = PSmem<F16>;
+  constexpr int STAGES = S::STAGES, BLOCK_N = P_BLOCK_N;
+  // pipeline steps per tile: 32-wide chunks (tf32) or pairs of them (fp16)
+  const int n_steps = F16 ? (p.k_chunks + 1) / 2 : p.k_chunks;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t staging = base + STAGES * S::STAGE_BYTES;
+  uint8_t* staging_ptr = base_ptr + STAGES * S::STAGE_BYTES;
+  const uint32_t bars = staging + S::STAGING_BYTES;
+  auto full_tma = [&](int s) { return bars + 8u * s; };
+  auto full_ab = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto acc_full = [&](int a) { return bars + 8u * (3 * STAGES + a); };
+  auto acc_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
+  const uint32_t aux_bar = bars + 8u * (3 * STAGES + 4);
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(staging_ptr + S::STAGING_BYTES + 8 * (3 * STAGES + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.n_out + BLOCK_N - 1) / BLOCK_N;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_tma(s), 1);
+      mbar_init(full_ab(s), F16 ? 256 : 128);
+      mbar_init(empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), 256);
+    }
+    mbar_init(aux_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_x1);
+    tma_prefetch_desc(&tm_whi);
+    tma_prefetch_desc(&tm_wlo);
+    tma_prefetch_desc(&tm_out);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // tile -> coordinates
+  auto decode = [&](int64_t tile, int& m0, int& n0, int& img, int& px0, int& py0) {
+    const int m_idx = (int)(tile / n_tiles);
+    m0 = m_idx * BLOCK_M;
+    n0 = (int)(tile % n_tiles) * BLOCK_N;
+    img = px0 = py0 = 0;
+    if (p.conv) {
+      img = m_idx / p.tiles_per_img;
+      const int rem = m_idx - img * p.tiles_per_img;
+      py0 = (rem / p.tiles_x) * CONV_TH;
+      px0 = (rem % p.tiles_x) * CONV_TW;
+    }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int64_t it = 0;  // running chunk counter across tiles
+      for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        int m0, n0, img, px0, py0;
+        decode(tile, m0, n0, img, px0, py0);
+        for (int kc = 0; kc < n_steps; ++kc, ++it) {
+          const int s = (int)(it % STAGES);
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(empty(s), ph ^ 1);
+          const uint32_t stage = base + s * S::STAGE_BYTES;
+          mbar_arrive_expect_tx(full_tma(s), S::X_BYTES + 2 * S::W_BYTES);
+          auto load_x = [&](uint32_t dst, int c) {  // 32-wide chunk c of the (concatenated / im2col) K axis
+            if (p.conv) {
+              const int tap = c / p.cin_chunks, cc = c - tap * p.cin_chunks;
+              // chunks past the end (odd chunk count in fp16 mode) read outside the channel axis: zero fill
+              tma_load_4d(dst, &tm_x1, full_tma(s), cc * BLOCK_K + (tap >= 9 ? (1 << 20) : 0), px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
+            } else if (c < p.k1_chunks) tma_load_2d(dst, &tm_x1, full_tma(s), c * BLOCK_K, m0);
+            else                        tma_load_2d(dst, &tm_x2, full_tma(s), (c - p.k1_chunks) * BLOCK_K + (c >= p.k_chunks ? (1 << 20) : 0), m0);
+          };
+          if (F16) {
+            load_x(stage, 2 * kc);
+            load_x(stage + A_BYTES, 2 * kc + 1);
+            tma_load_2d(stage + S::X_BYTES, &tm_whi, full_tma(s), kc * 64, n0);
+            tma_load_2d(stage + S::X_BYTES + S::W_BYTES, &tm_wlo, full_tma(s), kc * 64, n0);
+          } else {
+            load_x(stage, kc);
+            tma_load_2d(stage + S::X_BYTES, &tm_whi, full_tma(s), kc * BLOCK_K, n0);
+            tma_load_2d(stage + S::X_BYTES + S::W_BYTES, &tm_wlo, full_tma(s), kc * BLOCK_K, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(BLOCK_M, BLOCK_N, 0, 0) : make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
+      int64_t it = 0, local = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
+        const int acc = (int)(local & 1);
+        const uint32_t acc_ph = (uint32_t)((local >> 1) & 1);
+        mbar_wait(acc_empty(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kc = 0; kc < n_steps; ++kc, ++it) {
+          const int s = (int)(it % STAGES);
+          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+          mbar_wait(full_tma(s), ph);
+          mbar_wait(full_ab(s), ph);
+          tc_fence_after();
+          const uint32_t stage = base + s * S::STAGE_BYTES;
+          // every k-step advances 32 bytes along the swizzled 128-byte weight row (8 tf32 or 16 fp16) and
+          // 8 TMEM columns of the split x operand; small terms first
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t koff = k * 32;
+            const uint64_t b_hi = make_smem_desc(stage + S::X_BYTES + koff, 16, 1024);
+            const uint64_t b_lo = make_smem_desc(stage + S::X_BYTES + S::W_BYTES + koff, 16, 1024);
+            const uint32_t a_hi = tmem_base + S::A_COL0 + s * 64 + k * 8;
+            const uint32_t a_lo = a_hi + 32;
+            if (F16) {
+              mma_f16_ts(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
+              mma_f16_ts(tmem_d, a_hi, b_lo, idesc, 1);
+              mma_f16_ts(tmem_d, a_hi, b_hi, idesc, 1);
+            } else {
+              mma_tf32_ts(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
+              mma_tf32_ts(tmem_d, a_hi, b_lo, idesc, 1);
+              mma_tf32_ts(tmem_d, a_hi, b_hi, idesc, 1);
+            }
+          }
+          mma_commit(empty(s));
+        }
+        mma_commit(acc_full(acc));
+      }
+    }
+  } else if (warp < 10) {
+    // ---- operand transform: row t of every x chunk -> (hi | lo) in TMEM; two warp groups take alternate
+    //      chunks so that the split keeps pace with the MMA pipe of a whole SM ------------------------
+    const int t = (warp & 3) * 32 + lane;
+    const int group = (warp - 2) >> 2;
+    const float sx = F16 ? pow2f(f16_scale_exp(*p.x_absmax)) : 1.f;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      for (int kc = 0; kc < n_steps; ++kc, ++it) {
+        const int s = (int)(it % STAGES);
+        if (!F16 && (s & 1) != group) continue;
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(full_tma(s), ph);
+        const uint32_t a_dst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + S::A_COL0 + s * 64;
+        if (F16) {
+          const float* x_row = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES + group * A_BYTES + t * 128);
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = *reinterpret_cast<const float4*>(x_row + ((j ^ (t & 7)) * 4));
+            if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            v.x *= sx; v.y *= sx; v.z *= sx; v.w *= sx;
+            split_f16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
+            split_f16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+          }
+          tmem_st_32x16(a_dst + group * 16, hi);
+          tmem_st_32x16(a_dst + 32 + group * 16, lo);
+        } else {
+          const float* x_row = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES + t * 128);
+          float hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = *reinterpret_cast<const float4*>(x_row + ((j ^ (t & 7)) * 4));
+            if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            split_tf32(v.x, hi[4 * j], lo[4 * j]); split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+            split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+          }
+          tmem_st_32x32(a_dst, hi);
+          tmem_st_32x32(a_dst + 32, lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(full_ab(s));
+      }
+    }
+  } else {
+    // ---- epilogue warps 10-17: drain accumulator `acc`, release it, post-process, TMA store ------------
+    // Two warps per TMEM lane quarter (and per SM sub-partition): in each of the two rounds of a tile,
+    // group eh = 0/1 handles the 32-column block 2 * round + eh through its own 16 KB staging slot.
+    const int quarter = warp & 3;  // warps 10..17 -> TMEM lane quarters 2,3,0,1,2,3,0,1
+    const int eh = (warp - 10) >> 2;
+    const int t = quarter * 32 + lane;
+    const bool leader = (warp == 10 && lane == 0);
+    // fp16 mode: undo the two power-of-two operand scales (|exponent| <= 63 each, so the product is a float)
+    const float inv = F16 ? pow2f(-(f16_scale_exp(*p.x_absmax) + f16_scale_exp(*p.w_absmax))) : 1.f;
+    const int epi_mode = (p.mask && p.residual) || (p.aux_kind == 0 && (p.mask || p.residual)) ? 3 : p.aux_kind;
+    uint32_t aux_phase = 0;
+    float out_max = 0.f;
+    int64_t local = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
+      int m0, n0, img, px0, py0;
+      decode(tile, m0, n0, img, px0, py0);
+      const int acc = (int)(local & 1);
+      const uint32_t acc_ph = (uint32_t)((local >> 1) & 1);
+      const int n_blocks = min(BLOCK_N / 32, (p.n_out - n0 + 31) / 32);
+      const int64_t row = (int64_t)m0 + t;
+      const bool row_ok = row < p.rows;
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int round = 0; round < 2; ++round) {
+        const int cb0 = round * 2, cb1 = min(cb0 + 2, n_blocks);
+        if (cb0 < n_blocks) {
+          const int cb = cb0 + eh;
+          const bool active = cb < cb1;
+          // both staging slots are free: the leader waited for the previous stores' reads before the closing barrier
+          if (p.aux_kind) {
+            if (leader) {
+              mbar_arrive_expect_tx(aux_bar, (uint32_t)(cb1 - cb0) * A_BYTES);
+              for (int c = cb0; c < cb1; ++c) {
+                if (p.conv) tma_load_4d(staging + (c - cb0) * A_BYTES, &tm_aux, aux_bar, n0 + c * 32, px0, py0, img);
+                else tma_load_2d(staging + (c - cb0) * A_BYTES, &tm_aux, aux_bar, n0 + c * 32, m0);
+              }
+            }
+            mbar_wait(aux_bar, aux_phase);
+            aux_phase ^= 1;
+          }
+          if (round == 0) {
+            mbar_wait(acc_full(acc), acc_ph);
+            tc_fence_after();
+          }
+          if (active) {
+            const int nb = n0 + cb * 32;
+            // the bias slice first (one broadcast line per load, in flight while tensor memory is read); columns
+            // past n_out are clipped by the TMA store, so their index is only clamped to stay in bounds
+            float4 b[8];
+            if (p.bias) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) b[g] = ld4(p.bias + min(nb + g * 4, p.n_out - 4));
+            }
+            float v[32];
+            tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32), v);
+            float* srow = reinterpret_cast<float*>(staging_ptr + eh * A_BYTES + t * 128);
+            if (F16) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= inv;
+            }
+            if (p.bias) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) { v[4 * g] += b[g].x; v[4 * g + 1] += b[g].y; v[4 * g + 2] += b[g].z; v[4 * g + 3] += b[g].w; }
+            }
+            if (epi_mode == 1) {         // ReLU mask staged by TMA (input-gradient GEMM)
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 m = *reinterpret_cast<const float4*>(srow + ((g ^ (t & 7)) * 4));
+                v[4 * g] = m.x > 0.f ? v[4 * g] : 0.f; v[4 * g + 1] = m.y > 0.f ? v[4 * g + 1] : 0.f;
+                v[4 * g + 2] = m.z > 0.f ? v[4 * g + 2] : 0.f; v[4 * g + 3] = m.w > 0.f ? v[4 * g + 3] : 0.f;
+              }
+            } else if (epi_mode == 2) {  // residual staged by TMA
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 r = *reinterpret_cast<const float4*>(srow + ((g ^ (t & 7)) * 4));
+                v[4 * g] += r.x; v[4 * g + 1] += r.y; v[4 * g + 2] += r.z; v[4 * g + 3] += r.w;
+              }
+            } else if (epi_mode == 3) {  // general case: mask and residual together, read from global memory
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const int n = min(nb + g * 4, p.n_out - 4);  // clipped columns: any in-bounds address
+                if (p.mask) {
+                  float4 m;
+                  if (p.aux_kind == 1) m = *reinterpret_cast<const float4*>(srow + ((g ^ (t & 7)) * 4));
+                  else m = row_ok ? ld4(p.mask + row * p.ld_mask + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  v[4 * g] = m.x > 0.f ? v[4 * g] : 0.f; v[4 * g + 1] = m.y > 0.f ? v[4 * g + 1] : 0.f;
+                  v[4 * g + 2] = m.z > 0.f ? v[4 * g + 2] : 0.f; v[4 * g + 3] = m.w > 0.f ? v[4 * g + 3] : 0.f;
+                }
+                if (p.residual) {
+                  const float4 r = row_ok ? *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  v[4 * g] += r.x; v[4 * g + 1] += r.y; v[4 * g + 2] += r.z; v[4 * g + 3] += r.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(srow + ((g ^ (t & 7)) * 4)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            if (p.out_absmax && row_ok) {  // rows / columns outside the matrix hold bias-only garbage: skip them
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (nb + g * 4 < p.n_out)
+                  out_max = fmaxf(fmaxf(out_max, fmaxf(fabsf(v[4 * g]), fabsf(v[4 * g + 1]))), fmaxf(fabsf(v[4 * g + 2]), fabsf(v[4 * g + 3])));
+            }
+          }
+          if (round == 1 || cb1 == n_blocks) {
+            // the accumulator has been read completely (tcgen05.ld waited): hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(acc_empty(acc));
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+          if (leader) {
+            for (int c = cb0; c < cb1; ++c) {
+              if (p.conv) tma_store_4d(&tm_out, staging + (c - cb0) * A_BYTES, n0 + c * 32, px0, py0, img);
+              else tma_store_2d(&tm_out, staging + (c - cb0) * A_BYTES, n0 + c * 32, m0);
+            }
+            tma_store_commit_and_wait();  // staging has been read: it may be refilled
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+    }
+    if (p.out_absmax) {
+      uint32_t b = __float_as_uint(out_max);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+      if (lane == 0 && b) atomicMax(p.out_absmax, b);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
 
 // ---- weight gradient: dW[n, k] = sum_r g[r, n] * act(x[r, k]),  db[n] = sum_r g[r, n] ---------------
 // The reduction runs over the ROWS, so the operands are "MN-major".
@@ -589,6 +949,55 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, int64_t n, float*
   lo[i] = l;
 }
 
+// max |x| over a (rows, k) matrix with row pitch ld, as the bit pattern of the (non-negative) float, merged into
+// *slot with atomicMax (unsigned order == float order for non-negative values; NaN sorts above infinity)
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, int64_t ld, int k4, int64_t n4, uint32_t* __restrict__ slot) {
+  float m = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool flat = (ld == (int64_t)k4 * 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = i + u * stride;
+      if (j < n4) {
+        const int64_t off = flat ? j * 4 : (j / k4) * ld + (j % k4) * 4;
+        v[u] = __ldg(reinterpret_cast<const float4*>(x + off));
+      } else v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      // integer max of the magnitudes' bit patterns keeps NaN visible (fmaxf would drop it)
+      m = __uint_as_float(max(max(__float_as_uint(fabsf(v[u].x)), __float_as_uint(fabsf(v[u].y))),
+                              max(max(__float_as_uint(fabsf(v[u].z)), __float_as_uint(fabsf(v[u].w))), __float_as_uint(m))));
+    }
+  }
+  uint32_t b = __float_as_uint(m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+  __shared__ uint32_t warp_max[8];
+  if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    b = warp_max[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffu, b, o));
+    if (threadIdx.x == 0 && b) atomicMax(slot, b);
+  }
+}
+
+__global__ void split_f16_kernel(const float* __restrict__ w, int64_t n2, const uint32_t* __restrict__ absmax,
+                                 uint32_t* __restrict__ hi, uint32_t* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const float sc = pow2f(f16_scale_exp(*absmax));
+  const float2 v = reinterpret_cast<const float2*>(w)[i];
+  uint32_t h, l;
+  split_f16x2(v.x * sc, v.y * sc, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -618,6 +1027,19 @@ static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 2-D fp16 weight matrix [outer, inner] (K contiguous), box [box_outer, 64] = 128-byte swizzle rows
+static bool make_map_f16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // channels-last plane (B, H, W, C) as a 4-D tensor (C, W, H, B); box = 32 channels x bw x bh pixels of one image
 static bool make_map_4d(CUtensorMap* map, const float* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B,
                         uint32_t box_c, uint32_t bw, uint32_t bh, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
@@ -633,6 +1055,26 @@ static bool make_map_4d(CUtensorMap* map, const float* ptr, uint64_t C, uint64_t
 }
 
 struct PlaneGeom { int B, H, W; };  // conv mode only
+
+template <bool F16>
+static int launch_linear_persistent(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& whi, const CUtensorMap& wlo,
+                                    const CUtensorMap& mout, const CUtensorMap& maux, const LinearArgs& args,
+                                    cudaStream_t stream) {
+  auto kern = linear_x3_persistent_kernel<F16>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem<F16>::TOTAL) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return T2H_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t tiles = ((args.rows + BLOCK_M - 1) / BLOCK_M) * ((args.n_out + P_BLOCK_N - 1) / P_BLOCK_N);
+  const unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
+  kern<<<grid, P_THREADS, PSmem<F16>::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args, tiles);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
 
 template <int BLOCK_N, bool A_TMEM, int STAGES_>
 static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const float* w_hi, const float* w_lo, int k_total,
@@ -650,6 +1092,10 @@ static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const flo
     maux = mout;
     if (args.aux_kind == 1 && !make_map(&maux, args.mask, args.n_out, args.rows, args.ld_mask, 32, BLOCK_M)) return T2H_ERR_CUDA;
     if (args.aux_kind == 2 && !make_map(&maux, args.residual, args.n_out, args.rows, args.ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
+  }
+  if (BLOCK_N == 128 && A_TMEM) {
+    static const int one_tile = []() { const char* e = getenv("T2H_LINEAR_NONPERSISTENT"); return e ? atoi(e) : 0; }();  // ablation
+    if (!one_tile) return launch_linear_persistent<false>(x1, x2, whi, wlo, mout, maux, args, stream);
   }
   auto kern = linear_tf32x3_kernel<BLOCK_N, A_TMEM, STAGES_>;
   static bool configured = false;  // idempotent attribute, racing threads set the same value
@@ -707,6 +1153,7 @@ extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const floa
   a.residual = residual; a.ld_res = ld_res; a.out = out; a.ld_out = ld_out;
   a.aux_kind = mask ? 1 : (residual ? 2 : 0);
   a.conv = 0; a.tiles_x = a.tiles_per_img = a.cin_chunks = 0;
+  a.x_absmax = a.w_absmax = nullptr; a.out_absmax = nullptr;
   const int k_total = k1 + k2;
   cudaStream_t s = (cudaStream_t)stream;
   static const int ss_only = []() { const char* e = getenv("T2H_LINEAR_SS"); return e ? atoi(e) : 0; }();  // ablation
@@ -720,6 +1167,80 @@ extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const floa
   return launch_linear<128, true, 2>(m1, m2, w_hi, w_lo, k_total, a, s);
 }
 
+
+extern "C" int t2h_absmax(const float* x1, int64_t ld_x1, int k1, const float* x2, int64_t ld_x2, int k2, int64_t rows,
+                          uint32_t* slot, t2h_stream_t stream) {
+  if (!x1 || !slot || rows < 0 || k1 <= 0 || k2 < 0 || (k2 > 0 && !x2)) return T2H_ERR_INVALID_ARGUMENT;
+  if ((k1 % 4) || (k2 % 4) || (ld_x1 % 4) || (k2 > 0 && (ld_x2 % 4))) return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)x1 | (uintptr_t)x2) & 15) return T2H_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(slot, 0, sizeof(uint32_t), s) != cudaSuccess) { (void)cudaGetLastError(); return T2H_ERR_CUDA; }
+  const float* xs[2] = {x1, x2};
+  const int64_t lds[2] = {ld_x1, ld_x2};
+  const int ks[2] = {k1, k2};
+  for (int i = 0; i < 2; ++i) {
+    if (ks[i] == 0 || rows == 0) continue;
+    const int64_t n4 = rows * (ks[i] / 4);
+    int64_t blocks = (n4 + 1023) / 1024;  // four float4 per thread and sweep
+    if (blocks > 8 * kSMs) blocks = 8 * kSMs;
+    absmax_kernel<<<(unsigned)blocks, 256, 0, s>>>(xs[i], lds[i], ks[i] / 4, n4, slot);
+    T2H_CHECK_LAUNCH();
+  }
+  return T2H_OK;
+}
+
+extern "C" int t2h_split_f16(const float* w, int64_t n, const uint32_t* absmax, uint16_t* hi, uint16_t* lo, t2h_stream_t stream) {
+  if (!w || !absmax || !hi || !lo || n < 0) return T2H_ERR_INVALID_ARGUMENT;
+  if (n % 2) return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)w & 7) || (((uintptr_t)hi | (uintptr_t)lo) & 3)) return T2H_ERR_INVALID_ARGUMENT;
+  if (n == 0) return T2H_OK;
+  split_f16_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w, n / 2, absmax, reinterpret_cast<uint32_t*>(hi), reinterpret_cast<uint32_t*>(lo));
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const float* x2, int64_t ld_x2, int k2,
+                                  int64_t rows, const uint32_t* x_absmax, const uint16_t* w_hi, const uint16_t* w_lo,
+                                  const uint32_t* w_absmax, int n_out, const float* bias, int relu_in, const float* mask,
+                                  int64_t ld_mask, const float* residual, int64_t ld_res, float* out, int64_t ld_out,
+                                  uint32_t* out_absmax, t2h_stream_t stream) {
+  if (!x1 || !w_hi || !w_lo || !x_absmax || !w_absmax || !out || rows < 0 || k1 <= 0 || k2 < 0 || n_out <= 0)
+    return T2H_ERR_INVALID_ARGUMENT;
+  if (k2 > 0 && !x2) return T2H_ERR_INVALID_ARGUMENT;
+  // TMA: 16-byte aligned bases and row pitches (fp16 weight rows: K % 8); a second source starts on a chunk boundary
+  if ((k1 % 4) || (k2 % 4) || ((k1 + k2) % 8) || (ld_x1 % 4) || (k2 > 0 && ((ld_x2 % 4) || (k1 % BLOCK_K))) || (n_out % 4) ||
+      (ld_out % 4) || (residual && (ld_res % 4)) || (mask && (ld_mask % 4)))
+    return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)out | (uintptr_t)bias |
+       (uintptr_t)mask | (uintptr_t)residual) & 15)
+    return T2H_ERR_INVALID_ARGUMENT;
+  if (rows == 0) return T2H_OK;
+  CUtensorMap m1, m2, whi, wlo, mout, maux;
+  if (!make_map(&m1, x1, k1, rows, ld_x1, BLOCK_K, BLOCK_M)) return T2H_ERR_CUDA;
+  if (k2 > 0) { if (!make_map(&m2, x2, k2, rows, ld_x2, BLOCK_K, BLOCK_M)) return T2H_ERR_CUDA; }
+  else m2 = m1;
+  const int k_total = k1 + k2;
+  if (!make_map_f16(&whi, w_hi, k_total, n_out, P_BLOCK_N) || !make_map_f16(&wlo, w_lo, k_total, n_out, P_BLOCK_N)) return T2H_ERR_CUDA;
+  LinearArgs a;
+  a.rows = rows; a.n_out = n_out;
+  a.k1_chunks = (k1 + BLOCK_K - 1) / BLOCK_K;
+  a.k_chunks = a.k1_chunks + (k2 + BLOCK_K - 1) / BLOCK_K;
+  a.relu_in = relu_in; a.bias = bias; a.mask = mask; a.ld_mask = ld_mask;
+  a.residual = residual; a.ld_res = ld_res; a.out = out; a.ld_out = ld_out;
+  a.aux_kind = mask ? 1 : (residual ? 2 : 0);
+  a.conv = 0; a.tiles_x = a.tiles_per_img = a.cin_chunks = 0;
+  a.x_absmax = x_absmax; a.w_absmax = w_absmax; a.out_absmax = out_absmax;
+  if (out_absmax && cudaMemsetAsync(out_absmax, 0, sizeof(uint32_t), (cudaStream_t)stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return T2H_ERR_CUDA;
+  }
+  if (!make_map(&mout, out, n_out, rows, ld_out, 32, BLOCK_M)) return T2H_ERR_CUDA;
+  maux = mout;
+  if (a.aux_kind == 1 && !make_map(&maux, mask, n_out, rows, ld_mask, 32, BLOCK_M)) return T2H_ERR_CUDA;
+  if (a.aux_kind == 2 && !make_map(&maux, residual, n_out, rows, ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
+  return launch_linear_persistent<true>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
+}
 
 extern "C" int t2h_conv3x3_fwd(const float* x, int B, int H, int W, int cin, const float* w_hi, const float* w_lo,
                                int cout, const float* bias, int relu_in, const float* mask, const float* residual,
@@ -741,6 +1262,7 @@ extern "C" int t2h_conv3x3_fwd(const float* x, int B, int H, int W, int cin, con
   a.aux_kind = mask ? 1 : (residual ? 2 : 0);
   if (mask && residual) return T2H_ERR_UNSUPPORTED_SHAPE;  // only one epilogue operand is staged in conv mode
   a.conv = 1; a.tiles_x = W / CONV_TW; a.tiles_per_img = (H / CONV_TH) * a.tiles_x;
+  a.x_absmax = a.w_absmax = nullptr; a.out_absmax = nullptr;
   PlaneGeom pg{B, H, W};
   cudaStream_t s = (cudaStream_t)stream;
   const int k_total = 9 * cin;

@@ -21,45 +21,49 @@ from ._lib import ptr
 
 
 class _SplitCache:
-    """(weight, column slice, transposed?) -> (hi, lo), invalidated when the parameter changes."""
+    """(weight, column slice / tag, flavour) -> operand split, invalidated when the parameter changes.
+
+    tf32 flavour: (hi, lo) fp32 matrices; f16 flavour: (hi, lo, absmax) with fp16 matrices and the device
+    word holding the bit pattern of max |w| that fixes the power-of-two scale (t2h_absmax / t2h_split_f16)."""
 
     def __init__(self):
         self._store = {}
 
-    def get(self, weight, c0=0, c1=None, transposed=False):
-        c1 = weight.shape[1] if c1 is None else c1
-        key = (id(weight), c0, c1, transposed)
-        hit = None if capture_mode else self._store.get(key)
-        if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
-            return hit[3], hit[4]
-        with torch.no_grad():
-            w = weight.detach()[:, c0:c1]
-            w = w.t().contiguous() if transposed else w.contiguous()
+    @staticmethod
+    def _split(w, f16):
+        if not f16:
             hi, lo = torch.empty_like(w), torch.empty_like(w)
             _lib.call("t2h_split_tf32", ptr(w), w.numel(), ptr(hi), ptr(lo))
-        if capture_mode:
-            return hi, lo  # lives in the graph's private pool; not a cache entry
-        if len(self._store) > 4096:
-            self._store.clear()
-        self._store[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), hi, lo)
-        return hi, lo
-
-    def get_matrix(self, weight, tag, builder):
-        """(hi, lo) split of ``builder(weight.detach())`` (a 2-D fp32 matrix), cached per parameter version."""
-        key = (id(weight), tag)
-        hit = None if capture_mode else self._store.get(key)
-        if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
-            return hit[3], hit[4]
-        with torch.no_grad():
-            w = builder(weight.detach()).contiguous()
-            hi, lo = torch.empty_like(w), torch.empty_like(w)
-            _lib.call("t2h_split_tf32", ptr(w), w.numel(), ptr(hi), ptr(lo))
-        if capture_mode:
             return hi, lo
+        slot = torch.empty(1, dtype=torch.int32, device=w.device)
+        hi = torch.empty(w.shape, dtype=torch.float16, device=w.device)
+        lo = torch.empty_like(hi)
+        _lib.call("t2h_absmax", ptr(w), w.shape[1], w.shape[1], None, 0, 0, w.shape[0], ptr(slot))
+        _lib.call("t2h_split_f16", ptr(w), w.numel(), ptr(slot), ptr(hi), ptr(lo))
+        return hi, lo, slot
+
+    def _lookup(self, weight, key, builder, f16):
+        key = key + (f16,)
+        hit = None if capture_mode else self._store.get(key)
+        if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+            return hit[3]
+        with torch.no_grad():
+            split = self._split(builder(weight.detach()).contiguous(), f16)
+        if capture_mode:
+            return split  # lives in the graph's private pool; not a cache entry
         if len(self._store) > 4096:
             self._store.clear()
-        self._store[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), hi, lo)
-        return hi, lo
+        self._store[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), split)
+        return split
+
+    def get(self, weight, c0=0, c1=None, transposed=False, f16=False):
+        c1 = weight.shape[1] if c1 is None else c1
+        return self._lookup(weight, (id(weight), c0, c1, transposed),
+                            lambda w: w[:, c0:c1].t() if transposed else w[:, c0:c1], f16)
+
+    def get_matrix(self, weight, tag, builder, f16=False):
+        """split of ``builder(weight.detach())`` (a 2-D fp32 matrix), cached per parameter version."""
+        return self._lookup(weight, (id(weight), tag), builder, f16)
 
 
 _cache = _SplitCache()
@@ -68,6 +72,64 @@ _cache = _SplitCache()
 capture_mode = False
 # ablation switch for benchmarks / debugging only: run the point MLPs as plain cuBLAS fp32 GEMMs
 USE_LIBRARY_GEMM = os.environ.get("T2H_LINEAR", "") == "cublas"
+# wide layers run the 3xFP16 flavour (twice the tensor-core rate of 3xTF32, same fp32-grade accuracy);
+# T2H_LINEAR_F16=0 keeps everything on 3xTF32 (ablation)
+USE_F16 = os.environ.get("T2H_LINEAR_F16", "1") != "0"
+
+
+def use_f16(n_out, k_total):
+    return USE_F16 and n_out > 64 and k_total >= 128 and k_total % 8 == 0
+
+
+class _AbsmaxRegistry:
+    """Device words holding max |t| of live tensors, so that an operand maximum is computed once.
+
+    The fp16 GEMM publishes the maximum of its OUTPUT from the epilogue; a standalone ``t2h_absmax`` pass
+    registers its result too (the same gradient often feeds two GEMMs).  An entry is keyed on the data
+    pointer and only valid while the registered tensor object is alive (its memory cannot have been handed
+    to another tensor) and unmodified (same version counter); anything else is a miss and falls back to a
+    fresh pass, so a stale entry can never be used."""
+
+    def __init__(self):
+        self._entries = {}
+
+    def put(self, t, slot):
+        key = (t.data_ptr(), t.numel())
+        entries = self._entries
+
+        def drop(ref, key=key):
+            if entries.get(key, (None,))[0] is ref:
+                del entries[key]
+
+        if t.is_inference():  # no version counter: cannot tell whether it was modified
+            return
+        entries[key] = (weakref.ref(t, drop), t._version, slot)
+
+    def get(self, t):
+        e = self._entries.get((t.data_ptr(), t.numel()))
+        if e is None or not t.is_contiguous() or t.is_inference():
+            return None
+        owner = e[0]()
+        if owner is None or owner._version != e[1] or t._version != e[1] or not owner.is_contiguous():
+            return None
+        return e[2]
+
+
+_absmax = _AbsmaxRegistry()
+
+
+def operand_absmax(x1, x2=None):
+    """device word with max |[x1 | x2]| (registered result if there is one, else one streaming pass)."""
+    if x2 is None:
+        slot = _absmax.get(x1)
+        if slot is not None:
+            return slot
+    slot = torch.empty(1, dtype=torch.int32, device=x1.device)
+    _lib.call("t2h_absmax", ptr(x1), x1.stride(0), x1.shape[1], ptr(x2), 0 if x2 is None else x2.stride(0),
+              0 if x2 is None else x2.shape[1], x1.shape[0], ptr(slot))
+    if x2 is None and x1.is_contiguous():
+        _absmax.put(x1, slot)
+    return slot
 
 
 def _rowmajor(t):
@@ -77,9 +139,21 @@ def _rowmajor(t):
     return t
 
 
-def _launch_fwd(x1, x2, w_hi, w_lo, n_out, bias, relu_in, mask, residual, out):
+def _launch_fwd(x1, x2, split, n_out, bias, relu_in, mask, residual, out):
     rows, k1 = x1.shape
     k2 = 0 if x2 is None else x2.shape[1]
+    if len(split) == 3:  # fp16 flavour: operand maximum first, then the GEMM
+        w_hi, w_lo, w_slot = split
+        x_slot = operand_absmax(x1, x2)
+        out_slot = torch.empty(1, dtype=torch.int32, device=x1.device) if out.is_contiguous() else None
+        _lib.call("t2h_linear_fwd_f16", ptr(x1), x1.stride(0), k1, ptr(x2), 0 if x2 is None else x2.stride(0), k2, rows,
+                  ptr(x_slot), ptr(w_hi), ptr(w_lo), ptr(w_slot), n_out, ptr(bias), int(relu_in), ptr(mask),
+                  0 if mask is None else mask.stride(0), ptr(residual), 0 if residual is None else residual.stride(0),
+                  ptr(out), out.stride(0), ptr(out_slot))
+        if out_slot is not None:
+            _absmax.put(out, out_slot)
+        return
+    w_hi, w_lo = split
     _lib.call("t2h_linear_fwd", ptr(x1), x1.stride(0), k1, ptr(x2), 0 if x2 is None else x2.stride(0), k2, rows,
               ptr(w_hi), ptr(w_lo), n_out, ptr(bias), int(relu_in), ptr(mask), 0 if mask is None else mask.stride(0),
               ptr(residual), 0 if residual is None else residual.stride(0), ptr(out), out.stride(0))
@@ -112,9 +186,9 @@ class _LinearTC(torch.autograd.Function):
         x2 = None if x2 is None else _rowmajor(x2)
         residual = None if residual is None else _rowmajor(residual)
         n_out = weight.shape[0]
-        w_hi, w_lo = _cache.get(weight)
+        split = _cache.get(weight, f16=use_f16(n_out, weight.shape[1]))
         out = torch.empty(x1.shape[0], n_out, dtype=torch.float32, device=x1.device)
-        _launch_fwd(x1, x2, w_hi, w_lo, n_out, bias, relu_in, None, residual, out)
+        _launch_fwd(x1, x2, split, n_out, bias, relu_in, None, residual, out)
         ctx.save_for_backward(x1, x2, weight)
         ctx.relu_in = relu_in
         ctx.has_bias = bias is not None
@@ -129,13 +203,13 @@ class _LinearTC(torch.autograd.Function):
         need = ctx.needs_input_grad
         d_x1 = d_x2 = d_w = d_b = d_res = None
         if need[0]:
-            t_hi, t_lo = _cache.get(weight, 0, k1, transposed=True)
+            split = _cache.get(weight, 0, k1, transposed=True, f16=use_f16(k1, n_out))
             d_x1 = torch.empty_like(x1)
-            _launch_fwd(gy, None, t_hi, t_lo, k1, None, False, x1 if ctx.relu_in else None, None, d_x1)
+            _launch_fwd(gy, None, split, k1, None, False, x1 if ctx.relu_in else None, None, d_x1)
         if x2 is not None and need[1]:
-            t_hi, t_lo = _cache.get(weight, k1, k_total, transposed=True)
+            split = _cache.get(weight, k1, k_total, transposed=True, f16=use_f16(k_total - k1, n_out))
             d_x2 = torch.empty_like(x2)
-            _launch_fwd(gy, None, t_hi, t_lo, k_total - k1, None, False, x2 if ctx.relu_in else None, None, d_x2)
+            _launch_fwd(gy, None, split, k_total - k1, None, False, x2 if ctx.relu_in else None, None, d_x2)
         want_bias = ctx.has_bias and need[3]
         if need[2]:
             d_w = torch.empty(n_out, k_total, dtype=torch.float32, device=gy.device)
