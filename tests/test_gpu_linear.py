@@ -136,3 +136,141 @@ def test_linear_odd_widths_are_padded():
     yd.square().sum().backward()
     for got, ref in ((y, yd), (x.grad, xd.grad), (w.grad, wd.grad), (b.grad, bd.grad)):
         assert (got.double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+
+
+# ---- 3xFP16 flavour (t2h_absmax / t2h_split_f16 / t2h_linear_fwd_f16) ------------------------------------
+def _absmax_raw(x1, x2=None):
+    from tomosar2height_b200 import _lib
+    slot = torch.full((1,), 12345, dtype=torch.int32, device=x1.device)  # the call must reset it
+    _lib.call("t2h_absmax", _lib.ptr(x1), x1.stride(0), x1.shape[1], _lib.ptr(x2), 0 if x2 is None else x2.stride(0),
+              0 if x2 is None else x2.shape[1], x1.shape[0], _lib.ptr(slot))
+    return slot
+
+
+def _linear_f16_raw(x1, w, bias=None, x2=None, relu_in=False, mask=None, residual=None, want_out_max=True):
+    from tomosar2height_b200 import _lib
+    rows, k1 = x1.shape
+    k2 = 0 if x2 is None else x2.shape[1]
+    n_out = w.shape[0]
+    w = w.contiguous()
+    w_slot = _absmax_raw(w)
+    hi = torch.empty(w.shape, dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi)
+    _lib.call("t2h_split_f16", _lib.ptr(w), w.numel(), _lib.ptr(w_slot), _lib.ptr(hi), _lib.ptr(lo))
+    x_slot = _absmax_raw(x1, x2)
+    out = torch.empty(rows, n_out, device=x1.device, dtype=torch.float32)
+    out_slot = torch.full((1,), 777, dtype=torch.int32, device=x1.device) if want_out_max else None
+    _lib.call("t2h_linear_fwd_f16", _lib.ptr(x1), x1.stride(0), k1, _lib.ptr(x2), 0 if x2 is None else x2.stride(0), k2, rows,
+              _lib.ptr(x_slot), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(w_slot), n_out, _lib.ptr(bias), int(relu_in),
+              _lib.ptr(mask), 0 if mask is None else mask.stride(0), _lib.ptr(residual),
+              0 if residual is None else residual.stride(0), _lib.ptr(out), out.stride(0), _lib.ptr(out_slot))
+    return out, out_slot
+
+
+def test_absmax_is_exact_and_handles_strides():
+    g = torch.Generator().manual_seed(5)
+    for rows, k, ld in [(1, 4, 4), (1000, 32, 32), (4097, 96, 128), (300000, 64, 64)]:
+        buf = (torch.randn(rows, ld, generator=g) * 3).cuda()
+        buf[:, k:] = 1e6  # outside the matrix: must be ignored
+        x = buf[:, :k]
+        slot = _absmax_raw(x)
+        assert slot.view(torch.float32).item() == x.abs().max().item()
+    a, b = torch.randn(777, 32, generator=g).cuda(), (torch.randn(777, 64, generator=g) * 5).cuda()
+    assert _absmax_raw(a, b).view(torch.float32).item() == max(a.abs().max().item(), b.abs().max().item())
+    assert _absmax_raw(torch.zeros(64, 8).cuda()).item() == 0
+
+
+@pytest.mark.parametrize("rows,K,N", [(777, 128, 256), (3000, 512, 1024), (2500, 1024, 512), (5000, 256, 128),
+                                     (130, 160, 132), (100000, 256, 512)])
+def test_linear_f16_matches_fp64(rows, K, N):
+    g = torch.Generator().manual_seed(rows + K + N)
+    x = torch.randn(rows, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    y, out_slot = _linear_f16_raw(x, w, b)
+    ref = x.double() @ w.double().t() + b.double()
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    err32 = ((x @ w.t() + b).double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5 and err < 20 * err32 + 1e-6, (err, err32)
+    # the epilogue publishes max |out| exactly (the operand scale of a following layer)
+    assert out_slot.view(torch.float32).item() == y.abs().max().item()
+
+
+@pytest.mark.parametrize("scale", [1e-12, 1e-4, 1.0, 1e6, 1e20])
+def test_linear_f16_operand_scaling(scale):
+    """power-of-two operand scaling: the relative accuracy does not depend on the magnitude of the operands
+    (gradients are ~1e-9, fp16 underflows below 6e-8 and overflows above 65504)."""
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(2000, 256, generator=g) * scale).cuda()
+    w = (torch.randn(128, 256, generator=g) * (0.05 / scale ** 0.5)).cuda()
+    y, _ = _linear_f16_raw(x, w)
+    ref = x.double() @ w.double().t()
+    assert torch.isfinite(y).all()
+    assert (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+
+
+def test_linear_f16_rows_of_very_different_magnitude():
+    """rows spanning six orders of magnitude share one tensor scale: small rows keep ~1e-5 of THEIR OWN scale
+    (absolute floor 2^-40 of the tensor maximum, documented in include/t2h.h)."""
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(4096, 256, generator=g) * torch.exp(torch.empty(4096, 1).uniform_(-12, 3, generator=g))
+    w = torch.randn(256, 256, generator=g) / 16
+    y, _ = _linear_f16_raw(x.cuda(), w.cuda())
+    ref = x.double() @ w.double().t()
+    row_scale = ref.abs().amax(1, keepdim=True)
+    assert ((y.cpu().double() - ref).abs() / row_scale).max().item() < 1e-4
+
+
+def test_linear_f16_epilogues_concat_and_ragged_k():
+    g = torch.Generator().manual_seed(1)
+    rows = 1500
+    a = torch.randn(rows, 96, generator=g).cuda()    # 3 chunks + 2 chunks = odd number of 32-wide chunks
+    b2 = torch.randn(rows, 64, generator=g).cuda()
+    w = (torch.randn(200, 160, generator=g) / 12).cuda()
+    bias = torch.randn(200, generator=g).cuda()
+    res = torch.randn(rows, 200, generator=g).cuda()
+    mask = torch.randn(rows, 200, generator=g).cuda()
+    x = torch.cat([a, b2], 1).double().relu()
+    full = x @ w.double().t() + bias.double()
+    y, slot = _linear_f16_raw(a, w, bias, x2=b2, relu_in=True, mask=mask)
+    ref = full * (mask > 0).double()
+    assert (y.double() - ref).abs().max().item() < 2e-6 * full.abs().max().item()
+    assert slot.view(torch.float32).item() == y.abs().max().item()
+    y, slot = _linear_f16_raw(a, w, bias, x2=b2, relu_in=True, residual=res)
+    ref = full + res.double()
+    assert (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+    assert slot.view(torch.float32).item() == y.abs().max().item()
+    y, _ = _linear_f16_raw(a, w, bias, x2=b2, relu_in=True, mask=mask, residual=res, want_out_max=False)  # general epilogue
+    ref = full * (mask > 0).double() + res.double()
+    assert (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+    # K = 136 (multiple of 8, not of 32): the last chunk is zero-filled by TMA
+    xs = torch.randn(rows, 136, generator=g).cuda()
+    ws = (torch.randn(96, 136, generator=g) / 11).cuda()
+    y, _ = _linear_f16_raw(xs, ws)
+    ref = xs.double() @ ws.double().t()
+    assert (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+
+
+def test_absmax_registry_is_reused_and_never_stale():
+    from tomosar2height_b200 import linear as L
+    from tomosar2height_b200 import _lib
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3000, 256, generator=g).cuda()
+    w1 = torch.nn.Parameter((torch.randn(256, 256, generator=g) / 16).cuda())
+    w2 = torch.nn.Parameter((torch.randn(128, 256, generator=g) / 16).cuda())
+    assert L.use_f16(256, 256)
+    h = L.linear(x, w1)
+    slot = L._absmax.get(h.detach())
+    assert slot is not None and slot.view(torch.float32).item() == h.abs().max().item()
+    L.linear(h, w2, relu_in=True)                # fills the weight-split cache of w2
+    before = _lib.launch_count
+    y = L.linear(h, w2, relu_in=True)            # uses the published maximum: one launch (the GEMM), no absmax pass
+    assert _lib.launch_count - before == 1
+    ref = h.double().relu() @ w2.double().t()
+    assert (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+    with torch.no_grad():
+        h.mul_(1000.0)                            # modified in place: the registered maximum must not be used
+    assert L._absmax.get(h) is None
+    y = L.linear(h, w2, relu_in=True)
+    ref = h.double().relu() @ w2.double().t()
+    assert torch.isfinite(y).all() and (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
