@@ -169,6 +169,13 @@ size_t t2h_linear_wgrad_workspace_bytes(int64_t rows, int n_out, int k_in);
 int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float* x, int64_t ld_x, int64_t rows,
                      int n_out, int k_in, int relu_in, void* workspace, size_t workspace_bytes,
                      float* grad_w, int64_t ld_w, float* grad_b, t2h_stream_t stream);
+/* 3xFP16 flavour of the weight gradient for k_in > 64: g^T as packed fp16 pairs through tensor memory, x
+ * converted in shared memory to MN-major fp16 hi / lo tiles; operand scales from the two maxima (t2h_absmax).
+ * Same workspace, split and reduction as t2h_linear_wgrad. */
+int t2h_linear_wgrad_f16(const float* grad_out, int64_t ld_g, const uint32_t* g_absmax, const float* x,
+                         int64_t ld_x, const uint32_t* x_absmax, int64_t rows, int n_out, int k_in,
+                         int relu_in, void* workspace, size_t workspace_bytes, float* grad_w,
+                         int64_t ld_w, float* grad_b, t2h_stream_t stream);
 /* ---- f3: 3x3 / padding 1 convolutions of the plane CNN (alto.py:59-61,98-99,177-182,226-227,
  *      pixel.py:20-22) as implicit GEMM on the same tcgen05 3xTF32 pipeline.  Planes are channels-last
  *      (B, H, W, C); the weight is passed as the matrix [cout, 9*cin] with k = (3*ky + kx)*cin + ci

@@ -297,29 +297,31 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
 
 // ---- persistent variant (wide layers) ----------------------------------------------------------------
 // One CTA per SM walks the tile list (N-tile fastest, stride gridDim.x).  Roles: warp 0 TMA producer,
-// warp 1 MMA issuer, warps 2-9 operand transform (split x -> TMEM), warps 10-17 epilogue.  The fp32
+// warp 1 MMA issuer, warps 2-5 operand transform (split x -> TMEM), warps 6-13 epilogue.  The fp32
 // accumulator is DOUBLE-BUFFERED in tensor memory (2 x 128 columns) and the stage ring runs across tile
 // boundaries, so tile i+1 is loaded, split and multiplied while the epilogue warps drain, post-process and
 // TMA-store tile i: the ~6 us of per-tile prologue/epilogue that the one-tile-per-CTA kernel exposes
 // (TMEM allocation, barrier setup, first-load latency, store drain) is paid once per SM or hidden.
 // TMEM: 2 x 128 (accumulators) + 4 x 64 (split A stages) = all 512 columns.
-constexpr int P_BLOCK_N = 128;
-constexpr int P_THREADS = 576;  // producer, MMA, 2 x 4 transform warps, 2 x 4 epilogue warps
-// F16 = false (3xTF32): a stage is one 32-wide K chunk (x fp32 16 KB | w hi 16 KB | w lo 16 KB), 4 stages; the
-//   two transform groups take alternate stages (even stage count: a waiter must see every phase of a barrier).
+constexpr int P_THREADS = 448;  // producer, MMA, 4 transform warps, 2 x 4 epilogue warps (144 registers per thread)
+// F16 = false (3xTF32): a stage is one 32-wide K chunk (x fp32 16 KB | w hi 16 KB | w lo 16 KB), 4 stages.
 // F16 = true (3xFP16): a stage is 64 K elements (two fp32 x boxes of 16 KB | w hi fp16 16 KB | w lo fp16 16 KB),
-//   3 stages; transform group g splits box g of every stage.  The split x operand is packed two fp16 per
-//   32-bit TMEM column, so a stage again occupies 64 columns (32 hi + 32 lo).
-template <bool F16>
+//   3 stages.  The split x operand is packed two fp16 per 32-bit TMEM column, so a stage again occupies
+//   64 columns (32 hi + 32 lo).
+// BLOCK_N = 128 / 64 / 32 output columns per tile; narrower tiles have smaller weight stages and run a deeper ring
+// (the narrow layers are HBM-bound: bytes in flight per SM matter, not MMA issue).
+template <bool F16, int BLOCK_N>
 struct PSmem {
-  static constexpr int STAGES = F16 ? 3 : 4;
+  static constexpr int STAGES = F16 ? (BLOCK_N == 128 ? 3 : 4) : (BLOCK_N == 128 ? 4 : 6);
   static constexpr int X_BYTES = (F16 ? 2 : 1) * A_BYTES;
-  static constexpr int W_BYTES = F16 ? P_BLOCK_N * 64 * 2 : P_BLOCK_N * BLOCK_K * 4;
+  static constexpr int W_BYTES = F16 ? BLOCK_N * 64 * 2 : BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = X_BYTES + 2 * W_BYTES;        // x raw | w hi | w lo
   static constexpr int STAGING_BYTES = 2 * A_BYTES;                // epilogue staging: two 32-column blocks at a time
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int A_COL0 = 2 * P_BLOCK_N;
+  static constexpr int A_COL0 = 2 * BLOCK_N;
+  static_assert(A_COL0 + STAGES * 64 <= 512, "tensor memory: two accumulators + the split x stages");
+  static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
 
 // power-of-two operand scale from the bit pattern of max|v|: 2^e with e = 14 - floor(log2 max), so that the
@@ -332,14 +334,14 @@ __device__ __forceinline__ int f16_scale_exp(uint32_t absmax_bits) {
 }
 __device__ __forceinline__ float pow2f(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
 
-template <bool F16>
+template <bool F16, int BLOCK_N>
 __global__ void __launch_bounds__(P_THREADS, 1)
 linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                                 const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
                                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_aux,
                                 const LinearArgs p, const int64_t n_tiles_total) {
-  using S = PSmem<F16>;
-  constexpr int STAGES = S::STAGES, BLOCK_N = P_BLOCK_N;
+  using S = PSmem<F16, BLOCK_N>;
+  constexpr int STAGES = S::STAGES;
   // pipeline steps per tile: 32-wide chunks (tf32) or pairs of them (fp16)
   const int n_steps = F16 ? (p.k_chunks + 1) / 2 : p.k_chunks;
   extern __shared__ uint8_t smem_raw[];
@@ -353,9 +355,11 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
   auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto acc_full = [&](int a) { return bars + 8u * (3 * STAGES + a); };
   auto acc_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
-  const uint32_t aux_bar = bars + 8u * (3 * STAGES + 4);
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 5);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(staging_ptr + S::STAGING_BYTES + 8 * (3 * STAGES + 5));
+  auto aux_bar = [&](int g) { return bars + 8u * (3 * STAGES + 4 + g); };
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 6);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(staging_ptr + S::STAGING_BYTES + 8 * (3 * STAGES + 6));
+  // epilogue threads that hand an accumulator back per tile: both groups, or (32-wide tiles) the one that owns the tile
+  constexpr uint32_t EPI_ARRIVALS = BLOCK_N == 32 ? 128 : 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.n_out + BLOCK_N - 1) / BLOCK_N;
@@ -363,14 +367,14 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_tma(s), 1);
-      mbar_init(full_ab(s), F16 ? 256 : 128);
+      mbar_init(full_ab(s), 128);
       mbar_init(empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full(a), 1);
-      mbar_init(acc_empty(a), 256);
+      mbar_init(acc_empty(a), EPI_ARRIVALS);
+      mbar_init(aux_bar(a), 1);
     }
-    mbar_init(aux_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_x1);
     tma_prefetch_desc(&tm_whi);
@@ -471,33 +475,33 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
         mma_commit(acc_full(acc));
       }
     }
-  } else if (warp < 10) {
-    // ---- operand transform: row t of every x chunk -> (hi | lo) in TMEM; two warp groups take alternate
-    //      chunks so that the split keeps pace with the MMA pipe of a whole SM ------------------------
+  } else if (warp < 6) {
+    // ---- operand transform: row t of every x chunk -> (hi | lo) in TMEM ---------------------------------
     const int t = (warp & 3) * 32 + lane;
-    const int group = (warp - 2) >> 2;
     const float sx = F16 ? pow2f(f16_scale_exp(*p.x_absmax)) : 1.f;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       for (int kc = 0; kc < n_steps; ++kc, ++it) {
         const int s = (int)(it % STAGES);
-        if (!F16 && (s & 1) != group) continue;
         const uint32_t ph = (uint32_t)((it / STAGES) & 1);
         mbar_wait(full_tma(s), ph);
         const uint32_t a_dst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + S::A_COL0 + s * 64;
         if (F16) {
-          const float* x_row = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES + group * A_BYTES + t * 128);
-          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 v = *reinterpret_cast<const float4*>(x_row + ((j ^ (t & 7)) * 4));
-            if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            v.x *= sx; v.y *= sx; v.z *= sx; v.w *= sx;
-            split_f16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
-            split_f16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+          for (int box = 0; box < 2; ++box) {
+            const float* x_row = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES + box * A_BYTES + t * 128);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 v = *reinterpret_cast<const float4*>(x_row + ((j ^ (t & 7)) * 4));
+              if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              v.x *= sx; v.y *= sx; v.z *= sx; v.w *= sx;
+              split_f16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
+              split_f16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+            }
+            tmem_st_32x16(a_dst + box * 16, hi);
+            tmem_st_32x16(a_dst + 32 + box * 16, lo);
           }
-          tmem_st_32x16(a_dst + group * 16, hi);
-          tmem_st_32x16(a_dst + 32 + group * 16, lo);
         } else {
           const float* x_row = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES + t * 128);
           float hi[32], lo[32];
@@ -517,13 +521,17 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
       }
     }
   } else {
-    // ---- epilogue warps 10-17: drain accumulator `acc`, release it, post-process, TMA store ------------
-    // Two warps per TMEM lane quarter (and per SM sub-partition): in each of the two rounds of a tile,
-    // group eh = 0/1 handles the 32-column block 2 * round + eh through its own 16 KB staging slot.
-    const int quarter = warp & 3;  // warps 10..17 -> TMEM lane quarters 2,3,0,1,2,3,0,1
-    const int eh = (warp - 10) >> 2;
+    // ---- epilogue warps 6-13: drain accumulator `acc`, release it, post-process, TMA store --------------
+    // Two independent groups of four warps (one warp per TMEM lane quarter and SM sub-partition each), each
+    // with its own 16 KB staging slot, named barrier, TMA-store leader and aux barrier.  Group eh handles the
+    // 32-column blocks eh, eh + 2 of a tile; with 32-wide tiles the groups take alternate tiles.  A group only
+    // waits for ITS previous store to have been read out of shared memory right before it refills the slot.
+    const int quarter = warp & 3;  // warps 6..13 -> TMEM lane quarters 2,3,0,1,2,3,0,1
+    const int eh = (warp - 6) >> 2;
     const int t = quarter * 32 + lane;
-    const bool leader = (warp == 10 && lane == 0);
+    const bool leader = ((warp - 6) & 3) == 0 && lane == 0;
+    const uint32_t my_staging = staging + eh * A_BYTES;
+    float* srow = reinterpret_cast<float*>(staging_ptr + eh * A_BYTES + t * 128);
     // fp16 mode: undo the two power-of-two operand scales (|exponent| <= 63 each, so the product is a float)
     const float inv = F16 ? pow2f(-(f16_scale_exp(*p.x_absmax) + f16_scale_exp(*p.w_absmax))) : 1.f;
     const int epi_mode = (p.mask && p.residual) || (p.aux_kind == 0 && (p.mask || p.residual)) ? 3 : p.aux_kind;
@@ -531,6 +539,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
     float out_max = 0.f;
     int64_t local = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
+      if (BLOCK_N == 32 && (int)(local & 1) != eh) continue;
       int m0, n0, img, px0, py0;
       decode(tile, m0, n0, img, px0, py0);
       const int acc = (int)(local & 1);
@@ -539,105 +548,103 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
       const int64_t row = (int64_t)m0 + t;
       const bool row_ok = row < p.rows;
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-      for (int round = 0; round < 2; ++round) {
-        const int cb0 = round * 2, cb1 = min(cb0 + 2, n_blocks);
-        if (cb0 < n_blocks) {
-          const int cb = cb0 + eh;
-          const bool active = cb < cb1;
-          // both staging slots are free: the leader waited for the previous stores' reads before the closing barrier
-          if (p.aux_kind) {
-            if (leader) {
-              mbar_arrive_expect_tx(aux_bar, (uint32_t)(cb1 - cb0) * A_BYTES);
-              for (int c = cb0; c < cb1; ++c) {
-                if (p.conv) tma_load_4d(staging + (c - cb0) * A_BYTES, &tm_aux, aux_bar, n0 + c * 32, px0, py0, img);
-                else tma_load_2d(staging + (c - cb0) * A_BYTES, &tm_aux, aux_bar, n0 + c * 32, m0);
-              }
-            }
-            mbar_wait(aux_bar, aux_phase);
-            aux_phase ^= 1;
-          }
-          if (round == 0) {
-            mbar_wait(acc_full(acc), acc_ph);
-            tc_fence_after();
-          }
-          if (active) {
-            const int nb = n0 + cb * 32;
-            // the bias slice first (one broadcast line per load, in flight while tensor memory is read); columns
-            // past n_out are clipped by the TMA store, so their index is only clamped to stay in bounds
-            float4 b[8];
-            if (p.bias) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g) b[g] = ld4(p.bias + min(nb + g * 4, p.n_out - 4));
-            }
-            float v[32];
-            tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32), v);
-            float* srow = reinterpret_cast<float*>(staging_ptr + eh * A_BYTES + t * 128);
-            if (F16) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= inv;
-            }
-            if (p.bias) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g) { v[4 * g] += b[g].x; v[4 * g + 1] += b[g].y; v[4 * g + 2] += b[g].z; v[4 * g + 3] += b[g].w; }
-            }
-            if (epi_mode == 1) {         // ReLU mask staged by TMA (input-gradient GEMM)
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 m = *reinterpret_cast<const float4*>(srow + ((g ^ (t & 7)) * 4));
-                v[4 * g] = m.x > 0.f ? v[4 * g] : 0.f; v[4 * g + 1] = m.y > 0.f ? v[4 * g + 1] : 0.f;
-                v[4 * g + 2] = m.z > 0.f ? v[4 * g + 2] : 0.f; v[4 * g + 3] = m.w > 0.f ? v[4 * g + 3] : 0.f;
-              }
-            } else if (epi_mode == 2) {  // residual staged by TMA
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 r = *reinterpret_cast<const float4*>(srow + ((g ^ (t & 7)) * 4));
-                v[4 * g] += r.x; v[4 * g + 1] += r.y; v[4 * g + 2] += r.z; v[4 * g + 3] += r.w;
-              }
-            } else if (epi_mode == 3) {  // general case: mask and residual together, read from global memory
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const int n = min(nb + g * 4, p.n_out - 4);  // clipped columns: any in-bounds address
-                if (p.mask) {
-                  float4 m;
-                  if (p.aux_kind == 1) m = *reinterpret_cast<const float4*>(srow + ((g ^ (t & 7)) * 4));
-                  else m = row_ok ? ld4(p.mask + row * p.ld_mask + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                  v[4 * g] = m.x > 0.f ? v[4 * g] : 0.f; v[4 * g + 1] = m.y > 0.f ? v[4 * g + 1] : 0.f;
-                  v[4 * g + 2] = m.z > 0.f ? v[4 * g + 2] : 0.f; v[4 * g + 3] = m.w > 0.f ? v[4 * g + 3] : 0.f;
-                }
-                if (p.residual) {
-                  const float4 r = row_ok ? *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-                  v[4 * g] += r.x; v[4 * g + 1] += r.y; v[4 * g + 2] += r.z; v[4 * g + 3] += r.w;
-                }
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              *reinterpret_cast<float4*>(srow + ((g ^ (t & 7)) * 4)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-            if (p.out_absmax && row_ok) {  // rows / columns outside the matrix hold bias-only garbage: skip them
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (nb + g * 4 < p.n_out)
-                  out_max = fmaxf(fmaxf(out_max, fmaxf(fabsf(v[4 * g]), fabsf(v[4 * g + 1]))), fmaxf(fabsf(v[4 * g + 2]), fabsf(v[4 * g + 3])));
-            }
-          }
-          if (round == 1 || cb1 == n_blocks) {
-            // the accumulator has been read completely (tcgen05.ld waited): hand it back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(acc_empty(acc));
-          }
-          fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+      bool have_acc = false;
+#pragma unroll 1
+      for (int cb = (BLOCK_N == 32 ? 0 : eh); cb < n_blocks; cb += 2) {
+        // the slot is free once the group's previous store has been read
+        if (leader) tma_store_wait_read();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eh) : "memory");
+        if (p.aux_kind) {
           if (leader) {
-            for (int c = cb0; c < cb1; ++c) {
-              if (p.conv) tma_store_4d(&tm_out, staging + (c - cb0) * A_BYTES, n0 + c * 32, px0, py0, img);
-              else tma_store_2d(&tm_out, staging + (c - cb0) * A_BYTES, n0 + c * 32, m0);
-            }
-            tma_store_commit_and_wait();  // staging has been read: it may be refilled
+            mbar_arrive_expect_tx(aux_bar(eh), A_BYTES);
+            if (p.conv) tma_load_4d(my_staging, &tm_aux, aux_bar(eh), n0 + cb * 32, px0, py0, img);
+            else tma_load_2d(my_staging, &tm_aux, aux_bar(eh), n0 + cb * 32, m0);
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          mbar_wait(aux_bar(eh), aux_phase);
+          aux_phase ^= 1;
+        }
+        if (!have_acc) {
+          mbar_wait(acc_full(acc), acc_ph);
+          tc_fence_after();
+          have_acc = true;
+        }
+        const int nb = n0 + cb * 32;
+        // the bias slice first (one broadcast line per load, in flight while tensor memory is read); columns
+        // past n_out are clipped by the TMA store, so their index is only clamped to stay in bounds
+        float4 b[8];
+        if (p.bias) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) b[g] = ld4(p.bias + min(nb + g * 4, p.n_out - 4));
+        }
+        float v[32];
+        tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32), v);
+        if (cb + 2 >= n_blocks) {
+          // the group's last read of this accumulator (tcgen05.ld has been waited for)
+          tc_fence_before();
+          mbar_arrive(acc_empty(acc));
+        }
+        if (F16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= inv;
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) { v[4 * g] += b[g].x; v[4 * g + 1] += b[g].y; v[4 * g + 2] += b[g].z; v[4 * g + 3] += b[g].w; }
+        }
+        if (epi_mode == 1) {         // ReLU mask staged by TMA (input-gradient GEMM)
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 m = *reinterpret_cast<const float4*>(srow + ((g ^ (t & 7)) * 4));
+            v[4 * g] = m.x > 0.f ? v[4 * g] : 0.f; v[4 * g + 1] = m.y > 0.f ? v[4 * g + 1] : 0.f;
+            v[4 * g + 2] = m.z > 0.f ? v[4 * g + 2] : 0.f; v[4 * g + 3] = m.w > 0.f ? v[4 * g + 3] : 0.f;
+          }
+        } else if (epi_mode == 2) {  // residual staged by TMA
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 r = *reinterpret_cast<const float4*>(srow + ((g ^ (t & 7)) * 4));
+            v[4 * g] += r.x; v[4 * g + 1] += r.y; v[4 * g + 2] += r.z; v[4 * g + 3] += r.w;
+          }
+        } else if (epi_mode == 3) {  // general case: mask and residual together, read from global memory
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int n = min(nb + g * 4, p.n_out - 4);  // clipped columns: any in-bounds address
+            if (p.mask) {
+              float4 m;
+              if (p.aux_kind == 1) m = *reinterpret_cast<const float4*>(srow + ((g ^ (t & 7)) * 4));
+              else m = row_ok ? ld4(p.mask + row * p.ld_mask + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[4 * g] = m.x > 0.f ? v[4 * g] : 0.f; v[4 * g + 1] = m.y > 0.f ? v[4 * g + 1] : 0.f;
+              v[4 * g + 2] = m.z > 0.f ? v[4 * g + 2] : 0.f; v[4 * g + 3] = m.w > 0.f ? v[4 * g + 3] : 0.f;
+            }
+            if (p.residual) {
+              const float4 r = row_ok ? *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[4 * g] += r.x; v[4 * g + 1] += r.y; v[4 * g + 2] += r.z; v[4 * g + 3] += r.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(srow + ((g ^ (t & 7)) * 4)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        if (p.out_absmax && row_ok) {  // rows / columns outside the matrix hold bias-only garbage: skip them
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (nb + g * 4 < p.n_out)
+              out_max = fmaxf(fmaxf(out_max, fmaxf(fabsf(v[4 * g]), fabsf(v[4 * g + 1]))), fmaxf(fabsf(v[4 * g + 2]), fabsf(v[4 * g + 3])));
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eh) : "memory");
+        if (leader) {
+          if (p.conv) tma_store_4d(&tm_out, my_staging, n0 + cb * 32, px0, py0, img);
+          else tma_store_2d(&tm_out, my_staging, n0 + cb * 32, m0);
+          tma_store_commit();
         }
       }
+      if (BLOCK_N != 32 && !have_acc) {
+        // a group without a block in this (narrow last) tile still takes part in the accumulator hand-over, in step
+        mbar_wait(acc_full(acc), acc_ph);
+        mbar_arrive(acc_empty(acc));
+      }
     }
+    if (leader) tma_store_wait_all();  // global writes of the last stores complete before the CTA exits
     if (p.out_absmax) {
       uint32_t b = __float_as_uint(out_max);
 #pragma unroll
@@ -680,24 +687,35 @@ struct WgradArgs {
   int units_per_img;  // (H / 2) * tiles_x
   int cin;
   int a_cols;         // columns of g actually loaded per tile: min(128, n_out rounded up to 32)
+  // fp16x3 flavour: device words with the bit patterns of max |g| and max |x| (t2h_absmax)
+  const uint32_t* g_absmax;
+  const uint32_t* x_absmax;
 };
 
-template <int BLOCK_N>
+// F16 (BLOCK_N = 128 only): the x tile is TMA-loaded un-swizzled, converted to fp16 hi / lo by the transform
+// warps and re-written as two MN-major SWIZZLE_128B operands (64 fp16 = 128 B along k_in per row, 8-row atoms
+// 1024 B apart, the two 64-wide groups 4096 B apart); g^T goes to tensor memory as packed fp16 pairs.  A stage
+// then needs 2 k-steps of 16 rows (6 MMAs) instead of 4 of 8 (12 MMAs).
+template <int BLOCK_N, bool F16 = false>
 struct WgSmem {
-  static constexpr int B_B = (BLOCK_N / 32) * WG_GROUP_BYTES;
-  static constexpr int STAGE_BYTES = WG_A_BYTES + 2 * B_B;       // g raw | x hi | x lo
+  static constexpr int B_B = (BLOCK_N / 32) * WG_GROUP_BYTES;    // fp32 x tile (and each of its tf32 splits)
+  static constexpr int B16_B = WG_ROWS * BLOCK_N * 2;            // one fp16 operand tile
+  static constexpr int STAGE_BYTES = F16 ? WG_A_BYTES + B_B + 2 * B16_B   // g raw | x raw | x hi | x lo (fp16)
+                                         : WG_A_BYTES + 2 * B_B;          // g raw | x hi | x lo
   static constexpr int STAGES = BLOCK_N <= 64 ? 3 : 2;           // narrow tiles: 24-32 KB stages, deeper prefetch
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
-  static constexpr int TMEM_USED = BLOCK_N + STAGES * 64;        // accumulator + (g hi, g lo) per stage
+  static constexpr int A_COLS = F16 ? 32 : 64;                   // TMEM columns of (g hi, g lo) per stage
+  static constexpr int TMEM_USED = BLOCK_N + STAGES * A_COLS;    // accumulator + split g per stage
   static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool F16>
 __global__ void __launch_bounds__(kThreads)
-wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, const WgradArgs p) {
-  using S = WgSmem<BLOCK_N>;
+wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, const WgradArgs p) {
+  using S = WgSmem<BLOCK_N, F16>;
   constexpr int STAGES = S::STAGES;
   constexpr int B_B = S::B_B;
+  static_assert(!F16 || BLOCK_N == 128, "the fp16 flavour is written for 128-wide tiles");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -764,13 +782,28 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 1);  // A from TMEM, B MN-major
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(BLOCK_M, BLOCK_N, 0, 1) : make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 1);  // A from TMEM, B MN-major
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(full_tma(s), ph);
         mbar_wait(full_ab(s), ph);
         tc_fence_after();
+        if (F16) {
+          const uint32_t b_hi0 = base + s * S::STAGE_BYTES + WG_A_BYTES + B_B, b_lo0 = b_hi0 + S::B16_B;
+#pragma unroll
+          for (int k = 0; k < WG_ROWS / 16; ++k) {
+            const uint32_t koff = k * 2048;  // two 8-row atoms of 1024 bytes
+            const uint32_t a_hi = tmem_d + BLOCK_N + s * S::A_COLS + k * 8, a_lo = a_hi + 16;
+            const uint64_t b_hi = make_smem_desc(b_hi0 + koff, 4096, 1024, kLayoutSW128);
+            const uint64_t b_lo = make_smem_desc(b_lo0 + koff, 4096, 1024, kLayoutSW128);
+            mma_f16_ts(tmem_d, a_lo, b_hi, idesc, (it | k) != 0);
+            mma_f16_ts(tmem_d, a_hi, b_lo, idesc, 1);
+            mma_f16_ts(tmem_d, a_hi, b_hi, idesc, 1);
+          }
+          mma_commit(empty(s));
+          continue;
+        }
         const uint32_t b_hi0 = base + s * S::STAGE_BYTES + WG_A_BYTES, b_lo0 = b_hi0 + B_B;
 #pragma unroll
         for (int k = 0; k < WG_ROWS / UMMA_K; ++k) {
@@ -795,16 +828,56 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
       float z[32];
 #pragma unroll
       for (int r = 0; r < 32; ++r) z[r] = 0.f;
-      for (int s = 0; s < STAGES; ++s) {
-        tmem_st_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + BLOCK_N + s * 64, z);
-        tmem_st_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + BLOCK_N + s * 64 + 32, z);
-      }
+      for (int c = 0; c < STAGES * S::A_COLS; c += 32)
+        tmem_st_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + BLOCK_N + c, z);
       tmem_st_wait();
     }
+    const float sg = F16 ? pow2f(f16_scale_exp(*p.g_absmax)) : 1.f;
+    const float sx = F16 ? pow2f(f16_scale_exp(*p.x_absmax)) : 1.f;
     for (int it = 0; it < n_iter; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(full_tma(s), ph);
+      if (F16) {
+        if (a_live) {
+          // A: column t of the [32 rows][a_cols] tile -> TMEM lane t as 16 + 16 packed fp16 pairs (rows 2c, 2c+1)
+          const float* gcol = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES) + t;
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int r = 0; r < WG_ROWS; r += 2) {
+            const float v0 = gcol[r * p.a_cols], v1 = gcol[(r + 1) * p.a_cols];
+            bias_acc += v0;
+            bias_acc += v1;
+            split_f16x2(v0 * sg, v1 * sg, hi[r >> 1], lo[r >> 1]);
+          }
+          const uint32_t a_dst = tmem_d + ((uint32_t)(quarter * 32) << 16) + BLOCK_N + s * S::A_COLS;
+          tmem_st_32x16(a_dst, hi);
+          tmem_st_32x16(a_dst + 16, lo);
+        }
+        // B: fp32 [4 boxes][32 rows][32 floats] -> fp16 hi / lo, MN-major SWIZZLE_128B
+        const float4* raw = reinterpret_cast<const float4*>(base_ptr + s * S::STAGE_BYTES + WG_A_BYTES);
+        uint8_t* bhi = base_ptr + s * S::STAGE_BYTES + WG_A_BYTES + B_B;
+        uint8_t* blo = bhi + S::B16_B;
+#pragma unroll
+        for (int i = 0; i < B_B / 16 / 128; ++i) {
+          const int c = t + i * 128;           // float4 index: box (c >> 8), row ((c >> 3) & 31), quad (c & 7)
+          float4 v = raw[c];
+          if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          const int box = c >> 8, r = (c >> 3) & 31, q = c & 7;
+          uint2 h, l;
+          split_f16x2(v.x * sx, v.y * sx, h.x, l.x);
+          split_f16x2(v.z * sx, v.w * sx, h.y, l.y);
+          const int chunk = ((box & 1) << 2) | (q >> 1);  // 16-byte chunk of the 128-byte row (64 fp16 along k_in)
+          const int off = (box >> 1) * 4096 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4) + ((q & 1) << 3);
+          *reinterpret_cast<uint2*>(bhi + off) = h;
+          *reinterpret_cast<uint2*>(blo + off) = l;
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(full_ab(s));
+        continue;
+      }
       if (a_live) {
         // A: column t of the [32 rows][a_cols] tile -> TMEM lane t (hi | lo), plus the bias gradient
         const float* gcol = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES) + t;
@@ -852,6 +925,11 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_const
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      if (F16) {
+        const float inv = pow2f(-(f16_scale_exp(*p.g_absmax) + f16_scale_exp(*p.x_absmax)));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= inv;
       }
 #pragma unroll
       for (int gq = 0; gq < 8; ++gq) {
@@ -1056,22 +1134,22 @@ static bool make_map_4d(CUtensorMap* map, const float* ptr, uint64_t C, uint64_t
 
 struct PlaneGeom { int B, H, W; };  // conv mode only
 
-template <bool F16>
+template <bool F16, int BLOCK_N>
 static int launch_linear_persistent(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& whi, const CUtensorMap& wlo,
                                     const CUtensorMap& mout, const CUtensorMap& maux, const LinearArgs& args,
                                     cudaStream_t stream) {
-  auto kern = linear_x3_persistent_kernel<F16>;
+  auto kern = linear_x3_persistent_kernel<F16, BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem<F16>::TOTAL) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem<F16, BLOCK_N>::TOTAL) != cudaSuccess) {
       (void)cudaGetLastError();
       return T2H_ERR_CUDA;
     }
     configured = true;
   }
-  const int64_t tiles = ((args.rows + BLOCK_M - 1) / BLOCK_M) * ((args.n_out + P_BLOCK_N - 1) / P_BLOCK_N);
+  const int64_t tiles = ((args.rows + BLOCK_M - 1) / BLOCK_M) * ((args.n_out + BLOCK_N - 1) / BLOCK_N);
   const unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
-  kern<<<grid, P_THREADS, PSmem<F16>::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args, tiles);
+  kern<<<grid, P_THREADS, PSmem<F16, BLOCK_N>::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args, tiles);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
@@ -1093,9 +1171,11 @@ static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const flo
     if (args.aux_kind == 1 && !make_map(&maux, args.mask, args.n_out, args.rows, args.ld_mask, 32, BLOCK_M)) return T2H_ERR_CUDA;
     if (args.aux_kind == 2 && !make_map(&maux, args.residual, args.n_out, args.rows, args.ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
   }
-  if (BLOCK_N == 128 && A_TMEM) {
-    static const int one_tile = []() { const char* e = getenv("T2H_LINEAR_NONPERSISTENT"); return e ? atoi(e) : 0; }();  // ablation
-    if (!one_tile) return launch_linear_persistent<false>(x1, x2, whi, wlo, mout, maux, args, stream);
+  {
+    // T2H_LINEAR_NONPERSISTENT=1 (ablation): the one-tile-per-CTA kernels below; =2: only for the narrow tiles
+    static const int one_tile = []() { const char* e = getenv("T2H_LINEAR_NONPERSISTENT"); return e ? atoi(e) : 0; }();
+    if (one_tile == 0 || (one_tile == 2 && BLOCK_N == 128))
+      return launch_linear_persistent<false, BLOCK_N>(x1, x2, whi, wlo, mout, maux, args, stream);
   }
   auto kern = linear_tf32x3_kernel<BLOCK_N, A_TMEM, STAGES_>;
   static bool configured = false;  // idempotent attribute, racing threads set the same value
@@ -1221,7 +1301,8 @@ extern "C" int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const 
   if (k2 > 0) { if (!make_map(&m2, x2, k2, rows, ld_x2, BLOCK_K, BLOCK_M)) return T2H_ERR_CUDA; }
   else m2 = m1;
   const int k_total = k1 + k2;
-  if (!make_map_f16(&whi, w_hi, k_total, n_out, P_BLOCK_N) || !make_map_f16(&wlo, w_lo, k_total, n_out, P_BLOCK_N)) return T2H_ERR_CUDA;
+  const int bn = n_out <= 32 ? 32 : (n_out <= 64 ? 64 : 128);
+  if (!make_map_f16(&whi, w_hi, k_total, n_out, bn) || !make_map_f16(&wlo, w_lo, k_total, n_out, bn)) return T2H_ERR_CUDA;
   LinearArgs a;
   a.rows = rows; a.n_out = n_out;
   a.k1_chunks = (k1 + BLOCK_K - 1) / BLOCK_K;
@@ -1239,7 +1320,9 @@ extern "C" int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const 
   maux = mout;
   if (a.aux_kind == 1 && !make_map(&maux, mask, n_out, rows, ld_mask, 32, BLOCK_M)) return T2H_ERR_CUDA;
   if (a.aux_kind == 2 && !make_map(&maux, residual, n_out, rows, ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
-  return launch_linear_persistent<true>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
+  if (bn == 32) return launch_linear_persistent<true, 32>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
+  if (bn == 64) return launch_linear_persistent<true, 64>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
+  return launch_linear_persistent<true, 128>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
 }
 
 extern "C" int t2h_conv3x3_fwd(const float* x, int B, int H, int W, int cin, const float* w_hi, const float* w_lo,
@@ -1289,19 +1372,19 @@ extern "C" size_t t2h_linear_wgrad_workspace_bytes(int64_t rows, int n_out, int 
   return (size_t)wgrad_splits(rows, tiles) * n_out * (k_in + 1) * sizeof(float) + 256;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool F16 = false>
 static int launch_wgrad(const CUtensorMap& mg, const CUtensorMap& mx, WgradArgs a, int splits, cudaStream_t stream) {
-  auto kern = wgrad_tf32x3_kernel<BLOCK_N>;
+  auto kern = wgrad_x3_kernel<BLOCK_N, F16>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<BLOCK_N>::TOTAL) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<BLOCK_N, F16>::TOTAL) != cudaSuccess) {
       (void)cudaGetLastError();
       return T2H_ERR_CUDA;
     }
     configured = true;
   }
   dim3 grid((unsigned)((a.n_out + BLOCK_M - 1) / BLOCK_M), (unsigned)((a.k_in + BLOCK_N - 1) / BLOCK_N), (unsigned)splits);
-  kern<<<grid, kThreads, WgSmem<BLOCK_N>::TOTAL, stream>>>(mg, mx, a);
+  kern<<<grid, kThreads, WgSmem<BLOCK_N, F16>::TOTAL, stream>>>(mg, mx, a);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
@@ -1325,6 +1408,7 @@ extern "C" int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float
   a.partial = (float*)workspace;
   a.partial_bias = grad_b ? a.partial + (size_t)splits * n_out * k_in : nullptr;
   a.conv = 0; a.tiles_x = a.units_per_img = a.cin = 0;
+  a.g_absmax = a.x_absmax = nullptr;
   a.a_cols = n_out >= BLOCK_M ? BLOCK_M : ((n_out + 31) / 32) * 32;
   int st = T2H_OK;
   if (rows > 0) {
@@ -1341,6 +1425,40 @@ extern "C" int t2h_linear_wgrad(const float* grad_out, int64_t ld_g, const float
   return T2H_OK;
 }
 
+
+extern "C" int t2h_linear_wgrad_f16(const float* grad_out, int64_t ld_g, const uint32_t* g_absmax, const float* x,
+                                    int64_t ld_x, const uint32_t* x_absmax, int64_t rows, int n_out, int k_in, int relu_in,
+                                    void* workspace, size_t workspace_bytes, float* grad_w, int64_t ld_w, float* grad_b,
+                                    t2h_stream_t stream) {
+  if (!grad_out || !x || !g_absmax || !x_absmax || !grad_w || !workspace || rows < 0 || n_out <= 0 || k_in <= 0)
+    return T2H_ERR_INVALID_ARGUMENT;
+  if ((n_out % 4) || (k_in % 4) || (ld_g % 4) || (ld_x % 4) || (ld_w % 4) || k_in <= 64) return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)grad_out | (uintptr_t)x | (uintptr_t)grad_w | (uintptr_t)workspace) & 15) return T2H_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < t2h_linear_wgrad_workspace_bytes(rows, n_out, k_in)) return T2H_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tiles = ((n_out + BLOCK_M - 1) / BLOCK_M) * ((k_in + 127) / 128);
+  const int splits = rows > 0 ? wgrad_splits(rows, tiles) : 1;
+  WgradArgs a;
+  a.rows = rows; a.n_out = n_out; a.k_in = k_in; a.relu_in = relu_in;
+  int64_t per = (rows + splits - 1) / splits;
+  a.rows_per_split = ((per + WG_ROWS - 1) / WG_ROWS) * WG_ROWS;
+  if (a.rows_per_split < WG_ROWS) a.rows_per_split = WG_ROWS;
+  a.partial = (float*)workspace;
+  a.partial_bias = grad_b ? a.partial + (size_t)splits * n_out * k_in : nullptr;
+  a.conv = 0; a.tiles_x = a.units_per_img = a.cin = 0;
+  a.g_absmax = g_absmax; a.x_absmax = x_absmax;
+  a.a_cols = n_out >= BLOCK_M ? BLOCK_M : ((n_out + 31) / 32) * 32;
+  if (rows > 0) {
+    CUtensorMap mg, mx;
+    if (!make_map(&mg, grad_out, n_out, rows, ld_g, a.a_cols, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
+    if (!make_map(&mx, x, k_in, rows, ld_x, 32, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
+    const int st = launch_wgrad<128, true>(mg, mx, a, splits, s);
+    if (st) return st;
+  }
+  launch_wgrad_reduce(a.partial, a.partial_bias, rows > 0 ? splits : 0, n_out, k_in, grad_w, ld_w, grad_b, s);
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
 
 extern "C" size_t t2h_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int cin, int cout) {
   return t2h_linear_wgrad_workspace_bytes((int64_t)B * H * W, cout, 9 * cin);
@@ -1367,6 +1485,7 @@ extern "C" int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, i
   a.partial = (float*)workspace;
   a.partial_bias = grad_b ? a.partial + (size_t)splits * cout * k_in : nullptr;
   a.conv = 1; a.tiles_x = W / 16; a.units_per_img = (H / 2) * a.tiles_x; a.cin = cin;
+  a.g_absmax = a.x_absmax = nullptr;
   a.a_cols = cout >= BLOCK_M ? BLOCK_M : ((cout + 31) / 32) * 32;
   if (rows > 0) {
     CUtensorMap mg, mx;

@@ -75,6 +75,7 @@ USE_LIBRARY_GEMM = os.environ.get("T2H_LINEAR", "") == "cublas"
 # wide layers run the 3xFP16 flavour (twice the tensor-core rate of 3xTF32, same fp32-grade accuracy);
 # T2H_LINEAR_F16=0 keeps everything on 3xTF32 (ablation)
 USE_F16 = os.environ.get("T2H_LINEAR_F16", "1") != "0"
+USE_F16_WGRAD = USE_F16 and os.environ.get("T2H_WGRAD_F16", "1") != "0"
 
 
 def use_f16(n_out, k_total):
@@ -165,6 +166,11 @@ def _launch_wgrad(gy, x, relu_in, grad_w_view, grad_b=None):
     lib = _lib.load()
     ws_bytes = int(lib.t2h_linear_wgrad_workspace_bytes(rows, n_out, k_in))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gy.device)
+    if USE_F16_WGRAD and k_in >= 128 and n_out >= 32:
+        _lib.call("t2h_linear_wgrad_f16", ptr(gy), gy.stride(0), ptr(operand_absmax(gy)), ptr(x), x.stride(0),
+                  ptr(operand_absmax(x)), rows, n_out, k_in, int(relu_in), ptr(ws), ws_bytes, ptr(grad_w_view),
+                  grad_w_view.stride(0), ptr(grad_b))
+        return
     _lib.call("t2h_linear_wgrad", ptr(gy), gy.stride(0), ptr(x), x.stride(0), rows, n_out, k_in, int(relu_in), ptr(ws),
               ws_bytes, ptr(grad_w_view), grad_w_view.stride(0), ptr(grad_b))
 

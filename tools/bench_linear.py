@@ -35,8 +35,10 @@ for K, N in shapes:
     ref = torch.addmm(b.double(), x[:4096].relu().double(), w.double().t())
     err = ((out[:4096].double() - ref).abs().max() / ref.abs().max()).item()
     t_w = timeit(lambda: _launch_wgrad(gy, x, True, dw))
+    refw = gy.double().t() @ x.relu().double()
+    err_w = ((dw.double() - refw).abs().max() / refw.abs().max()).item()
     t_c = timeit(lambda: torch.addmm(b, x, w.t()))
     t_s = timeit(lambda: colsum(gy))
     fl = 2 * rows * K * N
     by = 4 * rows * (K + N)
-    print(f"{K:5d} {N:5d} | {t_f:8.3f} {fl/t_f/1e9:7.1f} {by/t_f/1e6:7.0f} | {t_w:8.3f} {fl/t_w/1e9:7.1f} {by/t_w/1e6:7.0f} | {t_c:9.3f} {fl/t_c/1e9:6.1f} | {t_s:.3f} | {t_32:8.3f} {fl/t_32/1e9:7.1f} | {t_a:.3f} | {err:.2e}")
+    print(f"{K:5d} {N:5d} | {t_f:8.3f} {fl/t_f/1e9:7.1f} {by/t_f/1e6:7.0f} | {t_w:8.3f} {fl/t_w/1e9:7.1f} {by/t_w/1e6:7.0f} | {t_c:9.3f} {fl/t_c/1e9:6.1f} | {t_s:.3f} | {t_32:8.3f} {fl/t_32/1e9:7.1f} | {t_a:.3f} | {err:.2e} | wgrad err {err_w:.2e}")
