@@ -273,8 +273,13 @@ def run_b200(args):
                 # (2MKN, one pass) over the MEASURED dense bf16 peak; the kernel issues 3 TF32 MMAs per
                 # algorithmic product and TF32 runs at half the bf16 rate, so 1/6 of this peak is the
                 # ceiling of the 3xTF32 scheme (stated in DESIGN.md).
+                # ceiling of the 3xTF32 scheme; the 3xFP16 kernels (*_f16) issue 3 fp16 MMAs at the bf16
+                # rate, ceiling 1/3 (stated in DESIGN.md).
+                passes = 3.0 if top.endswith("_f16") else 6.0
                 roofline = {"bound": "tensor", "kernel": top, "achieved": k["tflops"], "peak": tf_peak, "unit": "TFLOP/s",
                             "frac": k["tflops"] / tf_peak, "traffic": None, "peak_source": peak_src + " bf16 sustained",
+                            "scheme": "3xFP16" if passes == 3.0 else "3xTF32", "scheme_ceiling_frac": 1.0 / passes,
+                            "frac_of_scheme_ceiling": k["tflops"] * passes / tf_peak,
                             "hbm_gbs": k["gbs"], "hbm_frac": k["gbs"] / hbm_peak}
             else:
                 roofline = {"bound": "hbm", "kernel": top, "achieved": k["gbs"], "peak": hbm_peak, "unit": "GB/s",

@@ -190,6 +190,16 @@ size_t t2h_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int cin, int cout)
 int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, int H, int W, int cin, int cout,
                       int relu_in, void* workspace, size_t workspace_bytes, float* grad_w, float* grad_b,
                       t2h_stream_t stream);
+/* 3xFP16 flavours of the two convolution GEMMs (operand scales as for t2h_linear_fwd_f16; the weight matrix
+ * [cout, 9*cin] is split with t2h_split_f16). */
+int t2h_conv3x3_fwd_f16(const float* x, int B, int H, int W, int cin, const uint32_t* x_absmax,
+                        const uint16_t* w_hi, const uint16_t* w_lo, const uint32_t* w_absmax, int cout,
+                        const float* bias, int relu_in, const float* mask, const float* residual,
+                        float* out, uint32_t* out_absmax, t2h_stream_t stream);
+int t2h_conv3x3_wgrad_f16(const float* grad_out, const uint32_t* g_absmax, const float* x,
+                          const uint32_t* x_absmax, int B, int H, int W, int cin, int cout, int relu_in,
+                          void* workspace, size_t workspace_bytes, float* grad_w, float* grad_b,
+                          t2h_stream_t stream);
 /* bias gradient: out[c] = sum_r g[r, c], two-stage and deterministic */
 size_t t2h_colsum_workspace_bytes(int64_t rows, int n);
 int t2h_colsum(const float* g, int64_t ld_g, int64_t rows, int n, void* workspace,

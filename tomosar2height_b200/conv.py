@@ -19,7 +19,8 @@ import torch.nn.functional as F
 
 from . import _lib
 from ._lib import ptr
-from .linear import _cache, linear, USE_LIBRARY_GEMM
+from . import linear as _linear
+from .linear import _cache, linear, operand_absmax, publish_absmax, USE_LIBRARY_GEMM
 
 
 def _fwd_matrix(w):      # (Cout, Cin, 3, 3) -> [Cout, (ky, kx, ci)]
@@ -30,8 +31,17 @@ def _dgrad_matrix(w):    # -> [Cin, (ky', kx', co)] with the taps mirrored
     return w.flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1)
 
 
-def _launch_conv(x, w_hi, w_lo, cout, bias, relu_in, mask, out):
+def _launch_conv(x, split, cout, bias, relu_in, mask, out):
     B, H, W, cin = x.shape
+    if len(split) == 3:  # fp16 flavour (linear.py): operand maxima in, output maximum out
+        w_hi, w_lo, w_slot = split
+        x_slot = operand_absmax(x.view(-1, cin), owner=x)
+        out_slot = torch.empty(1, dtype=torch.int32, device=x.device)
+        _lib.call("t2h_conv3x3_fwd_f16", ptr(x), B, H, W, cin, ptr(x_slot), ptr(w_hi), ptr(w_lo), ptr(w_slot), cout, ptr(bias),
+                  int(relu_in), ptr(mask), None, ptr(out), ptr(out_slot))
+        publish_absmax(out, out_slot)
+        return
+    w_hi, w_lo = split
     _lib.call("t2h_conv3x3_fwd", ptr(x), B, H, W, cin, ptr(w_hi), ptr(w_lo), cout, ptr(bias), int(relu_in), ptr(mask),
               None, ptr(out))
 
@@ -42,9 +52,9 @@ class _Conv3x3TC(torch.autograd.Function):
         """x: channels-last (B, H, W, Cin) contiguous; returns (B, H, W, Cout)."""
         B, H, W, cin = x.shape
         cout = weight.shape[0]
-        w_hi, w_lo = _cache.get_matrix(weight, "conv3x3_fwd", _fwd_matrix)
+        split = _cache.get_matrix(weight, "conv3x3_fwd", _fwd_matrix, f16=_linear.USE_F16)
         out = torch.empty(B, H, W, cout, dtype=torch.float32, device=x.device)
-        _launch_conv(x, w_hi, w_lo, cout, bias, relu_in, None, out)
+        _launch_conv(x, split, cout, bias, relu_in, None, out)
         ctx.save_for_backward(x, weight)
         ctx.relu_in = relu_in
         ctx.has_bias = bias is not None
@@ -58,9 +68,9 @@ class _Conv3x3TC(torch.autograd.Function):
         cout = weight.shape[0]
         d_x = d_w = d_b = None
         if ctx.needs_input_grad[0]:
-            t_hi, t_lo = _cache.get_matrix(weight, "conv3x3_dgrad", _dgrad_matrix)
+            split = _cache.get_matrix(weight, "conv3x3_dgrad", _dgrad_matrix, f16=_linear.USE_F16)
             d_x = torch.empty_like(x)
-            _launch_conv(g, t_hi, t_lo, cin, None, False, x if ctx.relu_in else None, d_x)
+            _launch_conv(g, split, cin, None, False, x if ctx.relu_in else None, d_x)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             lib = _lib.load()
             ws_bytes = int(lib.t2h_conv3x3_wgrad_workspace_bytes(B, H, W, cin, cout))
@@ -68,8 +78,13 @@ class _Conv3x3TC(torch.autograd.Function):
             d_wm = torch.empty(cout, 9 * cin, dtype=torch.float32, device=g.device)
             if ctx.has_bias:
                 d_b = torch.empty(cout, dtype=torch.float32, device=g.device)
-            _lib.call("t2h_conv3x3_wgrad", ptr(g), ptr(x), B, H, W, cin, cout, int(ctx.relu_in), ptr(ws), ws_bytes,
-                      ptr(d_wm), ptr(d_b))
+            if _linear.USE_F16_WGRAD:
+                _lib.call("t2h_conv3x3_wgrad_f16", ptr(g), ptr(operand_absmax(g.view(-1, cout), owner=g)), ptr(x),
+                          ptr(operand_absmax(x.view(-1, cin), owner=x)), B, H, W, cin, cout, int(ctx.relu_in), ptr(ws),
+                          ws_bytes, ptr(d_wm), ptr(d_b))
+            else:
+                _lib.call("t2h_conv3x3_wgrad", ptr(g), ptr(x), B, H, W, cin, cout, int(ctx.relu_in), ptr(ws), ws_bytes,
+                          ptr(d_wm), ptr(d_b))
             d_w = d_wm.view(cout, 3, 3, cin).permute(0, 3, 1, 2)
         return d_x, d_w, d_b, None
 

@@ -1354,6 +1354,46 @@ extern "C" int t2h_conv3x3_fwd(const float* x, int B, int H, int W, int cin, con
   return launch_linear<128, true, 2>(mx, mx, w_hi, w_lo, k_total, a, s, &pg);
 }
 
+extern "C" int t2h_conv3x3_fwd_f16(const float* x, int B, int H, int W, int cin, const uint32_t* x_absmax,
+                                   const uint16_t* w_hi, const uint16_t* w_lo, const uint32_t* w_absmax, int cout,
+                                   const float* bias, int relu_in, const float* mask, const float* residual, float* out,
+                                   uint32_t* out_absmax, t2h_stream_t stream) {
+  if (!x || !w_hi || !w_lo || !x_absmax || !w_absmax || !out || B < 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0)
+    return T2H_ERR_INVALID_ARGUMENT;
+  if ((cin % BLOCK_K) || (cout % 4) || (W % CONV_TW) || (H % CONV_TH)) return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (mask && residual) return T2H_ERR_UNSUPPORTED_SHAPE;  // only one epilogue operand is staged in conv mode
+  if (((uintptr_t)x | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)out | (uintptr_t)bias | (uintptr_t)mask |
+       (uintptr_t)residual) & 15)
+    return T2H_ERR_INVALID_ARGUMENT;
+  if (B == 0) return T2H_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int k_total = 9 * cin;
+  const int bn = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
+  CUtensorMap mx, whi, wlo, mout, maux;
+  if (!make_map_4d(&mx, x, cin, W, H, B, BLOCK_K, CONV_TW, CONV_TH)) return T2H_ERR_CUDA;
+  if (!make_map_f16(&whi, w_hi, k_total, cout, bn) || !make_map_f16(&wlo, w_lo, k_total, cout, bn)) return T2H_ERR_CUDA;
+  if (!make_map_4d(&mout, out, cout, W, H, B, 32, CONV_TW, CONV_TH)) return T2H_ERR_CUDA;
+  maux = mout;
+  if (mask && !make_map_4d(&maux, mask, cout, W, H, B, 32, CONV_TW, CONV_TH)) return T2H_ERR_CUDA;
+  if (residual && !make_map_4d(&maux, residual, cout, W, H, B, 32, CONV_TW, CONV_TH)) return T2H_ERR_CUDA;
+  LinearArgs a;
+  a.rows = (int64_t)B * H * W; a.n_out = cout;
+  a.cin_chunks = cin / BLOCK_K;
+  a.k_chunks = a.k1_chunks = 9 * a.cin_chunks;
+  a.relu_in = relu_in; a.bias = bias; a.mask = mask; a.ld_mask = cout; a.residual = residual; a.ld_res = cout;
+  a.out = out; a.ld_out = cout;
+  a.aux_kind = mask ? 1 : (residual ? 2 : 0);
+  a.conv = 1; a.tiles_x = W / CONV_TW; a.tiles_per_img = (H / CONV_TH) * a.tiles_x;
+  a.x_absmax = x_absmax; a.w_absmax = w_absmax; a.out_absmax = out_absmax;
+  if (out_absmax && cudaMemsetAsync(out_absmax, 0, sizeof(uint32_t), s) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return T2H_ERR_CUDA;
+  }
+  if (bn == 32) return launch_linear_persistent<true, 32>(mx, mx, whi, wlo, mout, maux, a, s);
+  if (bn == 64) return launch_linear_persistent<true, 64>(mx, mx, whi, wlo, mout, maux, a, s);
+  return launch_linear_persistent<true, 128>(mx, mx, whi, wlo, mout, maux, a, s);
+}
+
 // ---- weight / bias gradient -----------------------------------------------------------------------
 static inline int wgrad_bn(int k_in) { return k_in <= 32 ? 32 : (k_in <= 64 ? 64 : 128); }
 
@@ -1464,9 +1504,10 @@ extern "C" size_t t2h_conv3x3_wgrad_workspace_bytes(int B, int H, int W, int cin
   return t2h_linear_wgrad_workspace_bytes((int64_t)B * H * W, cout, 9 * cin);
 }
 
-extern "C" int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, int H, int W, int cin, int cout,
-                                 int relu_in, void* workspace, size_t workspace_bytes, float* grad_w, float* grad_b,
-                                 t2h_stream_t stream) {
+static int conv3x3_wgrad_impl(const float* grad_out, const float* x, int B, int H, int W, int cin, int cout,
+                              int relu_in, void* workspace, size_t workspace_bytes, float* grad_w, float* grad_b,
+                              const uint32_t* g_absmax, const uint32_t* x_absmax, t2h_stream_t stream) {
+  const bool f16 = g_absmax != nullptr;
   if (!grad_out || !x || !grad_w || !workspace || B < 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) return T2H_ERR_INVALID_ARGUMENT;
   if ((cin % 32) || (cout % 4) || (W % 16) || (H % 2)) return T2H_ERR_UNSUPPORTED_SHAPE;
   if (((uintptr_t)grad_out | (uintptr_t)x | (uintptr_t)grad_w | (uintptr_t)workspace) & 15) return T2H_ERR_INVALID_ARGUMENT;
@@ -1474,7 +1515,7 @@ extern "C" int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, i
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t rows = (int64_t)B * H * W;
   const int k_in = 9 * cin;
-  const int bn = wgrad_bn(k_in);
+  const int bn = f16 ? 128 : wgrad_bn(k_in);
   const int tiles = ((cout + BLOCK_M - 1) / BLOCK_M) * ((k_in + bn - 1) / bn);
   const int splits = rows > 0 ? wgrad_splits(rows, tiles) : 1;
   WgradArgs a;
@@ -1485,14 +1526,15 @@ extern "C" int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, i
   a.partial = (float*)workspace;
   a.partial_bias = grad_b ? a.partial + (size_t)splits * cout * k_in : nullptr;
   a.conv = 1; a.tiles_x = W / 16; a.units_per_img = (H / 2) * a.tiles_x; a.cin = cin;
-  a.g_absmax = a.x_absmax = nullptr;
+  a.g_absmax = g_absmax; a.x_absmax = x_absmax;
   a.a_cols = cout >= BLOCK_M ? BLOCK_M : ((cout + 31) / 32) * 32;
   if (rows > 0) {
     CUtensorMap mg, mx;
     if (!make_map_4d(&mg, grad_out, cout, W, H, B, a.a_cols, 16, 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
-    if (!make_map_4d(&mx, x, cin, W, H, B, 32, 16, 2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
+    if (!make_map_4d(&mx, x, cin, W, H, B, 32, 16, 2, f16 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return T2H_ERR_CUDA;
     int st;
-    if (bn == 32) st = launch_wgrad<32>(mg, mx, a, splits, s);
+    if (f16) st = launch_wgrad<128, true>(mg, mx, a, splits, s);
+    else if (bn == 32) st = launch_wgrad<32>(mg, mx, a, splits, s);
     else if (bn == 64) st = launch_wgrad<64>(mg, mx, a, splits, s);
     else st = launch_wgrad<128>(mg, mx, a, splits, s);
     if (st) return st;
@@ -1500,6 +1542,21 @@ extern "C" int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, i
   launch_wgrad_reduce(a.partial, a.partial_bias, rows > 0 ? splits : 0, cout, k_in, grad_w, k_in, grad_b, s);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
+}
+
+extern "C" int t2h_conv3x3_wgrad(const float* grad_out, const float* x, int B, int H, int W, int cin, int cout,
+                                 int relu_in, void* workspace, size_t workspace_bytes, float* grad_w, float* grad_b,
+                                 t2h_stream_t stream) {
+  return conv3x3_wgrad_impl(grad_out, x, B, H, W, cin, cout, relu_in, workspace, workspace_bytes, grad_w, grad_b, nullptr,
+                            nullptr, stream);
+}
+
+extern "C" int t2h_conv3x3_wgrad_f16(const float* grad_out, const uint32_t* g_absmax, const float* x, const uint32_t* x_absmax,
+                                     int B, int H, int W, int cin, int cout, int relu_in, void* workspace,
+                                     size_t workspace_bytes, float* grad_w, float* grad_b, t2h_stream_t stream) {
+  if (!g_absmax || !x_absmax) return T2H_ERR_INVALID_ARGUMENT;
+  return conv3x3_wgrad_impl(grad_out, x, B, H, W, cin, cout, relu_in, workspace, workspace_bytes, grad_w, grad_b, g_absmax,
+                            x_absmax, stream);
 }
 
 extern "C" size_t t2h_colsum_workspace_bytes(int64_t rows, int n) {

@@ -119,18 +119,26 @@ class _AbsmaxRegistry:
 _absmax = _AbsmaxRegistry()
 
 
-def operand_absmax(x1, x2=None):
-    """device word with max |[x1 | x2]| (registered result if there is one, else one streaming pass)."""
+def operand_absmax(x1, x2=None, owner=None):
+    """device word with max |[x1 | x2]| (registered result if there is one, else one streaming pass).
+    ``owner``: the tensor object whose lifetime guards the registry entry when ``x1`` is a temporary 2-D view."""
+    owner = x1 if owner is None else owner
     if x2 is None:
-        slot = _absmax.get(x1)
+        slot = _absmax.get(owner)
         if slot is not None:
             return slot
     slot = torch.empty(1, dtype=torch.int32, device=x1.device)
     _lib.call("t2h_absmax", ptr(x1), x1.stride(0), x1.shape[1], ptr(x2), 0 if x2 is None else x2.stride(0),
               0 if x2 is None else x2.shape[1], x1.shape[0], ptr(slot))
-    if x2 is None and x1.is_contiguous():
-        _absmax.put(x1, slot)
+    if x2 is None and owner.is_contiguous():
+        _absmax.put(owner, slot)
     return slot
+
+
+def publish_absmax(t, slot):
+    """register ``slot`` (written by a kernel epilogue) as the maximum of the contiguous tensor ``t``."""
+    if t.is_contiguous():
+        _absmax.put(t, slot)
 
 
 def _rowmajor(t):
@@ -152,7 +160,7 @@ def _launch_fwd(x1, x2, split, n_out, bias, relu_in, mask, residual, out):
                   0 if mask is None else mask.stride(0), ptr(residual), 0 if residual is None else residual.stride(0),
                   ptr(out), out.stride(0), ptr(out_slot))
         if out_slot is not None:
-            _absmax.put(out, out_slot)
+            publish_absmax(out, out_slot)
         return
     w_hi, w_lo = split
     _lib.call("t2h_linear_fwd", ptr(x1), x1.stride(0), k1, ptr(x2), 0 if x2 is None else x2.stride(0), k2, rows,

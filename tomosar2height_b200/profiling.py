@@ -63,6 +63,14 @@ def _bytes(name, a):
     if name == "t2h_linear_wgrad":  # g, ld, x, ld, rows, n_out, k_in, relu, ws, ws_bytes, gw, ld, gb
         rows, n, k = a[4], a[5], a[6]
         return 4 * rows * (n + k) + 4 * n * k
+    if name == "t2h_linear_fwd_f16":  # x1, ld, k1, x2, ld, k2, rows, x_max, w_hi, w_lo, w_max, n_out, bias, relu, mask, ld, res, ld, out, ld, out_max
+        k, rows, n = a[2] + a[5], a[6], a[11]
+        return 4 * rows * (k + n + (n if a[14] else 0) + (n if a[16] else 0)) + 4 * k * n
+    if name == "t2h_linear_wgrad_f16":  # g, ld, g_max, x, ld, x_max, rows, n_out, k_in, ...
+        rows, n, k = a[6], a[7], a[8]
+        return 4 * rows * (n + k) + 4 * n * k
+    if name == "t2h_absmax":  # x1, ld, k1, x2, ld, k2, rows, slot
+        return 4 * a[6] * (a[2] + a[5])
     if name == "t2h_colsum":
         return 4 * a[2] * a[3]
     if name == "t2h_conv3x3_fwd":
@@ -71,6 +79,12 @@ def _bytes(name, a):
     if name == "t2h_conv3x3_wgrad":
         px = a[2] * a[3] * a[4]
         return 4 * px * (a[5] + a[6]) + 4 * 9 * a[5] * a[6]
+    if name == "t2h_conv3x3_fwd_f16":  # x, B, H, W, cin, x_max, w_hi, w_lo, w_max, cout, bias, relu, mask, res, out, out_max
+        px = a[1] * a[2] * a[3]
+        return 4 * px * (a[4] + a[9] + (a[9] if a[12] else 0) + (a[9] if a[13] else 0)) + 4 * 9 * a[4] * a[9]
+    if name == "t2h_conv3x3_wgrad_f16":  # g, g_max, x, x_max, B, H, W, cin, cout
+        px = a[4] * a[5] * a[6]
+        return 4 * px * (a[7] + a[8]) + 4 * 9 * a[7] * a[8]
     return 0
 
 
@@ -80,6 +94,14 @@ def _flops(name, a):
         return 2 * a[6] * (a[2] + a[5]) * a[9]
     if name == "t2h_linear_wgrad":
         return 2 * a[4] * a[5] * a[6]
+    if name == "t2h_conv3x3_fwd_f16":
+        return 2 * a[1] * a[2] * a[3] * 9 * a[4] * a[9]
+    if name == "t2h_conv3x3_wgrad_f16":
+        return 2 * a[4] * a[5] * a[6] * 9 * a[7] * a[8]
+    if name == "t2h_linear_fwd_f16":
+        return 2 * a[6] * (a[2] + a[5]) * a[11]
+    if name == "t2h_linear_wgrad_f16":
+        return 2 * a[6] * a[7] * a[8]
     if name == "t2h_conv3x3_fwd":   # x, B, H, W, cin, w_hi, w_lo, cout, ...
         return 2 * a[1] * a[2] * a[3] * 9 * a[4] * a[7]
     if name == "t2h_conv3x3_wgrad":  # g, x, B, H, W, cin, cout, ...
@@ -111,7 +133,8 @@ class KernelTimer:
             timer._orig(name, *args)
             stop.record()
             timer.records.setdefault(name, []).append((start, stop, _bytes(name, args), _flops(name, args)))
-            if name in ("t2h_linear_fwd", "t2h_linear_wgrad", "t2h_conv3x3_fwd", "t2h_conv3x3_wgrad"):
+            if name in ("t2h_linear_fwd", "t2h_linear_wgrad", "t2h_conv3x3_fwd", "t2h_conv3x3_wgrad",
+                        "t2h_linear_fwd_f16", "t2h_linear_wgrad_f16", "t2h_conv3x3_fwd_f16", "t2h_conv3x3_wgrad_f16"):
                 timer.shapes.setdefault((name, _shape(name, args)), []).append((start, stop, _flops(name, args)))
 
         _lib.call = timed_call
@@ -148,6 +171,14 @@ def _shape(name, a):
         return (a[6], a[2] + a[5], a[9])            # rows, K, N
     if name == "t2h_linear_wgrad":
         return (a[4], a[6], a[5])                   # rows, K, N
+    if name == "t2h_conv3x3_fwd_f16":
+        return (a[1] * a[2] * a[3], 9 * a[4], a[9])
+    if name == "t2h_conv3x3_wgrad_f16":
+        return (a[4] * a[5] * a[6], 9 * a[7], a[8])
+    if name == "t2h_linear_fwd_f16":
+        return (a[6], a[2] + a[5], a[11])
+    if name == "t2h_linear_wgrad_f16":
+        return (a[6], a[8], a[7])
     if name == "t2h_conv3x3_fwd":
         return (a[1] * a[2] * a[3], 9 * a[4], a[7])  # pixels, 9*cin, cout
     if name == "t2h_conv3x3_wgrad":
