@@ -17,8 +17,12 @@ def _rel(a, ref):
 @pytest.mark.parametrize("B,cin,cout,H,W", [(1, 32, 32, 8, 16), (2, 32, 64, 32, 32), (1, 64, 128, 64, 48), (2, 128, 64, 16, 16),
                                            (1, 256, 256, 32, 32), (1, 512, 256, 16, 32)])
 @pytest.mark.parametrize("relu_in", [False, True])
-def test_conv3x3_matches_fp64(B, cin, cout, H, W, relu_in):
+@pytest.mark.parametrize("flavour", ["f16", "tf32"])
+def test_conv3x3_matches_fp64(B, cin, cout, H, W, relu_in, flavour, monkeypatch):
     from tomosar2height_b200.conv import conv3x3
+    from tomosar2height_b200 import linear as L
+    monkeypatch.setattr(L, "USE_F16", flavour == "f16")        # 3xFP16 (default) or 3xTF32 entry points
+    monkeypatch.setattr(L, "USE_F16_WGRAD", flavour == "f16")
     g = torch.Generator().manual_seed(cin + cout + H)
     x = _cl(torch.randn(B, cin, H, W, generator=g).cuda()).requires_grad_(True)
     w = _cl((torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).cuda()).requires_grad_(True)

@@ -65,8 +65,12 @@ def test_linear_epilogues_and_concat():
 @pytest.mark.parametrize("rows,K,N", [(128, 32, 32), (1000, 64, 32), (5000, 32, 64), (3000, 128, 256), (2000, 512, 1024),
                                      (4100, 1024, 512), (130, 96, 48), (9000, 256, 128), (40, 64, 64)])
 @pytest.mark.parametrize("relu_in", [False, True])
-def test_linear_autograd_matches_fp64(rows, K, N, relu_in):
+@pytest.mark.parametrize("flavour", ["f16", "tf32"])
+def test_linear_autograd_matches_fp64(rows, K, N, relu_in, flavour, monkeypatch):
     from tomosar2height_b200.linear import linear
+    from tomosar2height_b200 import linear as L
+    monkeypatch.setattr(L, "USE_F16", flavour == "f16")        # wide layers: 3xFP16 (default) or 3xTF32 everywhere
+    monkeypatch.setattr(L, "USE_F16_WGRAD", flavour == "f16")
     g = torch.Generator().manual_seed(rows * 7 + K + N)
     x = torch.randn(rows, K, generator=g).cuda().requires_grad_(True)
     w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().requires_grad_(True)

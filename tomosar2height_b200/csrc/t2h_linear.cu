@@ -402,7 +402,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // TMA producer: the warp runs the loop, one elected lane issues (see tc::elect_one)
       int64_t it = 0;  // running chunk counter across tiles
       for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         int m0, n0, img, px0, py0;
@@ -411,6 +411,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           const int s = (int)(it % STAGES);
           const uint32_t ph = (uint32_t)((it / STAGES) & 1);
           mbar_wait(empty(s), ph ^ 1);
+          if (elect_one()) {
           const uint32_t stage = base + s * S::STAGE_BYTES;
           mbar_arrive_expect_tx(full_tma(s), S::X_BYTES + 2 * S::W_BYTES);
           auto load_x = [&](uint32_t dst, int c) {  // 32-wide chunk c of the (concatenated / im2col) K axis
@@ -431,35 +432,38 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
             tma_load_2d(stage + S::X_BYTES, &tm_whi, full_tma(s), kc * BLOCK_K, n0);
             tma_load_2d(stage + S::X_BYTES + S::W_BYTES, &tm_wlo, full_tma(s), kc * BLOCK_K, n0);
           }
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = F16 ? make_idesc_f16(BLOCK_M, BLOCK_N, 0, 0) : make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
-      int64_t it = 0, local = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
-        const int acc = (int)(local & 1);
-        const uint32_t acc_ph = (uint32_t)((local >> 1) & 1);
-        mbar_wait(acc_empty(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator
+    // the whole warp runs the loop (waits included); one elected lane issues the MMAs and their commits
+    constexpr uint32_t idesc = F16 ? make_idesc_f16(BLOCK_M, BLOCK_N, 0, 0) : make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
+    const uint32_t a_base = tmem_base + S::A_COL0;
+    int64_t it = 0, local = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
+      const int acc = (int)(local & 1);
+      const uint32_t acc_ph = (uint32_t)((local >> 1) & 1);
+      mbar_wait(acc_empty(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kc = 0; kc < n_steps; ++kc, ++it) {
+        const int s = (int)(it % STAGES);
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(full_tma(s), ph);
+        mbar_wait(full_ab(s), ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kc = 0; kc < n_steps; ++kc, ++it) {
-          const int s = (int)(it % STAGES);
-          const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-          mbar_wait(full_tma(s), ph);
-          mbar_wait(full_ab(s), ph);
-          tc_fence_after();
-          const uint32_t stage = base + s * S::STAGE_BYTES;
+        if (elect_one()) {
           // every k-step advances 32 bytes along the swizzled 128-byte weight row (8 tf32 or 16 fp16) and
           // 8 TMEM columns of the split x operand; small terms first
+          const uint64_t b_hi0 = make_smem_desc(base + s * S::STAGE_BYTES + S::X_BYTES, 16, 1024);
+          const uint64_t b_lo0 = make_smem_desc(base + s * S::STAGE_BYTES + S::X_BYTES + S::W_BYTES, 16, 1024);
+          const uint32_t a_hi0 = a_base + s * 64;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint32_t koff = k * 32;
-            const uint64_t b_hi = make_smem_desc(stage + S::X_BYTES + koff, 16, 1024);
-            const uint64_t b_lo = make_smem_desc(stage + S::X_BYTES + S::W_BYTES + koff, 16, 1024);
-            const uint32_t a_hi = tmem_base + S::A_COL0 + s * 64 + k * 8;
-            const uint32_t a_lo = a_hi + 32;
+            const uint64_t b_hi = b_hi0 + (uint64_t)(k * 2), b_lo = b_lo0 + (uint64_t)(k * 2);  // +32 bytes (>> 4)
+            const uint32_t a_hi = a_hi0 + k * 8, a_lo = a_hi + 32;
             if (F16) {
               mma_f16_ts(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
               mma_f16_ts(tmem_d, a_hi, b_lo, idesc, 1);
@@ -472,8 +476,10 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           }
           mma_commit(empty(s));
         }
-        mma_commit(acc_full(acc));
+        __syncwarp();
       }
+      if (elect_one()) mma_commit(acc_full(acc));
+      __syncwarp();
     }
   } else if (warp < 6) {
     // ---- operand transform: row t of every x chunk -> (hi | lo) in TMEM ---------------------------------
@@ -781,44 +787,46 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = F16 ? make_idesc_f16(BLOCK_M, BLOCK_N, 0, 1) : make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 1);  // A from TMEM, B MN-major
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(full_tma(s), ph);
-        mbar_wait(full_ab(s), ph);
-        tc_fence_after();
+    // the whole warp runs the loop; one elected lane issues the MMAs and commits (see tc::elect_one)
+    constexpr uint32_t idesc = F16 ? make_idesc_f16(BLOCK_M, BLOCK_N, 0, 1) : make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 1);  // A from TMEM, B MN-major
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(full_tma(s), ph);
+      mbar_wait(full_ab(s), ph);
+      tc_fence_after();
+      if (elect_one()) {
         if (F16) {
-          const uint32_t b_hi0 = base + s * S::STAGE_BYTES + WG_A_BYTES + B_B, b_lo0 = b_hi0 + S::B16_B;
+          const uint32_t b_hi0 = base + s * S::STAGE_BYTES + WG_A_BYTES + B_B;
+          const uint64_t d_hi0 = make_smem_desc(b_hi0, 4096, 1024, kLayoutSW128);
+          const uint64_t d_lo0 = make_smem_desc(b_hi0 + S::B16_B, 4096, 1024, kLayoutSW128);
 #pragma unroll
           for (int k = 0; k < WG_ROWS / 16; ++k) {
-            const uint32_t koff = k * 2048;  // two 8-row atoms of 1024 bytes
+            const uint64_t b_hi = d_hi0 + (uint64_t)(k * 128), b_lo = d_lo0 + (uint64_t)(k * 128);  // two 8-row atoms = 2048 bytes
             const uint32_t a_hi = tmem_d + BLOCK_N + s * S::A_COLS + k * 8, a_lo = a_hi + 16;
-            const uint64_t b_hi = make_smem_desc(b_hi0 + koff, 4096, 1024, kLayoutSW128);
-            const uint64_t b_lo = make_smem_desc(b_lo0 + koff, 4096, 1024, kLayoutSW128);
             mma_f16_ts(tmem_d, a_lo, b_hi, idesc, (it | k) != 0);
             mma_f16_ts(tmem_d, a_hi, b_lo, idesc, 1);
             mma_f16_ts(tmem_d, a_hi, b_hi, idesc, 1);
           }
-          mma_commit(empty(s));
-          continue;
-        }
-        const uint32_t b_hi0 = base + s * S::STAGE_BYTES + WG_A_BYTES, b_lo0 = b_hi0 + B_B;
+        } else {
+          const uint32_t b_hi0 = base + s * S::STAGE_BYTES + WG_A_BYTES;
+          const uint64_t d_hi0 = make_smem_desc(b_hi0, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
+          const uint64_t d_lo0 = make_smem_desc(b_hi0 + B_B, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
 #pragma unroll
-        for (int k = 0; k < WG_ROWS / UMMA_K; ++k) {
-          const uint32_t koff = k * 1024;  // 8 rows x 128 bytes
-          const uint32_t a_hi = tmem_d + BLOCK_N + s * 64 + k * UMMA_K, a_lo = a_hi + 32;
-          const uint64_t b_hi = make_smem_desc(b_hi0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
-          const uint64_t b_lo = make_smem_desc(b_lo0 + koff, WG_GROUP_BYTES, 512, kLayoutSW128Base32);
-          mma_tf32_ts(tmem_d, a_lo, b_hi, idesc, (it | k) != 0);
-          mma_tf32_ts(tmem_d, a_hi, b_lo, idesc, 1);
-          mma_tf32_ts(tmem_d, a_hi, b_hi, idesc, 1);
+          for (int k = 0; k < WG_ROWS / UMMA_K; ++k) {
+            const uint64_t b_hi = d_hi0 + (uint64_t)(k * 64), b_lo = d_lo0 + (uint64_t)(k * 64);  // 8 rows x 128 bytes
+            const uint32_t a_hi = tmem_d + BLOCK_N + s * 64 + k * UMMA_K, a_lo = a_hi + 32;
+            mma_tf32_ts(tmem_d, a_lo, b_hi, idesc, (it | k) != 0);
+            mma_tf32_ts(tmem_d, a_hi, b_lo, idesc, 1);
+            mma_tf32_ts(tmem_d, a_hi, b_hi, idesc, 1);
+          }
         }
         mma_commit(empty(s));
       }
-      mma_commit(tmem_full);
+      __syncwarp();
     }
+    if (elect_one()) mma_commit(tmem_full);
+    __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int t = quarter * 32 + lane;  // column n0 + t of g  <->  TMEM lane t
@@ -1398,10 +1406,11 @@ extern "C" int t2h_conv3x3_fwd_f16(const float* x, int B, int H, int W, int cin,
 static inline int wgrad_bn(int k_in) { return k_in <= 32 ? 32 : (k_in <= 64 ? 64 : 128); }
 
 static int wgrad_splits(int64_t rows, int tiles) {
-  int64_t want = (4 * kSMs + tiles - 1) / tiles;              // ~2 waves of 2 CTAs per SM
+  // two CTAs fit on an SM: fill at most two whole waves (rounding the split count UP would leave a third,
+  // nearly empty wave: 19 splits x 32 tiles = 608 CTAs on 592 slots cost 50% more than 18 x 32)
+  int64_t want = (4 * kSMs) / tiles;
   int64_t max_splits = (rows + WG_ROWS - 1) / WG_ROWS;
   if (want > max_splits) want = max_splits;
-  if (want > 512) want = 512;
   return (int)(want < 1 ? 1 : want);
 }
 

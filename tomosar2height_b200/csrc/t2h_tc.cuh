@@ -81,6 +81,20 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
 
+// one lane of a CONVERGED warp (the same one every time): the MMA / TMA issue loops run warp-uniformly and only
+// the issue itself is predicated, so the operands of the uniform-datapath instructions (UTCHMMA, UTMALDG) are
+// provably warp-uniform; issuing from inside an `if (lane == 0)` region makes the compiler wrap every such
+// instruction in an ELECT / BRA.U.ANY "waterfall" loop (~8 dependent instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMEM / tcgen05 ----------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
