@@ -758,11 +758,12 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
   const uint32_t tmem_d = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // TMA producer: the warp runs the loop, one elected lane issues
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(empty(s), ph ^ 1);
+        if (elect_one()) {
         const uint32_t stage = base + s * S::STAGE_BYTES;
         const int r = (int)(r_begin + (int64_t)it * WG_ROWS);
         mbar_arrive_expect_tx(full_tma(s), (uint32_t)(WG_ROWS * p.a_cols * 4) + B_B);
@@ -784,6 +785,8 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
           for (int gq = 0; gq < BLOCK_N / 32; ++gq)
             tma_load_2d(stage + WG_A_BYTES + gq * WG_GROUP_BYTES, &tm_x, full_tma(s), k0 + gq * 32, r);
         }
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -868,10 +871,12 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
         uint8_t* blo = bhi + S::B16_B;
 #pragma unroll
         for (int i = 0; i < B_B / 16 / 128; ++i) {
-          const int c = t + i * 128;           // float4 index: box (c >> 8), row ((c >> 3) & 31), quad (c & 7)
-          float4 v = raw[c];
+          // 16 consecutive lanes take one row of a box PAIR (2 x 8 float4 in, one whole 128-byte fp16 row out):
+          // quarter-warps read 128 contiguous bytes, half-warps write 128 contiguous (swizzled) bytes
+          const int unit = (t >> 4) + 8 * i, r = unit & 31, j = t & 15;
+          const int box = 2 * (unit >> 5) + (j >> 3), q = j & 7;
+          float4 v = raw[box * 256 + r * 8 + q];
           if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          const int box = c >> 8, r = (c >> 3) & 31, q = c & 7;
           uint2 h, l;
           split_f16x2(v.x * sx, v.y * sx, h.x, l.x);
           split_f16x2(v.z * sx, v.w * sx, h.y, l.y);

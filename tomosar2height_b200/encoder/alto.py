@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from .. import functional as T
 from ..conv import apply_conv
+from ..linear import use_f16, publish_absmax, operand_absmax
 from ..linear import linear
 from ..topology import Topology
 from .unet import conv3x3, conv1x1, upconv2x2, check_modes, xavier_normal_convs
@@ -33,7 +34,13 @@ class _Exchange:
         """plane ``c`` (B, C, r, r) sampled at the points of topology ``p`` -> (B*N, C) sorted rows
         (alto.py:90-95 / 199-205)."""
         level = p.level(c.shape[2])
-        return T.bilinear_sample(T.nchw_to_plane(c), level)
+        plane = T.nchw_to_plane(c)
+        sampled = T.bilinear_sample(plane, level)
+        if use_f16(2 * c.shape[1], c.shape[1]):
+            # operand scale of the fp16 GEMM that consumes the samples: bilinear interpolation is a convex
+            # combination, so max |plane| (a small tensor, often already known) bounds max |sampled|
+            publish_absmax(sampled, operand_absmax(plane.view(-1, plane.shape[-1]), owner=plane))
+        return sampled
 
     @staticmethod
     def generate_plane_features(p, c, channel, reso_plane):
