@@ -286,6 +286,16 @@ def run_b200(args):
                             "frac": k["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src}
             roofline.update({"launches": k["launches"], "ms_avg": k["ms_avg"], "bytes_per_launch": k["bytes_per_launch"],
                              "share_of_step": k["ms_total"] / (ms / args.steps)})
+            # measured DRAM traffic of ONE profiled launch of this kernel (ncu --set full, committed under profiles/);
+            # the launches of a step have many shapes, so the capture's own shape and algorithmic bytes ride along
+            try:
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+                    cap = json.load(f)
+                if cap.get("kernel") == top:
+                    roofline["traffic"] = cap["dram_bytes"]
+                    roofline["traffic_capture"] = {k2: cap[k2] for k2 in ("capture", "algorithmic_bytes", "note") if k2 in cap}
+            except (OSError, ValueError, KeyError):
+                pass
         line = {
             "metric": "fwd+bwd points/s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -715,8 +715,11 @@ struct WgSmem {
   static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
 };
 
+// producer warp, MMA warp, 4 warps that split g^T into tensor memory + half of the x tile and run the epilogue,
+// 4 more warps for the other half of the x tile (the operand conversion is what bounds this kernel)
+constexpr int WG_THREADS = 320;
 template <int BLOCK_N, bool F16>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(WG_THREADS)
 wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, const WgradArgs p) {
   using S = WgSmem<BLOCK_N, F16>;
   constexpr int STAGES = S::STAGES;
@@ -743,7 +746,7 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_tma(s), 1);
-      mbar_init(full_ab(s), 128);
+      mbar_init(full_ab(s), 256);
       mbar_init(empty(s), 1);
     }
     mbar_init(tmem_full, 1);
@@ -832,10 +835,12 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    const int t = quarter * 32 + lane;  // column n0 + t of g  <->  TMEM lane t
-    const bool a_live = quarter * 32 < p.a_cols;  // warp-uniform: this quarter holds real columns of g
+    const int t = quarter * 32 + lane;  // column n0 + t of g  <->  TMEM lane t   (warps 2-5)
+    const int tt = threadIdx.x - 64;    // 0..255 over all eight transform warps
+    const bool a_warp = warp < 6;       // these own a TMEM lane quarter: g^T operand and epilogue
+    const bool a_live = a_warp && quarter * 32 < p.a_cols;  // warp-uniform: this quarter holds real columns of g
     float bias_acc = 0.f;
-    if (!a_live) {  // lanes beyond the loaded columns: zero operand rows, written once for every stage
+    if (a_warp && !a_live) {  // lanes beyond the loaded columns: zero operand rows, written once for every stage
       float z[32];
 #pragma unroll
       for (int r = 0; r < 32; ++r) z[r] = 0.f;
@@ -870,10 +875,10 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
         uint8_t* bhi = base_ptr + s * S::STAGE_BYTES + WG_A_BYTES + B_B;
         uint8_t* blo = bhi + S::B16_B;
 #pragma unroll
-        for (int i = 0; i < B_B / 16 / 128; ++i) {
+        for (int i = 0; i < B_B / 16 / 256; ++i) {
           // 16 consecutive lanes take one row of a box PAIR (2 x 8 float4 in, one whole 128-byte fp16 row out):
           // quarter-warps read 128 contiguous bytes, half-warps write 128 contiguous (swizzled) bytes
-          const int unit = (t >> 4) + 8 * i, r = unit & 31, j = t & 15;
+          const int unit = (tt >> 4) + 16 * i, r = unit & 31, j = tt & 15;
           const int box = 2 * (unit >> 5) + (j >> 3), q = j & 7;
           float4 v = raw[box * 256 + r * 8 + q];
           if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -909,7 +914,7 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
       float4* bhi = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES + WG_A_BYTES);
       float4* blo = reinterpret_cast<float4*>(base_ptr + s * S::STAGE_BYTES + WG_A_BYTES + B_B);
 #pragma unroll
-      for (int c = t; c < B_B / 16; c += 128) {
+      for (int c = tt; c < B_B / 16; c += 256) {
         float4 v = bhi[c];
         if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         float4 h, l;
@@ -923,14 +928,14 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
       mbar_arrive(full_ab(s));
     }
     const int n = n0 + t;
-    if (p.partial_bias && blockIdx.y == 0 && n < p.n_out) p.partial_bias[(int64_t)blockIdx.z * p.n_out + n] = bias_acc;
+    if (a_warp && p.partial_bias && blockIdx.y == 0 && n < p.n_out) p.partial_bias[(int64_t)blockIdx.z * p.n_out + n] = bias_acc;
     float* dst = p.partial + ((int64_t)blockIdx.z * p.n_out + n) * p.k_in;
-    if (n_iter > 0) {
+    if (a_warp && n_iter > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = 0; a_warp && c0 < BLOCK_N; c0 += 32) {
       float v[32];
       if (n_iter > 0) {
         __syncwarp();
@@ -1438,7 +1443,7 @@ static int launch_wgrad(const CUtensorMap& mg, const CUtensorMap& mx, WgradArgs 
     configured = true;
   }
   dim3 grid((unsigned)((a.n_out + BLOCK_M - 1) / BLOCK_M), (unsigned)((a.k_in + BLOCK_N - 1) / BLOCK_N), (unsigned)splits);
-  kern<<<grid, kThreads, WgSmem<BLOCK_N, F16>::TOTAL, stream>>>(mg, mx, a);
+  kern<<<grid, WG_THREADS, WgSmem<BLOCK_N, F16>::TOTAL, stream>>>(mg, mx, a);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }

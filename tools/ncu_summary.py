@@ -20,5 +20,7 @@ for r in rows[2:]:
     for k in KEYS:
         if k in hdr:
             print(f"    {k:90s} {r[hdr.index(k)]:>18s} {units[hdr.index(k)]}")
-    rd, wr = (float(r[hdr.index(k)]) if k in hdr else 0.0 for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    print(f"    {'traffic = dram read + write (units as above)':90s} {rd + wr:18.3f}")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot = sum(float(r[hdr.index(k)]) * scale.get(units[hdr.index(k)], 1.0)
+              for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in hdr)
+    print(f"    {'traffic = dram__bytes_read.sum + dram__bytes_write.sum':90s} {tot / 1e9:18.6f} GB")
