@@ -154,6 +154,11 @@ int t2h_absmax(const float* x1, int64_t ld_x1, int k1, const float* x2, int64_t 
                int64_t rows, uint32_t* slot, t2h_stream_t stream);
 int t2h_split_f16(const float* w, int64_t n, const uint32_t* absmax, uint16_t* hi, uint16_t* lo,
                   t2h_stream_t stream);
+/* out = a + b (n fp32 values, n % 4 == 0) and *slot = bit pattern of max |out|: the sum of the two gradient
+ * branches of a tensor that is used twice (autograd's accumulation), with the operand maximum of the GEMM
+ * that consumes it taken on the way */
+int t2h_add_absmax(const float* a, const float* b, int64_t n, float* out, uint32_t* slot,
+                   t2h_stream_t stream);
 int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const float* x2, int64_t ld_x2, int k2,
                        int64_t rows, const uint32_t* x_absmax, const uint16_t* w_hi,
                        const uint16_t* w_lo, const uint32_t* w_absmax, int n_out, const float* bias,

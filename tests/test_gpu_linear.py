@@ -278,3 +278,24 @@ def test_absmax_registry_is_reused_and_never_stale():
     y = L.linear(h, w2, relu_in=True)
     ref = h.double().relu() @ w2.double().t()
     assert torch.isfinite(y).all() and (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+
+
+def test_fork2_sums_gradient_branches_and_publishes_their_maximum():
+    from tomosar2height_b200 import linear as L
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(5000, 256, generator=g).cuda().requires_grad_(True)
+    w = torch.nn.Parameter((torch.randn(128, 256, generator=g) / 16).cuda())
+    h = L.linear(x, torch.nn.Parameter((torch.randn(256, 256, generator=g) / 16).cuda()))
+    a, b = L.fork2(h)
+    seen = {}
+    h.register_hook(lambda gr: seen.setdefault("g", gr))
+    (L.linear(a, w).square().sum() + (b * 3.0).sum()).backward()
+    gr = seen["g"]
+    ref = (2 * (h.detach().double() @ w.double().t()) @ w.double()) + 3.0
+    assert (gr.double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+    slot = L._absmax.get(gr)
+    assert slot is not None and slot.view(torch.float32).item() == gr.abs().max().item()
+    # without autograd the fork is the identity
+    with torch.no_grad():
+        p, q = L.fork2(h)
+    assert p is h and q is h

@@ -53,6 +53,7 @@ SIGNATURES = {
     "t2h_linear_wgrad_f16": [_p, _i64, _p, _p, _i64, _p, _i64, _i32, _i32, _i32, _p, _sz, _p, _i64, _p, _p],
     "t2h_conv3x3_fwd_f16": [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _p],
     "t2h_conv3x3_wgrad_f16": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _sz, _p, _p, _p],
+    "t2h_add_absmax": [_p, _p, _i64, _p, _p, _p],
     "t2h_absmax": [_p, _i64, _i32, _p, _i64, _i32, _i64, _p, _p],
     "t2h_split_f16": [_p, _i64, _p, _p, _p, _p],
     "t2h_linear_fwd_f16": [_p, _i64, _i32, _p, _i64, _i32, _i64, _p, _p, _p, _p, _i32, _p, _i32, _p, _i64, _p, _i64, _p,

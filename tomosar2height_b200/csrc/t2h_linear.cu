@@ -1082,6 +1082,44 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
   }
 }
 
+// out = a + b with max |out| merged into *slot: the sum of two gradient branches is the operand of the next
+// input-gradient GEMM, so its maximum is taken while it is being written instead of in a second pass
+__global__ void __launch_bounds__(256) add_absmax_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int64_t n4,
+                                                         float4* __restrict__ out, uint32_t* __restrict__ slot) {
+  float m = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+    float4 va[4], vb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = i + u * stride;
+      if (j < n4) { va[u] = __ldg(a + j); vb[u] = __ldg(b + j); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = i + u * stride;
+      if (j < n4) {
+        const float4 o = make_float4(va[u].x + vb[u].x, va[u].y + vb[u].y, va[u].z + vb[u].z, va[u].w + vb[u].w);
+        out[j] = o;
+        m = __uint_as_float(max(max(__float_as_uint(fabsf(o.x)), __float_as_uint(fabsf(o.y))),
+                                max(max(__float_as_uint(fabsf(o.z)), __float_as_uint(fabsf(o.w))), __float_as_uint(m))));
+      }
+    }
+  }
+  uint32_t bits = __float_as_uint(m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+  __shared__ uint32_t warp_max[8];
+  if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = bits;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    bits = warp_max[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffu, bits, o));
+    if (threadIdx.x == 0 && bits) atomicMax(slot, bits);
+  }
+}
+
 __global__ void split_f16_kernel(const float* __restrict__ w, int64_t n2, const uint32_t* __restrict__ absmax,
                                  uint32_t* __restrict__ hi, uint32_t* __restrict__ lo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1284,6 +1322,22 @@ extern "C" int t2h_absmax(const float* x1, int64_t ld_x1, int k1, const float* x
     absmax_kernel<<<(unsigned)blocks, 256, 0, s>>>(xs[i], lds[i], ks[i] / 4, n4, slot);
     T2H_CHECK_LAUNCH();
   }
+  return T2H_OK;
+}
+
+extern "C" int t2h_add_absmax(const float* a, const float* b, int64_t n, float* out, uint32_t* slot, t2h_stream_t stream) {
+  if (!a || !b || !out || !slot || n < 0) return T2H_ERR_INVALID_ARGUMENT;
+  if (n % 4) return T2H_ERR_UNSUPPORTED_SHAPE;
+  if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) return T2H_ERR_INVALID_ARGUMENT;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(slot, 0, sizeof(uint32_t), s) != cudaSuccess) { (void)cudaGetLastError(); return T2H_ERR_CUDA; }
+  if (n == 0) return T2H_OK;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 1023) / 1024;
+  if (blocks > 8 * kSMs) blocks = 8 * kSMs;
+  add_absmax_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), n4,
+                                                     reinterpret_cast<float4*>(out), slot);
+  T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
 

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from .. import functional as T
 from ..conv import apply_conv
-from ..linear import use_f16, publish_absmax, operand_absmax
+from ..linear import use_f16, publish_absmax, operand_absmax, fork2
 from ..linear import linear
 from ..topology import Topology
 from .unet import conv3x3, conv1x1, upconv2x2, check_modes, xavier_normal_convs
@@ -53,7 +53,9 @@ class _Exchange:
         hidden = linear(sampled, self.fc_comm[0].weight, self.fc_comm[0].bias)
         carry = None if c_last is None else linear(c_last, self.fc_c.weight, self.fc_c.bias)
         c = linear(hidden, self.fc_comm[2].weight, self.fc_comm[2].bias, relu_in=True, residual=carry)
-        return self.generate_plane_features(p, c, plane.shape[1], plane.shape[2]), c
+        # c feeds the mean-scatter AND the next level's fc_c: sum the two gradient branches in one kernel
+        c_plane, c_next = fork2(c)
+        return self.generate_plane_features(p, c_plane, plane.shape[1], plane.shape[2]), c_next
 
 
 class DownConv(nn.Module, _Exchange):

@@ -141,6 +141,36 @@ def publish_absmax(t, slot):
         _absmax.put(t, slot)
 
 
+class _Fork2(torch.autograd.Function):
+    """Identity with two outputs.  A tensor that feeds two consumers gets its gradient as the sum of two
+    branches; autograd would add them with a library kernel and the fp16 GEMM that consumes the sum would then
+    need a pass of its own for the operand maximum.  The backward of this node does both in one kernel."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None or g2 is None:
+            return g1 if g2 is None else g2
+        if not (g1.is_cuda and g1.dtype == torch.float32 and g1.is_contiguous() and g2.is_contiguous()
+                and g1.numel() % 4 == 0 and g1.data_ptr() % 16 == 0 and g2.data_ptr() % 16 == 0):
+            return g1 + g2
+        out = torch.empty_like(g1)
+        slot = torch.empty(1, dtype=torch.int32, device=g1.device)
+        _lib.call("t2h_add_absmax", ptr(g1), ptr(g2), g1.numel(), ptr(out), ptr(slot))
+        publish_absmax(out, slot)
+        return out
+
+
+def fork2(x):
+    """``x`` twice, for two consumers (see ``_Fork2``); a plain pass-through when no gradient is needed."""
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        return x, x
+    return _Fork2.apply(x)
+
+
 def _rowmajor(t):
     """2-D fp32 CUDA view usable by TMA: unit column stride, 16-byte aligned base and pitch."""
     if t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16:
