@@ -69,6 +69,8 @@ def _bytes(name, a):
     if name == "t2h_linear_wgrad_f16":  # g, ld, g_max, x, ld, x_max, rows, n_out, k_in, ...
         rows, n, k = a[6], a[7], a[8]
         return 4 * rows * (n + k) + 4 * n * k
+    if name == "t2h_add_absmax":  # a, b, n, out, slot
+        return 12 * a[2]
     if name == "t2h_absmax":  # x1, ld, k1, x2, ld, k2, rows, slot
         return 4 * a[6] * (a[2] + a[5])
     if name == "t2h_colsum":
