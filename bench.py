@@ -113,7 +113,7 @@ def cpu_reference_step(cfg, params, cloud, dsm):
     pa, pb = oracle.oracle_forward(P, cfg, cloud)
     loss = oracle.oracle_loss(pa, pb, dsm, False)
     loss.backward()
-    return time.perf_counter() - t0, float(loss)
+    return time.perf_counter() - t0, float(loss.detach())
 
 
 def run_reference(args):
