@@ -121,6 +121,10 @@ def _oracle_rows(fn, rows, cloud, reso, B, N):
 def test_seg_max_pool_fwd_bwd(T, C, sorted_rows):
     B, N, R = 2, 6000, 64
     cloud = synthetic_cloud(B, N, seed=C)
+    # a facade: 2500 points of tile 0 in ONE fine cell and 900 of tile 1 in another (the kernels hand cells with
+    # more than 128 rows to the whole CTA), with exact ties among them
+    cloud[0, 500:3000, :2] = torch.tensor([0.4005, 0.7003]) + 1e-4 * torch.rand(2500, 2, generator=torch.Generator().manual_seed(7))
+    cloud[1, 100:1000, :2] = torch.tensor([0.9101, 0.0303]) + 1e-4 * torch.rand(900, 2, generator=torch.Generator().manual_seed(8))
     topo = _topo(cloud, R)
     g = torch.Generator().manual_seed(C + 1)
     feat = torch.randn(B * N, C, generator=g)

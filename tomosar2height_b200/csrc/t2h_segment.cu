@@ -32,84 +32,151 @@ __device__ __forceinline__ int64_t plane_row(const SegGeom& g, int64_t seg) {
   return (b << g.log2_cells) + (int64_t)iy * g.reso + ix;
 }
 
+// Cells with more than kHeavyMax rows (a facade in a clustered tile holds thousands of points) are not walked by
+// their one warp -- that warp would run long after the rest of the grid has finished -- but deferred and
+// processed by all eight warps of the CTA, partial results combined through shared memory.  The (value,
+// original point index) order that decides the argmax is total, so the combination order does not matter.
+constexpr int kHeavyMax = 128;
+
 template <class RS>
 __global__ void __launch_bounds__(kSegWarps * kWarp)
 seg_max_fwd_kernel(const float* __restrict__ rows, SegGeom g, float* __restrict__ pooled,
                    float* __restrict__ plane, int32_t* __restrict__ arg) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  const int lane = threadIdx.x & 31;
-  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
-  if (seg >= g.n_seg) return;
+  constexpr bool DEFER = C <= 256;  // 64 * C bytes of shared memory for the partial results
+  __shared__ float hv_val[DEFER ? kSegWarps * C : 1];
+  __shared__ int hv_pos[DEFER ? kSegWarps * C : 1];
+  __shared__ int hv_beg[kSegWarps], hv_len[kSegWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + warp;
+  const bool valid = seg < g.n_seg;
   const int sub = lane / LPR, l = lane % LPR;
-  const int beg = g.cell_start[seg << g.shift], end = g.cell_start[(seg + 1) << g.shift];
+  int beg = 0, end = 0;
+  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
+  const bool heavy = DEFER && valid && end - beg > kHeavyMax;
+  if (DEFER && lane == 0) { hv_len[warp] = heavy ? end - beg : 0; hv_beg[warp] = beg; }
 
   float best[CH][4];
   int bpos[CH][4];
-#pragma unroll
-  for (int c = 0; c < CH; ++c)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { best[c][k] = -FLT_MAX; bpos[c][k] = INT32_MAX; }
-
-  for (int i = beg + sub; i < end; i += RPI) {
-    const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
-    const float* src = rows + row * C + l * 4;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      float4 v = ld4(src + c * LPR * 4);
-      const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        // strict >: the first row wins ties (rows of one fine cell are in point order); inside a
-        // coarser segment equal values are resolved by the original point index
-        bool take = e[k] > best[c][k];
-        if (g.tie && e[k] == best[c][k] && bpos[c][k] != INT32_MAX) take = g.tie[i] < g.tie[bpos[c][k]];
-        if (take) { best[c][k] = e[k]; bpos[c][k] = i; }
-      }
-    }
-  }
-  // merge the RPI sub-rows: larger value wins, equal values -> smaller sorted position
-#pragma unroll
-  for (int off = LPR; off < kWarp; off <<= 1) {
+  auto reset = [&]() {
 #pragma unroll
     for (int c = 0; c < CH; ++c)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float ov = __shfl_xor_sync(0xffffffffu, best[c][k], off);
-        int op = __shfl_xor_sync(0xffffffffu, bpos[c][k], off);
-        bool take = ov > best[c][k];
-        if (ov == best[c][k] && op != INT32_MAX && bpos[c][k] != INT32_MAX)
-          take = g.tie ? (g.tie[op] < g.tie[bpos[c][k]]) : (op < bpos[c][k]);
-        if (take) { best[c][k] = ov; bpos[c][k] = op; }
+      for (int k = 0; k < 4; ++k) { best[c][k] = -FLT_MAX; bpos[c][k] = INT32_MAX; }
+  };
+  // does candidate (ov, op) beat (bv, bp)?  larger value; equal values -> smaller original point index
+  // (= smaller sorted position when the sorted order inside the segment is the point order)
+  auto beats = [&](float ov, int op, float bv, int bp) -> bool {
+    if (ov > bv) return true;
+    if (ov == bv && op != INT32_MAX && bp != INT32_MAX) return g.tie ? (g.tie[op] < g.tie[bp]) : (op < bp);
+    return false;
+  };
+  auto scan = [&](int first, int last, int step) {
+    for (int i = first; i < last; i += step) {
+      const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+      const float* src = rows + row * C + l * 4;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float4 v = ld4(src + c * LPR * 4);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // strict >: the first row wins ties (rows of one fine cell are in point order); inside a
+          // coarser segment equal values are resolved by the original point index
+          bool take = e[k] > best[c][k];
+          if (g.tie && e[k] == best[c][k] && bpos[c][k] != INT32_MAX) take = g.tie[i] < g.tie[bpos[c][k]];
+          if (take) { best[c][k] = e[k]; bpos[c][k] = i; }
+        }
       }
-  }
-  const bool empty = beg >= end;
-  const int64_t prow = plane_row(g, seg);
-#pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    float4 v;
-    int4 a;
-    int* ap = &a.x;
-    float* vp = &v.x;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool none = empty || bpos[c][k] == INT32_MAX;
-      vp[k] = none ? 0.0f : best[c][k];
-      ap[k] = none ? -1 : (g.perm ? g.perm[bpos[c][k]] : bpos[c][k]);
-      best[c][k] = vp[k];
     }
-    if (sub == 0) {
-      const int64_t o = prow * C + (c * LPR + l) * 4;
-      if (plane) st4(plane + o, v);
-      *reinterpret_cast<int4*>(arg + o) = a;
+  };
+  auto merge_subs = [&]() {  // the RPI sub-rows of the warp
+#pragma unroll
+    for (int off = LPR; off < kWarp; off <<= 1) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best[c][k], off);
+          const int op = __shfl_xor_sync(0xffffffffu, bpos[c][k], off);
+          if (beats(ov, op, best[c][k], bpos[c][k])) { best[c][k] = ov; bpos[c][k] = op; }
+        }
     }
-  }
-  if (pooled) {
-    for (int i = beg + sub; i < end; i += RPI) {
+  };
+  // plane / arg of segment `sg` (written by the sub-row 0 lanes when `writer`); best becomes the pooled value
+  auto emit = [&](int64_t sg, bool empty, bool writer) {
+    const int64_t prow = plane_row(g, sg);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 v;
+      int4 a;
+      int* ap = &a.x;
+      float* vp = &v.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool none = empty || bpos[c][k] == INT32_MAX;
+        vp[k] = none ? 0.0f : best[c][k];
+        ap[k] = none ? -1 : (g.perm ? g.perm[bpos[c][k]] : bpos[c][k]);
+        best[c][k] = vp[k];
+      }
+      if (writer && sub == 0) {
+        const int64_t o = prow * C + (c * LPR + l) * 4;
+        if (plane) st4(plane + o, v);
+        *reinterpret_cast<int4*>(arg + o) = a;
+      }
+    }
+  };
+  auto gather_back = [&](int first, int last, int step) {
+    for (int i = first; i < last; i += step) {
       const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
       float* dst = pooled + row * C + l * 4;
 #pragma unroll
       for (int c = 0; c < CH; ++c)
         st4(dst + c * LPR * 4, make_float4(best[c][0], best[c][1], best[c][2], best[c][3]));
+    }
+  };
+
+  if (valid && !heavy) {
+    reset();
+    scan(beg + sub, end, RPI);
+    merge_subs();
+    emit(seg, beg >= end, true);
+    if (pooled) gather_back(beg + sub, end, RPI);
+  }
+  if constexpr (DEFER) {
+    __syncthreads();
+    for (int w = 0; w < kSegWarps; ++w) {
+      const int hl = hv_len[w];
+      if (hl == 0) continue;  // uniform across the CTA
+      const int hb = hv_beg[w];
+      reset();
+      scan(hb + warp * RPI + sub, hb + hl, kSegWarps * RPI);
+      merge_subs();
+      if (sub == 0) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            hv_val[warp * C + (c * LPR + l) * 4 + k] = best[c][k];
+            hv_pos[warp * C + (c * LPR + l) * 4 + k] = bpos[c][k];
+          }
+      }
+      __syncthreads();
+      // every warp folds the eight partials (it needs the result for the gather-back of its rows)
+      for (int q = 0; q < kSegWarps; ++q) {
+        if (q == warp) continue;
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float ov = hv_val[q * C + (c * LPR + l) * 4 + k];
+            const int op = hv_pos[q * C + (c * LPR + l) * 4 + k];
+            if (beats(ov, op, best[c][k], bpos[c][k])) { best[c][k] = ov; bpos[c][k] = op; }
+          }
+      }
+      emit((int64_t)blockIdx.x * kSegWarps + w, false, warp == 0);
+      if (pooled) gather_back(hb + warp * RPI + sub, hb + hl, kSegWarps * RPI);
+      __syncthreads();  // the partial buffers are free again
     }
   }
 }
@@ -119,19 +186,25 @@ __global__ void __launch_bounds__(kSegWarps * kWarp)
 seg_max_bwd_kernel(const float* __restrict__ grad_pooled, const float* __restrict__ grad_plane, SegGeom g,
                    const int32_t* __restrict__ arg, float* __restrict__ grad_rows) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  const int lane = threadIdx.x & 31;
-  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
-  if (seg >= g.n_seg) return;
+  constexpr bool DEFER = C <= 256;
+  __shared__ float4 hv_sum[DEFER ? kSegWarps * (C / 4) : 1];
+  __shared__ int hv_beg[kSegWarps], hv_len[kSegWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + warp;
+  const bool valid = seg < g.n_seg;
   const int sub = lane / LPR, l = lane % LPR;
-  const int beg = g.cell_start[seg << g.shift], end = g.cell_start[(seg + 1) << g.shift];
-  if (beg >= end) return;
-  const int64_t prow = plane_row(g, seg);
+  int beg = 0, end = 0;
+  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
+  const bool heavy = DEFER && valid && end - beg > kHeavyMax;
+  if (DEFER && lane == 0) { hv_len[warp] = heavy ? end - beg : 0; hv_beg[warp] = beg; }
 
   float4 acc[CH];
+  auto reset = [&]() {
 #pragma unroll
-  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (grad_pooled) {
-    for (int i = beg + sub; i < end; i += RPI) {
+    for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto sum_rows = [&](int first, int last, int step) {  // pooled-gradient rows, then the RPI sub-rows of the warp
+    for (int i = first; i < last; i += step) {
       const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
       const float* src = grad_pooled + row * C + l * 4;
 #pragma unroll
@@ -147,28 +220,67 @@ seg_max_bwd_kernel(const float* __restrict__ grad_pooled, const float* __restric
         float4 o = shfl_xor4(acc[c], off);
         acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
       }
-  }
-  int4 a[CH];
-#pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int64_t o = prow * C + (c * LPR + l) * 4;
-    a[c] = *reinterpret_cast<const int4*>(arg + o);
-    if (grad_plane) {
-      float4 v = ld4(grad_plane + o);
-      acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
-    }
-  }
-  for (int i = beg + sub; i < end; i += RPI) {
-    const int row32 = g.perm ? g.perm[i] : i;
-    float* dst = grad_rows + (int64_t)row32 * C + l * 4;
+  };
+  // add the plane gradient, then route the total to the saved argmax row of every channel
+  auto route = [&](int64_t sg, int first, int last, int step) {
+    const int64_t prow = plane_row(g, sg);
+    int4 a[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      float4 v;
-      v.x = a[c].x == row32 ? acc[c].x : 0.f;
-      v.y = a[c].y == row32 ? acc[c].y : 0.f;
-      v.z = a[c].z == row32 ? acc[c].z : 0.f;
-      v.w = a[c].w == row32 ? acc[c].w : 0.f;
-      st4(dst + c * LPR * 4, v);
+      const int64_t o = prow * C + (c * LPR + l) * 4;
+      a[c] = *reinterpret_cast<const int4*>(arg + o);
+      if (grad_plane) {
+        float4 v = ld4(grad_plane + o);
+        acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+      }
+    }
+    for (int i = first; i < last; i += step) {
+      const int row32 = g.perm ? g.perm[i] : i;
+      float* dst = grad_rows + (int64_t)row32 * C + l * 4;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        float4 v;
+        v.x = a[c].x == row32 ? acc[c].x : 0.f;
+        v.y = a[c].y == row32 ? acc[c].y : 0.f;
+        v.z = a[c].z == row32 ? acc[c].z : 0.f;
+        v.w = a[c].w == row32 ? acc[c].w : 0.f;
+        st4(dst + c * LPR * 4, v);
+      }
+    }
+  };
+
+  if (valid && !heavy && beg < end) {
+    reset();
+    if (grad_pooled) sum_rows(beg + sub, end, RPI);
+    route(seg, beg + sub, end, RPI);
+  }
+  if constexpr (DEFER) {
+    __syncthreads();
+    for (int w = 0; w < kSegWarps; ++w) {
+      const int hl = hv_len[w];
+      if (hl == 0) continue;  // uniform across the CTA
+      const int hb = hv_beg[w];
+      reset();
+      if (grad_pooled) {
+        // contiguous slice per warp, partial sums added in warp order: a fixed order, like the light path
+        const int slice = (hl + kSegWarps - 1) / kSegWarps;
+        const int my_beg = min(hb + warp * slice, hb + hl), my_end = min(my_beg + slice, hb + hl);
+        sum_rows(my_beg + sub, my_end, RPI);
+        if (sub == 0) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) hv_sum[warp * (C / 4) + c * LPR + l] = acc[c];
+        }
+        __syncthreads();
+        reset();
+        for (int q = 0; q < kSegWarps; ++q)
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const float4 o = hv_sum[q * (C / 4) + c * LPR + l];
+            acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
+          }
+      }
+      route((int64_t)blockIdx.x * kSegWarps + w, hb + warp * RPI + sub, hb + hl, kSegWarps * RPI);
+      __syncthreads();  // hv_sum is free again
     }
   }
 }
