@@ -418,25 +418,43 @@ seg_reduce_fwd_kernel(const float* __restrict__ rows, SegGeom g, int mean, float
 template <class RS>
 __global__ void __launch_bounds__(kSegWarps * kWarp)
 seg_broadcast_kernel(const float* __restrict__ plane, SegGeom g, int mean, float* __restrict__ rows) {
+  // Light cells: one warp writes the cell's rows (CTA z = 0 only).  Cells with more than kHeavyMax rows are
+  // deferred: all eight warps of the CTA -- and, on coarse levels, the gridDim.y CTAs that share the cell
+  // group -- write interleaved row slices, so a facade's thousands of rows do not hang on one warp.
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  const int lane = threadIdx.x & 31;
-  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
-  if (seg >= g.n_seg) return;
+  __shared__ int hv_beg[kSegWarps], hv_len[kSegWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + warp;
+  const bool valid = seg < g.n_seg;
   const int sub = lane / LPR, l = lane % LPR;
-  const int beg = g.cell_start[seg << g.shift], end = g.cell_start[(seg + 1) << g.shift];
-  if (beg >= end) return;
-  const float inv = mean ? __fdiv_rn(1.0f, (float)(end - beg)) : 1.0f;
-  const int64_t prow = plane_row(g, seg);
-  float4 v[CH];
+  int beg = 0, end = 0;
+  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
+  const bool heavy = valid && end - beg > kHeavyMax;
+  if (lane == 0) { hv_len[warp] = heavy ? end - beg : 0; hv_beg[warp] = beg; }
+
+  auto write_rows = [&](int64_t sg, int n_rows, int first, int last, int step) {
+    const float inv = mean ? __fdiv_rn(1.0f, (float)n_rows) : 1.0f;
+    const int64_t prow = plane_row(g, sg);
+    float4 v[CH];
 #pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    v[c] = ld4(plane + prow * C + (c * LPR + l) * 4);
-    v[c].x *= inv; v[c].y *= inv; v[c].z *= inv; v[c].w *= inv;
-  }
-  for (int i = beg + sub; i < end; i += RPI) {
-    const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+    for (int c = 0; c < CH; ++c) {
+      v[c] = ld4(plane + prow * C + (c * LPR + l) * 4);
+      v[c].x *= inv; v[c].y *= inv; v[c].z *= inv; v[c].w *= inv;
+    }
+    for (int i = first; i < last; i += step) {
+      const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) st4(rows + row * C + (c * LPR + l) * 4, v[c]);
+      for (int c = 0; c < CH; ++c) st4(rows + row * C + (c * LPR + l) * 4, v[c]);
+    }
+  };
+  if (valid && !heavy && beg < end && blockIdx.y == 0) write_rows(seg, end - beg, beg + sub, end, RPI);
+  __syncthreads();
+  const int slot = (int)blockIdx.y * kSegWarps + warp, n_slots = (int)gridDim.y * kSegWarps;
+  for (int w = 0; w < kSegWarps; ++w) {
+    const int hl = hv_len[w];
+    if (hl == 0) continue;
+    const int hb = hv_beg[w];
+    write_rows((int64_t)blockIdx.x * kSegWarps + w, hl, hb + slot * RPI + sub, hb + hl, n_slots * RPI);
   }
 }
 
@@ -524,7 +542,9 @@ extern "C" int t2h_seg_broadcast(const float* plane, const int32_t* perm, const 
   if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
   SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso, log2_cells_of(reso)};
-  T2H_DISPATCH_ROWSHAPE(C, seg_broadcast_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
+  // coarse levels (few cells, many rows each): four CTAs share every group of cells for its heavy ones
+  const dim3 grid(seg_blocks(n_seg), n_seg < 16384 ? 4 : 1);
+  T2H_DISPATCH_ROWSHAPE(C, seg_broadcast_kernel<RS><<<grid, kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
                                plane, g, mean, rows));
   T2H_CHECK_LAUNCH();
   return T2H_OK;
