@@ -5,14 +5,19 @@
 //
 //   y[r, n] = sum_k act(x[r, k]) * w[n, k] + bias[n]      (* mask[r, n] > 0)  (+ residual[r, n])
 //
-// fp32 in / fp32 out with fp32-grade accuracy: every operand is split into two TF32 terms
-// (hi + lo) and three tcgen05.mma.kind::tf32 products are accumulated in TMEM in fp32
-// (hi*hi + lo*hi + hi*lo, "3xTF32").  One CTA computes a 128-row x BLOCK_N tile:
-//   warp 0     TMA producer: x chunk (128 x 32 fp32, SWIZZLE_128B) + pre-split weight chunks
-//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5  in-place operand transform (optional ReLU, hi/lo split) and, after the K loop,
-//              the epilogue (tcgen05.ld -> bias / mask / residual -> global)
-// connected by mbarrier pipelines (TMA -> transform -> MMA -> slot free; MMA -> epilogue).
+// fp32 in / fp32 out with fp32-grade accuracy on the tensor cores: every operand is split into hi + lo and
+// three tcgen05.mma products (lo*hi + hi*lo + hi*hi) are accumulated in fp32 in tensor memory -- as TF32
+// terms ("3xTF32", kind::tf32) or, for the wide layers, as fp16 terms of power-of-two scaled operands
+// ("3xFP16", kind::f16, twice the rate; see f16_scale_exp).  Kernels in this file:
+//   linear_x3_persistent_kernel   forward / input-gradient GEMM and 3x3 convolution (implicit GEMM), the
+//                                 product path: one persistent CTA per SM, TMA producer warp, MMA warp,
+//                                 operand-split warps (x -> TMEM), two epilogue groups, double-buffered
+//                                 TMEM accumulators
+//   linear_tf32x3_kernel          the earlier one-tile-per-CTA kernel, kept as the ablation baseline
+//                                 (T2H_LINEAR_NONPERSISTENT=1)
+//   wgrad_x3_kernel, wgrad_reduce_kernel   weight / bias gradient (MN-major operands, row split + fixed-order sum)
+//   absmax_kernel, add_absmax_kernel, split_*_kernel, colsum kernels   operand maxima, weight splits, bias gradient
+// The stages of every GEMM are connected by mbarrier pipelines (TMA -> split -> MMA -> slot free; MMA -> epilogue).
 #include "t2h_common.cuh"
 #include "t2h_tc.cuh"
 #include <cstdlib>

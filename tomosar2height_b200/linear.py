@@ -1,4 +1,5 @@
-"""nn.Linear on the point path as tcgen05 3xTF32 GEMMs (t2h_linear_fwd / t2h_linear_wgrad / t2h_colsum).
+"""nn.Linear on the point path as tcgen05 split-precision GEMMs (t2h_linear_fwd[_f16] / t2h_linear_wgrad[_f16] /
+t2h_colsum): 3xTF32 for narrow layers, 3xFP16 with power-of-two operand scaling for K >= 128.
 
 ``linear(x, weight, bias, x2=None, relu_in=False, residual=None)`` computes
 
@@ -7,8 +8,10 @@
 with fp32 inputs / outputs and fp32-grade accuracy, and is differentiable: the backward runs the
 input-gradient GEMM through the same forward kernel (weight transposed, ReLU mask and gradient
 accumulation fused in the epilogue) and the weight gradient through the MN-major kernel.  Weights stay
-ordinary fp32 ``nn.Parameter``s; their TF32 hi/lo splits (and transposes) are derived caches keyed on
-the parameter's version counter.
+ordinary fp32 ``nn.Parameter``s; their hi/lo splits (and transposes) are derived caches keyed on
+the parameter's version counter.  The fp16 flavour needs the maximum magnitude of every operand: the
+GEMM epilogues publish it for their outputs, ``_AbsmaxRegistry`` hands it to the consumer, and only tensors
+that come from elsewhere take a streaming ``t2h_absmax`` pass.
 """
 import os
 import weakref
