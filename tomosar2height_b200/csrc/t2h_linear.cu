@@ -315,16 +315,24 @@ constexpr int P_THREADS = 448;  // producer, MMA, 4 transform warps, 2 x 4 epilo
 //   64 columns (32 hi + 32 lo).
 // BLOCK_N = 128 / 64 / 32 output columns per tile; narrower tiles have smaller weight stages and run a deeper ring
 // (the narrow layers are HBM-bound: bytes in flight per SM matter, not MMA issue).
-template <bool F16, int BLOCK_N>
+// WSTEPS > 0 (fp16, 128-wide tiles, K <= 64 * WSTEPS): WEIGHT-RESIDENT variant.  With a grid that is a multiple
+// of the number of N-tiles the raster `tile += gridDim.x` keeps every CTA on ONE N-tile, so its weight tile
+// (K x 128 fp16 hi + lo, <= 128 KB) is loaded once and stays in shared memory; the stage ring then carries the
+// x chunks only, which halves the L2 -> SM tile traffic that bounds these layers.
+template <bool F16, int BLOCK_N, int WSTEPS = 0>
 struct PSmem {
-  static constexpr int STAGES = F16 ? (BLOCK_N == 128 ? 3 : 4) : (BLOCK_N == 128 ? 4 : 6);
+  static constexpr bool WRES = WSTEPS > 0;
+  static constexpr int STAGES = WRES ? (WSTEPS <= 2 ? 4 : 2) : (F16 ? (BLOCK_N == 128 ? 3 : 4) : (BLOCK_N == 128 ? 4 : 6));
   static constexpr int X_BYTES = (F16 ? 2 : 1) * A_BYTES;
   static constexpr int W_BYTES = F16 ? BLOCK_N * 64 * 2 : BLOCK_N * BLOCK_K * 4;
-  static constexpr int STAGE_BYTES = X_BYTES + 2 * W_BYTES;        // x raw | w hi | w lo
+  static constexpr int STAGE_BYTES = WRES ? X_BYTES : X_BYTES + 2 * W_BYTES;   // x raw (| w hi | w lo)
+  static constexpr int WREGION_BYTES = WSTEPS * 2 * W_BYTES;       // resident weight: per k-step (w hi | w lo)
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + WREGION_BYTES;
   static constexpr int STAGING_BYTES = 2 * A_BYTES;                // epilogue staging: two 32-column blocks at a time
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
+  static constexpr int TOTAL = STAGING_OFF + STAGING_BYTES + 256 + 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int A_COL0 = 2 * BLOCK_N;
+  static_assert(!WRES || (F16 && BLOCK_N == 128), "weight-resident: fp16, 128-wide tiles");
   static_assert(A_COL0 + STAGES * 64 <= 512, "tensor memory: two accumulators + the split x stages");
   static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
@@ -339,21 +347,23 @@ __device__ __forceinline__ int f16_scale_exp(uint32_t absmax_bits) {
 }
 __device__ __forceinline__ float pow2f(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
 
-template <bool F16, int BLOCK_N>
+template <bool F16, int BLOCK_N, int WSTEPS>
 __global__ void __launch_bounds__(P_THREADS, 1)
 linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                                 const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
                                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_aux,
                                 const LinearArgs p, const int64_t n_tiles_total) {
-  using S = PSmem<F16, BLOCK_N>;
+  using S = PSmem<F16, BLOCK_N, WSTEPS>;
   constexpr int STAGES = S::STAGES;
+  constexpr bool WRES = S::WRES;
   // pipeline steps per tile: 32-wide chunks (tf32) or pairs of them (fp16)
   const int n_steps = F16 ? (p.k_chunks + 1) / 2 : p.k_chunks;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t staging = base + STAGES * S::STAGE_BYTES;
-  uint8_t* staging_ptr = base_ptr + STAGES * S::STAGE_BYTES;
+  const uint32_t wregion = base + STAGES * S::STAGE_BYTES;  // (weight-resident variant)
+  const uint32_t staging = base + S::STAGING_OFF;
+  uint8_t* staging_ptr = base_ptr + S::STAGING_OFF;
   const uint32_t bars = staging + S::STAGING_BYTES;
   auto full_tma = [&](int s) { return bars + 8u * s; };
   auto full_ab = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -361,6 +371,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
   auto acc_full = [&](int a) { return bars + 8u * (3 * STAGES + a); };
   auto acc_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
   auto aux_bar = [&](int g) { return bars + 8u * (3 * STAGES + 4 + g); };
+  const uint32_t w_full = bars + 8u * (3 * STAGES + 7);
   const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 6);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(staging_ptr + S::STAGING_BYTES + 8 * (3 * STAGES + 6));
   // epilogue threads that hand an accumulator back per tile: both groups, or (32-wide tiles) the one that owns the tile
@@ -380,6 +391,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
       mbar_init(acc_empty(a), EPI_ARRIVALS);
       mbar_init(aux_bar(a), 1);
     }
+    mbar_init(w_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_x1);
     tma_prefetch_desc(&tm_whi);
@@ -408,6 +420,18 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
 
   if (warp == 0) {
     {  // TMA producer: the warp runs the loop, one elected lane issues (see tc::elect_one)
+      if (WRES && (int64_t)blockIdx.x < n_tiles_total) {
+        // the CTA's one weight tile: every k-step's (hi | lo) pair, once
+        if (elect_one()) {
+          const int n0w = (int)(blockIdx.x % n_tiles) * BLOCK_N;
+          mbar_arrive_expect_tx(w_full, (uint32_t)n_steps * 2 * S::W_BYTES);
+          for (int kc = 0; kc < n_steps; ++kc) {
+            tma_load_2d(wregion + kc * 2 * S::W_BYTES, &tm_whi, w_full, kc * 64, n0w);
+            tma_load_2d(wregion + kc * 2 * S::W_BYTES + S::W_BYTES, &tm_wlo, w_full, kc * 64, n0w);
+          }
+        }
+        __syncwarp();
+      }
       int64_t it = 0;  // running chunk counter across tiles
       for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         int m0, n0, img, px0, py0;
@@ -418,7 +442,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           mbar_wait(empty(s), ph ^ 1);
           if (elect_one()) {
           const uint32_t stage = base + s * S::STAGE_BYTES;
-          mbar_arrive_expect_tx(full_tma(s), S::X_BYTES + 2 * S::W_BYTES);
+          mbar_arrive_expect_tx(full_tma(s), S::X_BYTES + (WRES ? 0 : 2 * S::W_BYTES));
           auto load_x = [&](uint32_t dst, int c) {  // 32-wide chunk c of the (concatenated / im2col) K axis
             if (p.conv) {
               const int tap = c / p.cin_chunks, cc = c - tap * p.cin_chunks;
@@ -430,8 +454,10 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           if (F16) {
             load_x(stage, 2 * kc);
             load_x(stage + A_BYTES, 2 * kc + 1);
-            tma_load_2d(stage + S::X_BYTES, &tm_whi, full_tma(s), kc * 64, n0);
-            tma_load_2d(stage + S::X_BYTES + S::W_BYTES, &tm_wlo, full_tma(s), kc * 64, n0);
+            if (!WRES) {
+              tma_load_2d(stage + S::X_BYTES, &tm_whi, full_tma(s), kc * 64, n0);
+              tma_load_2d(stage + S::X_BYTES + S::W_BYTES, &tm_wlo, full_tma(s), kc * 64, n0);
+            }
           } else {
             load_x(stage, kc);
             tma_load_2d(stage + S::X_BYTES, &tm_whi, full_tma(s), kc * BLOCK_K, n0);
@@ -446,6 +472,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
     // the whole warp runs the loop (waits included); one elected lane issues the MMAs and their commits
     constexpr uint32_t idesc = F16 ? make_idesc_f16(BLOCK_M, BLOCK_N, 0, 0) : make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
     const uint32_t a_base = tmem_base + S::A_COL0;
+    if (WRES && (int64_t)blockIdx.x < n_tiles_total) mbar_wait(w_full, 0);
     int64_t it = 0, local = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
       const int acc = (int)(local & 1);
@@ -462,8 +489,9 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
         if (elect_one()) {
           // every k-step advances 32 bytes along the swizzled 128-byte weight row (8 tf32 or 16 fp16) and
           // 8 TMEM columns of the split x operand; small terms first
-          const uint64_t b_hi0 = make_smem_desc(base + s * S::STAGE_BYTES + S::X_BYTES, 16, 1024);
-          const uint64_t b_lo0 = make_smem_desc(base + s * S::STAGE_BYTES + S::X_BYTES + S::W_BYTES, 16, 1024);
+          const uint32_t w_tile = WRES ? wregion + kc * 2 * S::W_BYTES : base + s * S::STAGE_BYTES + S::X_BYTES;
+          const uint64_t b_hi0 = make_smem_desc(w_tile, 16, 1024);
+          const uint64_t b_lo0 = make_smem_desc(w_tile + S::W_BYTES, 16, 1024);
           const uint32_t a_hi0 = a_base + s * 64;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -1195,22 +1223,26 @@ static bool make_map_4d(CUtensorMap* map, const float* ptr, uint64_t C, uint64_t
 
 struct PlaneGeom { int B, H, W; };  // conv mode only
 
-template <bool F16, int BLOCK_N>
+template <bool F16, int BLOCK_N, int WSTEPS = 0>
 static int launch_linear_persistent(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& whi, const CUtensorMap& wlo,
                                     const CUtensorMap& mout, const CUtensorMap& maux, const LinearArgs& args,
                                     cudaStream_t stream) {
-  auto kern = linear_x3_persistent_kernel<F16, BLOCK_N>;
+  auto kern = linear_x3_persistent_kernel<F16, BLOCK_N, WSTEPS>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem<F16, BLOCK_N>::TOTAL) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem<F16, BLOCK_N, WSTEPS>::TOTAL) != cudaSuccess) {
       (void)cudaGetLastError();
       return T2H_ERR_CUDA;
     }
     configured = true;
   }
   const int64_t tiles = ((args.rows + BLOCK_M - 1) / BLOCK_M) * ((args.n_out + BLOCK_N - 1) / BLOCK_N);
-  const unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
-  kern<<<grid, P_THREADS, PSmem<F16, BLOCK_N>::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args, tiles);
+  unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
+  if (WSTEPS > 0) {  // a multiple of the N-tile count: `tile += gridDim.x` then keeps each CTA on one N-tile
+    const unsigned n_tiles = (unsigned)((args.n_out + BLOCK_N - 1) / BLOCK_N);
+    grid = (grid / n_tiles) * n_tiles;
+  }
+  kern<<<grid, P_THREADS, PSmem<F16, BLOCK_N, WSTEPS>::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args, tiles);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
@@ -1399,6 +1431,16 @@ extern "C" int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const 
   if (a.aux_kind == 2 && !make_map(&maux, residual, n_out, rows, ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
   if (bn == 32) return launch_linear_persistent<true, 32>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
   if (bn == 64) return launch_linear_persistent<true, 64>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
+  // K <= 256: the weight tile of a CTA's N-tile can stay resident in shared memory (T2H_LINEAR_WRES=1).  OFF by
+  // default -- measured: it halves the L2 -> SM tile traffic but leaves only 2 x-stages (64 KB in flight) for
+  // K = 256, and the layer gets SLOWER (256 -> 512: 0.53 vs 0.44 ms), i.e. these layers are bound by the depth
+  // of the load pipeline, not by the fabric; K = 128 (4 stages) is a wash (0.154 vs 0.157 ms).
+  static const int wres = []() { const char* e = getenv("T2H_LINEAR_WRES"); return e ? atoi(e) : 0; }();
+  const int n_steps = (a.k_chunks + 1) / 2, n_tiles128 = (n_out + 127) / 128;
+  if (wres && n_tiles128 <= kSMs) {
+    if (n_steps <= 2) return launch_linear_persistent<true, 128, 2>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
+    if (n_steps <= 4) return launch_linear_persistent<true, 128, 4>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
+  }
   return launch_linear_persistent<true, 128>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
 }
 
