@@ -319,12 +319,17 @@ constexpr int P_THREADS = 448;  // producer, MMA, 4 transform warps, 2 x 4 epilo
 // of the number of N-tiles the raster `tile += gridDim.x` keeps every CTA on ONE N-tile, so its weight tile
 // (K x 128 fp16 hi + lo, <= 128 KB) is loaded once and stays in shared memory; the stage ring then carries the
 // x chunks only, which halves the L2 -> SM tile traffic that bounds these layers.
-template <bool F16, int BLOCK_N, int WSTEPS = 0>
+// PAIR (fp16, 128-wide tiles): two CTAs of a cluster (the two SMs of a TPC) compute a 256 x 128 tile with
+// tcgen05.mma.cta_group::2 -- each CTA transforms its own 128 rows of x into its own tensor memory, stages only
+// HALF of the weight tile (64 of the 128 output columns; the MMA reads both halves) and drains its own
+// accumulator.  48 KB instead of 64 KB per step and SM, so four stages fit: fewer bytes per MMA cycle and a
+// deeper load pipeline, which is what bounds the single-CTA kernel.
+template <bool F16, int BLOCK_N, int WSTEPS = 0, bool PAIR = false>
 struct PSmem {
   static constexpr bool WRES = WSTEPS > 0;
-  static constexpr int STAGES = WRES ? (WSTEPS <= 2 ? 4 : 2) : (F16 ? (BLOCK_N == 128 ? 3 : 4) : (BLOCK_N == 128 ? 4 : 6));
+  static constexpr int STAGES = PAIR ? 4 : (WRES ? (WSTEPS <= 2 ? 4 : 2) : (F16 ? (BLOCK_N == 128 ? 3 : 4) : (BLOCK_N == 128 ? 4 : 6)));
   static constexpr int X_BYTES = (F16 ? 2 : 1) * A_BYTES;
-  static constexpr int W_BYTES = F16 ? BLOCK_N * 64 * 2 : BLOCK_N * BLOCK_K * 4;
+  static constexpr int W_BYTES = (F16 ? BLOCK_N * 64 * 2 : BLOCK_N * BLOCK_K * 4) / (PAIR ? 2 : 1);
   static constexpr int STAGE_BYTES = WRES ? X_BYTES : X_BYTES + 2 * W_BYTES;   // x raw (| w hi | w lo)
   static constexpr int WREGION_BYTES = WSTEPS * 2 * W_BYTES;       // resident weight: per k-step (w hi | w lo)
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + WREGION_BYTES;
@@ -333,6 +338,7 @@ struct PSmem {
   static constexpr int TMEM_COLS = 512;
   static constexpr int A_COL0 = 2 * BLOCK_N;
   static_assert(!WRES || (F16 && BLOCK_N == 128), "weight-resident: fp16, 128-wide tiles");
+  static_assert(!PAIR || (F16 && BLOCK_N == 128 && !WRES), "CTA pairs: fp16, 128-wide tiles");
   static_assert(A_COL0 + STAGES * 64 <= 512, "tensor memory: two accumulators + the split x stages");
   static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
@@ -347,13 +353,17 @@ __device__ __forceinline__ int f16_scale_exp(uint32_t absmax_bits) {
 }
 __device__ __forceinline__ float pow2f(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
 
-template <bool F16, int BLOCK_N, int WSTEPS>
+template <bool F16, int BLOCK_N, int WSTEPS, bool PAIR>
 __global__ void __launch_bounds__(P_THREADS, 1)
 linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                                 const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
                                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_aux,
                                 const LinearArgs p, const int64_t n_tiles_total) {
-  using S = PSmem<F16, BLOCK_N, WSTEPS>;
+  using S = PSmem<F16, BLOCK_N, WSTEPS, PAIR>;
+  // PAIR: rank of this CTA in its pair; the pair (not the CTA) walks the list of 256-row tiles
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+  const int64_t vblock = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t vgrid = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
   constexpr int STAGES = S::STAGES;
   constexpr bool WRES = S::WRES;
   // pipeline steps per tile: 32-wide chunks (tf32) or pairs of them (fp16)
@@ -372,10 +382,11 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
   auto acc_empty = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
   auto aux_bar = [&](int g) { return bars + 8u * (3 * STAGES + 4 + g); };
   const uint32_t w_full = bars + 8u * (3 * STAGES + 7);
+  auto w_pair = [&](int s) { return bars + 8u * (3 * STAGES + 8 + s); };  // PAIR: both weight halves landed (leader's)
   const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 6);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(staging_ptr + S::STAGING_BYTES + 8 * (3 * STAGES + 6));
   // epilogue threads that hand an accumulator back per tile: both groups, or (32-wide tiles) the one that owns the tile
-  constexpr uint32_t EPI_ARRIVALS = BLOCK_N == 32 ? 128 : 256;
+  constexpr uint32_t EPI_ARRIVALS = BLOCK_N == 32 ? 4 : 8;  // one arrival per epilogue warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.n_out + BLOCK_N - 1) / BLOCK_N;
@@ -383,12 +394,13 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_tma(s), 1);
-      mbar_init(full_ab(s), 128);
+      mbar_init(full_ab(s), PAIR ? 8 : 4);      // one arrival per transform warp (PAIR: of both CTAs, on the leader's)
       mbar_init(empty(s), 1);
+      if (PAIR) mbar_init(w_pair(s), 2);        // the two producers (the leader's arrival carries the byte count)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full(a), 1);
-      mbar_init(acc_empty(a), EPI_ARRIVALS);
+      mbar_init(acc_empty(a), PAIR ? 2 * EPI_ARRIVALS : EPI_ARRIVALS);  // PAIR: both CTAs' epilogues, on the leader's
       mbar_init(aux_bar(a), 1);
     }
     mbar_init(w_full, 1);
@@ -398,15 +410,19 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
     tma_prefetch_desc(&tm_wlo);
     tma_prefetch_desc(&tm_out);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, S::TMEM_COLS);
+    else tmem_alloc(tmem_slot, S::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // tile -> coordinates
   auto decode = [&](int64_t tile, int& m0, int& n0, int& img, int& px0, int& py0) {
-    const int m_idx = (int)(tile / n_tiles);
+    const int m_idx = PAIR ? 2 * (int)(tile / n_tiles) + (int)rank : (int)(tile / n_tiles);
     m0 = m_idx * BLOCK_M;
     n0 = (int)(tile % n_tiles) * BLOCK_N;
     img = px0 = py0 = 0;
@@ -433,7 +449,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
         __syncwarp();
       }
       int64_t it = 0;  // running chunk counter across tiles
-      for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      for (int64_t tile = vblock; tile < n_tiles_total; tile += vgrid) {
         int m0, n0, img, px0, py0;
         decode(tile, m0, n0, img, px0, py0);
         for (int kc = 0; kc < n_steps; ++kc, ++it) {
@@ -442,7 +458,14 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           mbar_wait(empty(s), ph ^ 1);
           if (elect_one()) {
           const uint32_t stage = base + s * S::STAGE_BYTES;
-          mbar_arrive_expect_tx(full_tma(s), S::X_BYTES + (WRES ? 0 : 2 * S::W_BYTES));
+          mbar_arrive_expect_tx(full_tma(s), S::X_BYTES + ((WRES || PAIR) ? 0 : 2 * S::W_BYTES));
+          if (PAIR) {
+            // this CTA's 64 weight rows (hi | lo) of the step; the bytes of both CTAs are counted on the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(w_pair(s), 4 * S::W_BYTES);
+            else mbar_arrive_remote(w_pair(s), 0);
+            tma_load_2d_pair(stage + S::X_BYTES, &tm_whi, w_pair(s), kc * 64, n0 + (int)rank * (BLOCK_N / 2));
+            tma_load_2d_pair(stage + S::X_BYTES + S::W_BYTES, &tm_wlo, w_pair(s), kc * 64, n0 + (int)rank * (BLOCK_N / 2));
+          }
           auto load_x = [&](uint32_t dst, int c) {  // 32-wide chunk c of the (concatenated / im2col) K axis
             if (p.conv) {
               const int tap = c / p.cin_chunks, cc = c - tap * p.cin_chunks;
@@ -454,7 +477,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           if (F16) {
             load_x(stage, 2 * kc);
             load_x(stage + A_BYTES, 2 * kc + 1);
-            if (!WRES) {
+            if (!WRES && !PAIR) {
               tma_load_2d(stage + S::X_BYTES, &tm_whi, full_tma(s), kc * 64, n0);
               tma_load_2d(stage + S::X_BYTES + S::W_BYTES, &tm_wlo, full_tma(s), kc * 64, n0);
             }
@@ -470,21 +493,29 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
     }
   } else if (warp == 1) {
     // the whole warp runs the loop (waits included); one elected lane issues the MMAs and their commits
-    constexpr uint32_t idesc = F16 ? make_idesc_f16(BLOCK_M, BLOCK_N, 0, 0) : make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
+    // (PAIR: only the leader CTA issues; its MMAs drive the tensor cores of both SMs)
+    constexpr uint32_t idesc = F16 ? make_idesc_f16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N, 0, 0) : make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
+    if (!PAIR || rank == 0) {
     const uint32_t a_base = tmem_base + S::A_COL0;
     if (WRES && (int64_t)blockIdx.x < n_tiles_total) mbar_wait(w_full, 0);
     int64_t it = 0, local = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
+    for (int64_t tile = vblock; tile < n_tiles_total; tile += vgrid, ++local) {
       const int acc = (int)(local & 1);
       const uint32_t acc_ph = (uint32_t)((local >> 1) & 1);
-      mbar_wait(acc_empty(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator
+      if (PAIR) mbar_wait_cluster(acc_empty(acc), acc_ph ^ 1);
+      else mbar_wait(acc_empty(acc), acc_ph ^ 1);  // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
       for (int kc = 0; kc < n_steps; ++kc, ++it) {
         const int s = (int)(it % STAGES);
         const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-        mbar_wait(full_tma(s), ph);
-        mbar_wait(full_ab(s), ph);
+        if (PAIR) {
+          mbar_wait_cluster(w_pair(s), ph);
+          mbar_wait_cluster(full_ab(s), ph);
+        } else {
+          mbar_wait(full_tma(s), ph);
+          mbar_wait(full_ab(s), ph);
+        }
         tc_fence_after();
         if (elect_one()) {
           // every k-step advances 32 bytes along the swizzled 128-byte weight row (8 tf32 or 16 fp16) and
@@ -497,7 +528,11 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           for (int k = 0; k < 4; ++k) {
             const uint64_t b_hi = b_hi0 + (uint64_t)(k * 2), b_lo = b_lo0 + (uint64_t)(k * 2);  // +32 bytes (>> 4)
             const uint32_t a_hi = a_hi0 + k * 8, a_lo = a_hi + 32;
-            if (F16) {
+            if (PAIR) {
+              mma_f16_ts_pair(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
+              mma_f16_ts_pair(tmem_d, a_hi, b_lo, idesc, 1);
+              mma_f16_ts_pair(tmem_d, a_hi, b_hi, idesc, 1);
+            } else if (F16) {
               mma_f16_ts(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
               mma_f16_ts(tmem_d, a_hi, b_lo, idesc, 1);
               mma_f16_ts(tmem_d, a_hi, b_hi, idesc, 1);
@@ -507,19 +542,24 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
               mma_tf32_ts(tmem_d, a_hi, b_hi, idesc, 1);
             }
           }
-          mma_commit(empty(s));
+          if (PAIR) mma_commit_pair(empty(s));
+          else mma_commit(empty(s));
         }
         __syncwarp();
       }
-      if (elect_one()) mma_commit(acc_full(acc));
+      if (elect_one()) {
+        if (PAIR) mma_commit_pair(acc_full(acc));
+        else mma_commit(acc_full(acc));
+      }
       __syncwarp();
+    }
     }
   } else if (warp < 6) {
     // ---- operand transform: row t of every x chunk -> (hi | lo) in TMEM ---------------------------------
     const int t = (warp & 3) * 32 + lane;
     const float sx = F16 ? pow2f(f16_scale_exp(*p.x_absmax)) : 1.f;
     int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+    for (int64_t tile = vblock; tile < n_tiles_total; tile += vgrid) {
       for (int kc = 0; kc < n_steps; ++kc, ++it) {
         const int s = (int)(it % STAGES);
         const uint32_t ph = (uint32_t)((it / STAGES) & 1);
@@ -556,7 +596,11 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(full_ab(s));
+        __syncwarp();
+        if (lane == 0) {  // one (possibly remote) arrival per warp
+          if (PAIR && rank != 0) mbar_arrive_remote(full_ab(s), 0);
+          else mbar_arrive(full_ab(s));
+        }
       }
     }
   } else {
@@ -577,7 +621,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
     uint32_t aux_phase = 0;
     float out_max = 0.f;
     int64_t local = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++local) {
+    for (int64_t tile = vblock; tile < n_tiles_total; tile += vgrid, ++local) {
       if (BLOCK_N == 32 && (int)(local & 1) != eh) continue;
       int m0, n0, img, px0, py0;
       decode(tile, m0, n0, img, px0, py0);
@@ -620,7 +664,11 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
         if (cb + 2 >= n_blocks) {
           // the group's last read of this accumulator (tcgen05.ld has been waited for)
           tc_fence_before();
-          mbar_arrive(acc_empty(acc));
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_remote(acc_empty(acc), 0);
+            else mbar_arrive(acc_empty(acc));
+          }
         }
         if (F16) {
 #pragma unroll
@@ -680,7 +728,11 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
       if (BLOCK_N != 32 && !have_acc) {
         // a group without a block in this (narrow last) tile still takes part in the accumulator hand-over, in step
         mbar_wait(acc_full(acc), acc_ph);
-        mbar_arrive(acc_empty(acc));
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR && rank != 0) mbar_arrive_remote(acc_empty(acc), 0);
+          else mbar_arrive(acc_empty(acc));
+        }
       }
     }
     if (leader) tma_store_wait_all();  // global writes of the last stores complete before the CTA exits
@@ -692,8 +744,12 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
+  if (PAIR) cluster_sync_all();  // nobody's barriers, shared or tensor memory are touched by the peer any more
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, S::TMEM_COLS);
+    else tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
 }
 
 // ---- weight gradient: dW[n, k] = sum_r g[r, n] * act(x[r, k]),  db[n] = sum_r g[r, n] ---------------
@@ -1223,14 +1279,15 @@ static bool make_map_4d(CUtensorMap* map, const float* ptr, uint64_t C, uint64_t
 
 struct PlaneGeom { int B, H, W; };  // conv mode only
 
-template <bool F16, int BLOCK_N, int WSTEPS = 0>
+template <bool F16, int BLOCK_N, int WSTEPS = 0, bool PAIR = false>
 static int launch_linear_persistent(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& whi, const CUtensorMap& wlo,
                                     const CUtensorMap& mout, const CUtensorMap& maux, const LinearArgs& args,
                                     cudaStream_t stream) {
-  auto kern = linear_x3_persistent_kernel<F16, BLOCK_N, WSTEPS>;
+  auto kern = linear_x3_persistent_kernel<F16, BLOCK_N, WSTEPS, PAIR>;
+  using S = PSmem<F16, BLOCK_N, WSTEPS, PAIR>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem<F16, BLOCK_N, WSTEPS>::TOTAL) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
       (void)cudaGetLastError();
       return T2H_ERR_CUDA;
     }
@@ -1242,7 +1299,28 @@ static int launch_linear_persistent(const CUtensorMap& x1, const CUtensorMap& x2
     const unsigned n_tiles = (unsigned)((args.n_out + BLOCK_N - 1) / BLOCK_N);
     grid = (grid / n_tiles) * n_tiles;
   }
-  kern<<<grid, P_THREADS, PSmem<F16, BLOCK_N, WSTEPS>::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args, tiles);
+  if (PAIR) {
+    // pairs of CTAs (cluster of 2 = the two SMs of a TPC) walk the list of 256-row tiles
+    const int64_t m_tiles = (args.rows + BLOCK_M - 1) / BLOCK_M, n_tiles = (args.n_out + BLOCK_N - 1) / BLOCK_N;
+    const int64_t pair_tiles = ((m_tiles + 1) / 2) * n_tiles;
+    const unsigned pairs = (unsigned)(pair_tiles < kSMs / 2 ? pair_tiles : kSMs / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(P_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, x1, x2, whi, wlo, mout, maux, args, pair_tiles) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return T2H_ERR_CUDA;
+    }
+    return T2H_OK;
+  }
+  kern<<<grid, P_THREADS, S::TOTAL, stream>>>(x1, x2, whi, wlo, mout, maux, args, tiles);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
@@ -1431,6 +1509,14 @@ extern "C" int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const 
   if (a.aux_kind == 2 && !make_map(&maux, residual, n_out, rows, ld_res, 32, BLOCK_M)) return T2H_ERR_CUDA;
   if (bn == 32) return launch_linear_persistent<true, 32>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
   if (bn == 64) return launch_linear_persistent<true, 64>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
+  // CTA pairs (cta_group::2) for 128-wide tiles; T2H_LINEAR_PAIR=0 falls back to one CTA per tile (ablation).
+  // The weight maps then have 64-row boxes (each CTA of a pair stages half of the weight tile).
+  static const int pair = []() { const char* e = getenv("T2H_LINEAR_PAIR"); return e ? atoi(e) : 1; }();
+  if (pair && rows >= 2 * BLOCK_M) {
+    CUtensorMap whi2, wlo2;
+    if (!make_map_f16(&whi2, w_hi, k_total, n_out, 64) || !make_map_f16(&wlo2, w_lo, k_total, n_out, 64)) return T2H_ERR_CUDA;
+    return launch_linear_persistent<true, 128, 0, true>(m1, m2, whi2, wlo2, mout, maux, a, (cudaStream_t)stream);
+  }
   // K <= 256: the weight tile of a CTA's N-tile can stay resident in shared memory (T2H_LINEAR_WRES=1).  OFF by
   // default -- measured: it halves the L2 -> SM tile traffic but leaves only 2 x-stages (64 KB in flight) for
   // K = 256, and the layer gets SLOWER (256 -> 512: 0.53 vs 0.44 ms), i.e. these layers are bound by the depth
@@ -1510,6 +1596,12 @@ extern "C" int t2h_conv3x3_fwd_f16(const float* x, int B, int H, int W, int cin,
   }
   if (bn == 32) return launch_linear_persistent<true, 32>(mx, mx, whi, wlo, mout, maux, a, s);
   if (bn == 64) return launch_linear_persistent<true, 64>(mx, mx, whi, wlo, mout, maux, a, s);
+  static const int pair = []() { const char* e = getenv("T2H_LINEAR_PAIR"); return e ? atoi(e) : 1; }();
+  if (pair && a.rows >= 2 * BLOCK_M) {
+    CUtensorMap whi2, wlo2;
+    if (!make_map_f16(&whi2, w_hi, k_total, cout, 64) || !make_map_f16(&wlo2, w_lo, k_total, cout, 64)) return T2H_ERR_CUDA;
+    return launch_linear_persistent<true, 128, 0, true>(mx, mx, whi2, wlo2, mout, maux, a, s);
+  }
   return launch_linear_persistent<true, 128>(mx, mx, whi, wlo, mout, maux, a, s);
 }
 
