@@ -124,3 +124,31 @@ def test_install_as_reference_alias():
         for k in [k for k in sys.modules if k == "tomosar2height" or k.startswith("tomosar2height.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_absmax_registry_never_returns_a_stale_entry():
+    """host logic of linear._AbsmaxRegistry (CPU tensors stand in; the slot is an opaque object): an entry is valid
+    only for the live, unmodified tensor it was registered for, and for views of it."""
+    import gc
+    import torch
+    from tomosar2height_b200.linear import _AbsmaxRegistry
+    reg = _AbsmaxRegistry()
+    t = torch.randn(64, 8)
+    slot = object()
+    reg.put(t, slot)
+    assert reg.get(t) is slot
+    assert reg.get(t.view(32, 16)) is slot            # same storage, same version: the maximum is shape-independent
+    assert reg.get(t[:32]) is None                    # different extent
+    assert reg.get(t.t()) is None                     # not contiguous
+    t.add_(1.0)                                       # modified in place: version counter moved on
+    assert reg.get(t) is None
+    reg.put(t, slot)
+    assert reg.get(t) is slot
+    ptr, n = t.data_ptr(), t.numel()
+    del t
+    gc.collect()
+    assert (ptr, n) not in reg._entries               # entry dropped with its owner: a recycled address cannot hit
+    a = torch.randn(16, 4)
+    b = a.clone()
+    reg.put(a, slot)
+    assert reg.get(b) is None                         # equal contents, different storage
