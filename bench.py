@@ -113,7 +113,7 @@ def cpu_reference_step(cfg, params, cloud, dsm):
     pa, pb = oracle.oracle_forward(P, cfg, cloud)
     loss = oracle.oracle_loss(pa, pb, dsm, False)
     loss.backward()
-    return time.perf_counter() - t0, float(loss.detach())
+    return time.perf_counter() - t0, float(loss.detach()), pa.detach()
 
 
 def run_reference(args):
@@ -315,9 +315,18 @@ def run_b200(args):
             torch.set_num_threads(cores)
             n_cpu = args.cpu_points
             c1, d1 = synthetic_batch(1, n_cpu, seed=0)
-            t_cpu, _ = cpu_reference_step(cfg, params, c1, d1)
+            t_cpu, loss_cpu, pa_cpu = cpu_reference_step(cfg, params, c1, d1)
             line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "points/s", "cores": cores, "kind": "port",
                                     "sample": f"1 tile of {n_cpu} points, fwd+L1+bwd once through oracle/ (torch CPU, {cores} threads), {t_cpu:.1f} s"}
+            # the same tile through the CUDA path (current parameters = the oracle's: AdamW steps are undone by
+            # reloading them): the checker's result is compared, not thrown away
+            model.load_state_dict(params)
+            with torch.no_grad():
+                pa_gpu, _ = model(input_cloud=c1.to(dev))
+            loss_gpu = torch.nn.functional.l1_loss(pa_gpu.squeeze(), d1.to(dev).squeeze()).item()
+            line["parity"] = {"tile_points": n_cpu,
+                              "heights_rel": float((pa_gpu.cpu() - pa_cpu).abs().max() / pa_cpu.abs().max()),
+                              "loss_rel": abs(loss_gpu - loss_cpu) / abs(loss_cpu), "tolerance": 1e-4}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
