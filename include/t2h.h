@@ -76,32 +76,50 @@ int t2h_gather_rows(const float* src, const int32_t* perm, int64_t n_rows, int w
 int t2h_scatter_rows(const float* src, const int32_t* perm, int64_t n_rows, int width, float* dst,
                      t2h_stream_t stream);
 
-/* ---- a2: pointnet.py:92-99 pool_local = torch_scatter.scatter_max + gather ------------------
+/* ---- a2 / a3: segmented reductions over the sorted points ---------------------------------------
+ * All of them are ROW-BALANCED: work is split into fixed chunks of consecutive sorted positions
+ * (`row_keys[i]` = sort key of sorted position i, i.e. keys_sorted of t2h_sort_by_cell; the segment of a
+ * level is row_keys[i] >> shift), so a cell with thousands of points costs the same per row as a cell with
+ * one.  Cells inside a chunk are finished by the walker; cells that cross a chunk border leave partials in
+ * `workspace` (t2h_seg_workspace_bytes) that a fix-up launch adds in chunk order.  No atomics.           */
+size_t t2h_seg_workspace_bytes(int64_t n_rows, int64_t n_seg, int C);
+
+/* a2: pointnet.py:92-99 pool_local = torch_scatter.scatter_max + gather.
  * Per segment and channel: max over the segment's rows, ties -> first row in sorted order
  * (= smallest point index, the torch_scatter CPU rule), empty -> 0 / arg -1.
- *   pooled (n_rows, C), nullable: the max broadcast back to every row of the segment
+ *   pooled (n_rows, C), nullable: the max broadcast back to every row of the segment (needs plane)
  *   plane  (n_seg, C),  nullable: the per-cell max, rows in row-major (b, y, x) cell order
  *   arg    (n_seg, C)  int32   : winning ROW index (same row order as plane), -1 if empty
  *   tie_rank, nullable: original point index of every sorted position; needed for the tie rule
  *     when a segment spans several sort keys (shift > 0), where sorted order != point order       */
-int t2h_seg_max_fwd(const float* rows, const int32_t* perm, const int32_t* tie_rank,
-                    const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton,
-                    int reso, float* pooled, float* plane, int32_t* arg, t2h_stream_t stream);
-/* grad_rows[row, c] = (row == arg[seg, c]) ? sum_{rows of seg} grad_pooled[., c] + grad_plane[seg, c] : 0 */
-int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane, const int32_t* perm,
-                    const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton,
-                    int reso, const int32_t* arg, float* grad_rows, t2h_stream_t stream);
+int t2h_seg_max_fwd(const float* rows, int64_t n_rows, const int32_t* perm, const int32_t* tie_rank,
+                    const int32_t* row_keys, const int32_t* cell_start, int64_t n_seg, int shift, int C,
+                    int morton, int reso, void* workspace, size_t workspace_bytes, float* pooled,
+                    float* plane, int32_t* arg, t2h_stream_t stream);
+/* grad_rows[row, c] = (row == arg[seg, c]) ? sum_{rows of seg} grad_pooled[., c] + grad_plane[seg, c] : 0
+ * (either gradient may be NULL; the workspace is only needed with grad_pooled) */
+int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane, int64_t n_rows, const int32_t* perm,
+                    const int32_t* row_keys, const int32_t* cell_start, int64_t n_seg, int shift, int C,
+                    int morton, int reso, const int32_t* arg, void* workspace, size_t workspace_bytes,
+                    float* grad_rows, t2h_stream_t stream);
 
-/* ---- a3: pointnet.py:101-111, alto.py:76-88,187-197 torch_scatter.scatter_mean ---------------
+/* a3: pointnet.py:101-111, alto.py:76-88,187-197 torch_scatter.scatter_mean.
  * plane[cell, :] = sum of the segment's rows (/ count when mean != 0); empty cell -> 0.        */
-int t2h_seg_reduce_fwd(const float* rows, int64_t n_rows, const int32_t* perm,
-                       const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton,
-                       int reso, int mean, float* plane, t2h_stream_t stream);
+int t2h_seg_reduce_fwd(const float* rows, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
+                       const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                       int mean, void* workspace, size_t workspace_bytes, float* plane, t2h_stream_t stream);
 /* rows[row, :] = plane[cell(row), :] (/ count when mean != 0): backward of the mean, and the
- * gather-back of pool_local when scatter_type == 'mean'                                        */
-int t2h_seg_broadcast(const float* plane, const int32_t* perm, const int32_t* cell_start,
-                      int64_t n_seg, int shift, int C, int morton, int reso, int mean,
-                      float* rows, t2h_stream_t stream);
+ * gather-back of pool_local when scatter_type == 'mean'; a pure row-parallel map               */
+int t2h_seg_broadcast(const float* plane, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
+                      const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                      int mean, float* rows, t2h_stream_t stream);
+/* the scatter_mean pair under the names of SURVEY.md §8(b): = t2h_seg_reduce_fwd(mean = 1) / t2h_seg_broadcast(mean = 1) */
+int t2h_seg_mean_fwd(const float* rows, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
+                     const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                     void* workspace, size_t workspace_bytes, float* plane, t2h_stream_t stream);
+int t2h_seg_mean_bwd(const float* grad_plane, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
+                     const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                     float* grad_rows, t2h_stream_t stream);
 
 /* ---- a4: alto.py:90-95,199-205 F.grid_sample(bilinear, border, align_corners=True) -----------
  * out_rows[row, :] = 4-tap bilinear sample of plane[b] at (x, y) = xyz_sorted[i, 0:2]
@@ -110,15 +128,20 @@ int t2h_seg_broadcast(const float* plane, const int32_t* perm, const int32_t* ce
 int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, const float* xyz_sorted,
                             int64_t point_stride, const int32_t* perm, const int32_t* tile_ids,
                             int64_t n_points, int64_t n_per_batch, float* out_rows, t2h_stream_t stream);
-/* grad_plane (B, r, r, C), atomic-free and deterministic.  With Morton keys and C in {32..1024} (and a
- * workspace): shared-memory-staged scatter, one CTA per 8x8 block of cells with a one-cell halo, single
- * writer per accumulator, block tiles merged in a fixed order.  Otherwise (workspace NULL, row-major keys,
- * odd C): gather over the 3x3 neighbour cells of every plane cell. */
-size_t t2h_bilinear_sample_bwd_workspace_bytes(int reso, int C, int64_t n_seg, int morton);
+/* grad_plane (B, r, r, C), atomic-free and deterministic (replaces grid_sampler_2d_backward's atomicAdd).
+ * With Morton keys, `row_keys` and a workspace:
+ *   - few rows per cell, C in {32, 64, 128}: warp-private shared-memory accumulator tiles over Morton blocks of
+ *     cells with a one-cell halo (single writer per accumulator, sorted point order), region tiles merged in a
+ *     fixed order;
+ *   - otherwise (C = 32, 64 or a multiple of 128): row-balanced walk that keeps the nine (3x3 target) partial
+ *     sums of the current cell in registers, chunk-border partials added in chunk order, then a 9-tap gather.
+ * Else (workspace / row_keys NULL, row-major keys, other C): gather over the 3x3 neighbour cells of every
+ * plane cell. */
+size_t t2h_bilinear_sample_bwd_workspace_bytes(int reso, int C, int64_t n_points, int64_t n_seg, int morton);
 int t2h_bilinear_sample_bwd(const float* grad_rows, int64_t n_points, int reso, int C,
                             const float* xyz_sorted, int64_t point_stride, const int32_t* perm,
-                            const int32_t* cell_start, int64_t n_seg, int shift, int morton,
-                            void* workspace, size_t workspace_bytes, float* grad_plane,
+                            const int32_t* row_keys, const int32_t* cell_start, int64_t n_seg, int shift,
+                            int morton, void* workspace, size_t workspace_bytes, float* grad_plane,
                             t2h_stream_t stream);
 
 /* ---- a5: pixel.py:105-111 F.interpolate(bilinear, align_corners=True) ----------------------- */

@@ -43,7 +43,10 @@ def test_header_cites_reference():
 def test_argument_validation_without_gpu(lib):
     # invalid arguments are rejected before any launch, so this is safe on a CPU box
     assert lib.t2h_cell_index(None, 10, 2, 256, None, None) == 1
-    assert lib.t2h_seg_reduce_fwd(None, 8, None, None, 8, 0, 32, 0, 4, 1, None, None) == 1
+    # rows, n_rows, perm, row_keys, cell_start, n_seg, shift, C, morton, reso, mean, ws, ws_bytes, plane, stream
+    assert lib.t2h_seg_reduce_fwd(None, 8, None, None, None, 8, 0, 32, 0, 4, 1, None, 0, None, None) == 1
+    assert lib.t2h_seg_mean_fwd(None, 8, None, None, None, 8, 0, 32, 0, 4, None, 0, None, None) == 1
+    assert lib.t2h_seg_workspace_bytes(1 << 20, 1 << 16, 32) >= (1 << 20) // 32 * 2 * 32 * 8
     assert lib.t2h_xy_keys(None, 0, 3, 1, 100, 1, None, None) == 1
 
 

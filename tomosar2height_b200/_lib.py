@@ -32,13 +32,16 @@ SIGNATURES = {
     "t2h_sort_by_cell": [_p, _i64, _i64, _p, _sz, _p, _p, _p, _p],
     "t2h_gather_rows": [_p, _p, _i64, _i32, _p, _p],
     "t2h_scatter_rows": [_p, _p, _i64, _i32, _p, _p],
-    "t2h_seg_max_fwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p],
-    "t2h_seg_max_bwd": [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p],
-    "t2h_seg_reduce_fwd": [_p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
-    "t2h_seg_broadcast": [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
+    "t2h_seg_workspace_bytes": [_i64, _i64, _i32],
+    "t2h_seg_max_fwd": [_p, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _sz, _p, _p, _p, _p],
+    "t2h_seg_max_bwd": [_p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _sz, _p, _p],
+    "t2h_seg_reduce_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _sz, _p, _p],
+    "t2h_seg_broadcast": [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
+    "t2h_seg_mean_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _sz, _p, _p],
+    "t2h_seg_mean_bwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_bilinear_sample_fwd": [_p, _i32, _i32, _p, _i64, _p, _p, _i64, _i64, _p, _p],
-    "t2h_bilinear_sample_bwd_workspace_bytes": [_i32, _i32, _i64, _i32],
-    "t2h_bilinear_sample_bwd": [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _i64, _i32, _i32, _p, _sz, _p, _p],
+    "t2h_bilinear_sample_bwd_workspace_bytes": [_i32, _i32, _i64, _i64, _i32],
+    "t2h_bilinear_sample_bwd": [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _p, _sz, _p, _p],
     "t2h_upsample_bilinear_fwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_upsample_bilinear_bwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_split_tf32": [_p, _i64, _p, _p, _p],
@@ -61,7 +64,8 @@ SIGNATURES = {
 }
 _RESTYPE = {"t2h_status_string": ctypes.c_char_p, "t2h_sort_workspace_bytes": _sz,
             "t2h_linear_wgrad_workspace_bytes": _sz, "t2h_colsum_workspace_bytes": _sz,
-            "t2h_conv3x3_wgrad_workspace_bytes": _sz, "t2h_bilinear_sample_bwd_workspace_bytes": _sz}
+            "t2h_conv3x3_wgrad_workspace_bytes": _sz, "t2h_bilinear_sample_bwd_workspace_bytes": _sz,
+            "t2h_seg_workspace_bytes": _sz}
 
 _lib = None
 _lock = threading.Lock()

@@ -10,7 +10,6 @@
 // order (grid_sample taps of a point in cell cx are always within {cx-1, cx, cx+1}, because the
 // corner-aligned coordinate p*(r-1) lies in (cx-1, cx+1) when p*r is in [cx, cx+1)).
 #include "t2h_common.cuh"
-#include <cstdlib>
 
 namespace t2h {
 
@@ -212,293 +211,145 @@ sample_bwd_kernel(const float* __restrict__ grad_rows, int reso, const float* __
   }
 }
 
-// ---- G2, tiled: shared-memory-staged, atomic-free, deterministic ------------------------------------
-// A CTA owns a T x T block of plane cells.  With Morton keys its points are ONE contiguous range of the
-// sorted order, so their gradient rows stream in coalesced and are read exactly once.  Every point
-// scatters its four weighted contributions into a (T+2) x (T+2) accumulator tile in shared memory
-// (taps of a point of cell cx lie in columns cx-1..cx+1, hence the one-cell halo).  Determinism without
-// atomics comes from ownership: the 8 warps form CG channel groups x PG point groups; a warp only ever
-// touches its own 32*V-channel slice of its point group's private tile, in point order, so each
-// accumulator has a single writer and a fixed summation order.  Private tiles are then summed in group
-// order into a per-block scratch tile; sample_bwd_merge_kernel adds the (<= 4) overlapping block tiles
-// of every plane cell in a fixed order.
 constexpr int kTileWarps = 8;
 
-template <int C, int T>
-struct TileCfg {
-  static constexpr int CG = (C / 32 < kTileWarps) ? C / 32 : kTileWarps;  // channel groups
-  static constexpr int V = C / (32 * CG);                                // floats per lane
-  static constexpr int PG = kTileWarps / CG;                             // point groups (private tiles)
-  static constexpr int TW = T + 2;
-  static constexpr int TILE_FLOATS = TW * TW * C;
-  static constexpr int SMEM = PG * TILE_FLOATS * 4;
+// ---- G2, fine levels (few rows per cell): warp-private shared-memory tiles ------------------------------
+// A CTA owns a Morton-aligned region of 8 blocks of TW x TW cells (4 blocks wide, 2 tall); warp w owns block w,
+// whose points are ONE contiguous range of the sorted order, and a private (TW+2) x (TW+2) accumulator tile
+// (taps of a point of cell cx lie in columns cx-1..cx+1, hence the one-cell halo).  Rows stream in coalesced and
+// are read exactly once.  A row of C floats is LPR = C/4 lanes x float4; the G = 32/LPR lane groups of the warp
+// all load the SAME row and each adds it into a different one of the row's four taps (G = 4: one tap each,
+// G = 1: four taps in turn), so no two lanes ever touch one accumulator at the same time and every accumulator
+// sees its contributions in sorted point order: atomic-free, deterministic, and a fat cell only costs its own
+// warp time in proportion to its rows.  The eight private tiles are then summed (fixed block order) into the
+// region's haloed tile in scratch; sample_bwd_merge_kernel adds the (<= 4) overlapping region tiles of every
+// plane cell.
+template <int C, int TW>
+struct WTile {
+  static constexpr int LPR = C / 4, G = 32 / LPR, TAPS = 4 / G;
+  static constexpr int TWH = TW + 2;
+  static constexpr int TILE_FLOATS = TWH * TWH * C;
+  static constexpr int RW = 4 * TW, RH = 2 * TW;          // region extent in cells
+  static constexpr int RWH = RW + 2, RHH = RH + 2;        // with the halo
+  static constexpr int LOG2_REGION = (TW == 4) ? 7 : 5;   // log2(8 * TW * TW)
+  static constexpr int LOG2_BLOCK = (TW == 4) ? 4 : 2;
+  static constexpr int STAGE_WORDS = 32 * 9;              // per warp: 32 rows x (4 tap cells, 4 weights, row)
+  static constexpr int SMEM = (kTileWarps * TILE_FLOATS + kTileWarps * STAGE_WORDS) * 4;
 };
 
-template <int C, int T>
-__global__ void __launch_bounds__(kTileWarps * kWarp)
-sample_bwd_tiled_kernel(const float* __restrict__ grad_rows, int reso, const float* __restrict__ xyz, int64_t stride,
-                        const int32_t* __restrict__ perm, const int32_t* __restrict__ cell_start, int shift,
-                        int log2_cells, float* __restrict__ scratch) {
-  using Cfg = TileCfg<C, T>;
-  constexpr int CG = Cfg::CG, V = Cfg::V, PG = Cfg::PG, TW = Cfg::TW;
-  extern __shared__ float tile_smem[];
-  constexpr int LOG2_T2 = (T == 8) ? 6 : ((T == 4) ? 4 : ((T == 2) ? 2 : 0));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pg = warp / CG, cg = warp % CG;
-  // block index -> tile (image) and Morton block code -> origin
-  const int64_t blk = blockIdx.x;
-  const int blocks_log2 = log2_cells - LOG2_T2;
-  const int64_t img = blk >> blocks_log2;
-  const uint32_t bcode = (uint32_t)(blk - (img << blocks_log2));
-  const int bx0 = (int)compact1by1(bcode) * T, by0 = (int)compact1by1(bcode >> 1) * T;
-  const int64_t key0 = (img << log2_cells) + ((int64_t)bcode << LOG2_T2);
-  const int p0 = cell_start[key0 << shift], p1 = cell_start[(key0 + (1 << LOG2_T2)) << shift];
-
-  for (int f = threadIdx.x; f < PG * Cfg::TILE_FLOATS / 4; f += kTileWarps * kWarp)
-    reinterpret_cast<float4*>(tile_smem)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-
-  // this point group's contiguous slice of the block's points
-  const int len = p1 - p0, chunk = (len + PG - 1) / PG;
-  const int q0 = min(p0 + pg * chunk, p1), q1 = min(q0 + chunk, p1);
-  float* priv = tile_smem + pg * Cfg::TILE_FLOATS + cg * 32 * V + lane * V;
-  const float* gbase = grad_rows + cg * 32 * V + lane * V;
-  for (int base_i = q0; base_i < q1; base_i += kWarp) {
-    const int nb = min(kWarp, q1 - base_i);
-    int my_cell = 0, my_row = 0;
-    float my_nw = 0.f, my_ne = 0.f, my_sw = 0.f, my_se = 0.f;
+// rows [r0, r1) of the sorted order (all inside the block whose haloed tile origin is (bx0 - 1, by0 - 1)) -> tile.
+// Lane j resolves the taps of row j of a 32-row batch once and parks them in the warp's staging arrays; the row
+// loads of the NEXT U rows are in flight while the current U rows are added (double buffer).
+template <int C, int TW>
+__device__ __forceinline__ void wtile_accumulate(float* __restrict__ tile, int* __restrict__ st_cell, float* __restrict__ st_w,
+                                                 int* __restrict__ st_row, const float* __restrict__ grad_rows, int reso,
+                                                 const float* __restrict__ xyz, int64_t stride, const int32_t* __restrict__ perm,
+                                                 int r0, int r1, int bx0, int by0, int lane) {
+  using Cfg = WTile<C, TW>;
+  constexpr int LPR = Cfg::LPR, TAPS = Cfg::TAPS, TWH = Cfg::TWH;
+  constexpr int U = 8;
+  const int sub = lane / LPR, l = lane % LPR;
+  const float* gbase = grad_rows + l * 4;
+  for (int base_i = r0; base_i < r1; base_i += kWarp) {
+    const int nb = min(kWarp, r1 - base_i);
     if (lane < nb) {
       const int i = base_i + lane;
       const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + (int64_t)i * stride));
       const Taps t = make_taps(pxy.x, pxy.y, reso);
-      my_nw = __fmul_rn(t.wx0, t.wy0);
-      my_ne = (t.x0 + 1 < reso) ? __fmul_rn(t.wx1, t.wy0) : 0.f;
-      my_sw = (t.y0 + 1 < reso) ? __fmul_rn(t.wx0, t.wy1) : 0.f;
-      my_se = (t.x0 + 1 < reso && t.y0 + 1 < reso) ? __fmul_rn(t.wx1, t.wy1) : 0.f;
-      // local coordinates in the haloed tile; clamp defensively (a point is always within one cell)
-      const int lx = min(max(t.x0 - bx0 + 1, 0), T), ly = min(max(t.y0 - by0 + 1, 0), T);
-      my_cell = ly * TW + lx;
-      my_row = perm ? perm[i] : i;
+      const bool in_x = t.x0 + 1 < reso, in_y = t.y0 + 1 < reso;
+      // local coordinates in the haloed tile; clamp defensively (a point is always within one cell of its own)
+      const int lx = min(max(t.x0 - bx0 + 1, 0), TW), ly = min(max(t.y0 - by0 + 1, 0), TW);
+      const int c0 = (ly * TWH + lx) * C;
+      // taps beyond the last row / column do not exist (ATen skips them): cell -1
+      *reinterpret_cast<int4*>(st_cell + lane * 4) =
+          make_int4(c0, in_x ? c0 + C : -1, in_y ? c0 + TWH * C : -1, (in_x && in_y) ? c0 + TWH * C + C : -1);
+      *reinterpret_cast<float4*>(st_w + lane * 4) = make_float4(__fmul_rn(t.wx0, t.wy0), __fmul_rn(t.wx1, t.wy0),
+                                                                __fmul_rn(t.wx0, t.wy1), __fmul_rn(t.wx1, t.wy1));
+      st_row[lane] = perm ? __ldg(perm + i) : i;
     }
-    // U points per trip: issue all row loads first (memory-level parallelism), then the shared-memory updates
-    constexpr int U = (V <= 2) ? 8 : 4;
+    __syncwarp();
+    float4 cur[U], nxt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) cur[u] = ld4_stream(gbase + (int64_t)st_row[min(u, nb - 1)] * C);
     for (int j0 = 0; j0 < nb; j0 += U) {
-      int cell[U];
-      float wq[U][4], g[U][V];
+      if (j0 + U < nb) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = min(j0 + u, nb - 1);
-        cell[u] = __shfl_sync(0xffffffffu, my_cell, j);
-        const int row = __shfl_sync(0xffffffffu, my_row, j);
-        wq[u][0] = __shfl_sync(0xffffffffu, my_nw, j); wq[u][1] = __shfl_sync(0xffffffffu, my_ne, j);
-        wq[u][2] = __shfl_sync(0xffffffffu, my_sw, j); wq[u][3] = __shfl_sync(0xffffffffu, my_se, j);
-        const float* gp = gbase + (int64_t)row * C;
-        if constexpr (V == 1) {
-          g[u][0] = __ldg(gp);
-        } else if constexpr (V == 2) {
-          const float2 t2 = __ldg(reinterpret_cast<const float2*>(gp));
-          g[u][0] = t2.x; g[u][1] = t2.y;
-        } else {
-          const float4 t4 = ld4(gp);
-          g[u][0] = t4.x; g[u][1] = t4.y; g[u][2] = t4.z; g[u][3] = t4.w;
-        }
+        for (int u = 0; u < U; ++u) nxt[u] = ld4_stream(gbase + (int64_t)st_row[min(j0 + U + u, nb - 1)] * C);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (j0 + u >= nb) break;
-        float* a = priv + cell[u] * C;
+        if (j0 + u < nb) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          a[v] += wq[u][0] * g[u][v];
-          a[C + v] += wq[u][1] * g[u][v];
-          a[TW * C + v] += wq[u][2] * g[u][v];
-          a[TW * C + C + v] += wq[u][3] * g[u][v];
+          for (int tt = 0; tt < TAPS; ++tt) {
+            const int t = sub * TAPS + tt;
+            const int cell = st_cell[(j0 + u) * 4 + t];
+            const float w = st_w[(j0 + u) * 4 + t];
+            if (cell >= 0) {
+              float4* a = reinterpret_cast<float4*>(tile + cell + l * 4);
+              float4 v = *a;
+              v.x += w * cur[u].x; v.y += w * cur[u].y; v.z += w * cur[u].z; v.w += w * cur[u].w;
+              *a = v;
+            }
+          }
         }
+        __syncwarp();  // the next row may hit the accumulators another lane group just wrote
       }
-    }
-  }
-  __syncthreads();
-  // private tiles -> scratch, summed in point-group order
-  float* dst = scratch + blk * (int64_t)Cfg::TILE_FLOATS;
-  for (int f = threadIdx.x; f < Cfg::TILE_FLOATS / 4; f += kTileWarps * kWarp) {
-    float4 acc = reinterpret_cast<const float4*>(tile_smem)[f];
 #pragma unroll
-    for (int q = 1; q < PG; ++q) {
-      const float4 o = reinterpret_cast<const float4*>(tile_smem + q * Cfg::TILE_FLOATS)[f];
-      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      for (int u = 0; u < U; ++u) cur[u] = nxt[u];
     }
-    st4(dst + f * 4, acc);
+    __syncwarp();      // the staging arrays are rewritten by the next batch
   }
 }
 
-// ---- G2, cell-parallel: register accumulation of the 3x3 target partials ------------------------------
-// All points of one own cell (cx, cy) contribute to the same 3x3 target cells (cx-1..cx+1, cy-1..cy+1),
-// so a warp that walks a cell's (contiguous) rows keeps nine partial sums in REGISTERS -- no per-point
-// shared-memory traffic, rows are read once, coalesced.  A CTA owns a T x T Morton block of cells; per
-// round its 8 warps are split into (cells x row slices x 128-channel groups).  Slice partials are combined
-// through shared memory in slice order, every own cell's nine partials are staged in shared memory, and
-// the block's haloed (T+2) x (T+2) output tile is assembled from them in a fixed order and written to
-// scratch; sample_bwd_merge_kernel adds the overlapping block tiles.  No atomics, fixed summation order.
-template <int C, int T>
-struct CellCfg {
-  static constexpr int CW = C < 128 ? C : 128;   // channels per warp
-  static constexpr int CGN = C / CW;             // channel groups
-  static constexpr int RF = kTileWarps / CGN;    // warps per channel group = cells per round x slices
-  static constexpr int LPR = CW / 4, RPI = 32 / LPR;
-  static constexpr int NC = T * T, TW = T + 2;
-  static constexpr int PARTS_FLOATS = kTileWarps * 9 * CW;
-  static constexpr int STAGE_FLOATS = NC * 9 * C;
-  static constexpr int SMEM = (PARTS_FLOATS + STAGE_FLOATS) * 4;
-  static constexpr int LOG2_T2 = (T == 8) ? 6 : ((T == 4) ? 4 : ((T == 2) ? 2 : 0));
-};
+// Blocks with more than kHeavyBlock rows (a facade end, thousands of points in a few cells) are not walked by
+// their one warp -- the rest of the grid would have finished long before -- but left to the row-balanced pass
+// below (sample_bwd_wtile_heavy_kernel), which adds them into the region tile afterwards.
+constexpr int kHeavyBlock = 128;
 
-template <int C, int T>
+template <int C, int TW>
 __global__ void __launch_bounds__(kTileWarps * kWarp)
-sample_bwd_cell_kernel(const float* __restrict__ grad_rows, int reso, const float* __restrict__ xyz, int64_t stride,
-                       const int32_t* __restrict__ perm, const int32_t* __restrict__ cell_start, int shift,
-                       int log2_cells, int slices, float* __restrict__ scratch) {
-  // gridDim.y = ZS: on coarse levels (hundreds of rows per cell) the rows of every cell are additionally
-  // split over ZS CTAs, each writing its own scratch tile; the merge kernel adds them in z order
-  using Cfg = CellCfg<C, T>;
-  constexpr int CW = Cfg::CW, CGN = Cfg::CGN, RF = Cfg::RF, LPR = Cfg::LPR, RPI = Cfg::RPI, NC = Cfg::NC, TW = Cfg::TW;
-  extern __shared__ float cell_smem[];
-  float* parts = cell_smem;                       // [warp][9][CW]
-  float* stage = cell_smem + Cfg::PARTS_FLOATS;   // [own cell][9][C]
-  __shared__ int cell_heavy[NC];
-  constexpr int kHeavyRows = 96;                  // rows per slice beyond which a cell counts as heavy
+sample_bwd_wtile_kernel(const float* __restrict__ grad_rows, int reso, const float* __restrict__ xyz, int64_t stride,
+                        const int32_t* __restrict__ perm, const int32_t* __restrict__ cell_start, int shift,
+                        int log2_cells, float* __restrict__ scratch) {
+  using Cfg = WTile<C, TW>;
+  constexpr int TWH = Cfg::TWH;
+  extern __shared__ float wt_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, l = lane % LPR;
-  const int cg = warp % CGN, rest = warp / CGN;
-  const int sl = rest % slices, cr = rest / slices;
-  const int cells_per_round = RF / slices;
+  float* tile = wt_smem + warp * Cfg::TILE_FLOATS;
+  int* st_cell = reinterpret_cast<int*>(wt_smem + kTileWarps * Cfg::TILE_FLOATS) + warp * Cfg::STAGE_WORDS;  // [32][4]
+  float* st_w = reinterpret_cast<float*>(st_cell + 32 * 4);                                                  // [32][4]
+  int* st_row = st_cell + 32 * 8;                                                                           // [32]
 
-  const int64_t blk = blockIdx.x;
-  const int blocks_log2 = log2_cells - Cfg::LOG2_T2;
-  const int64_t img = blk >> blocks_log2;
-  const uint32_t bcode = (uint32_t)(blk - (img << blocks_log2));
-  const int bx0 = (int)compact1by1(bcode) * T, by0 = (int)compact1by1(bcode >> 1) * T;
-  const int64_t key0 = (img << log2_cells) + ((int64_t)bcode << Cfg::LOG2_T2);
-  const float* gbase = grad_rows + cg * CW + l * 4;
+  // region -> image, origin; warp -> block origin
+  const int64_t region = blockIdx.x;
+  const int regions_log2 = log2_cells - Cfg::LOG2_REGION;
+  const int64_t img = region >> regions_log2;
+  const uint32_t rcode = (uint32_t)(region - (img << regions_log2)) << Cfg::LOG2_REGION;  // Morton code of the first cell
+  const int rx0 = (int)compact1by1(rcode), ry0 = (int)compact1by1(rcode >> 1);
+  const int bx = (warp & 1) | (((warp >> 2) & 1) << 1), by = (warp >> 1) & 1;
+  const int bx0 = rx0 + bx * TW, by0 = ry0 + by * TW;
+  const int64_t key0 = (img << log2_cells) + rcode + ((int64_t)warp << Cfg::LOG2_BLOCK);
+  const int p0 = __ldg(cell_start + (key0 << shift)), p1 = __ldg(cell_start + ((key0 + (1 << Cfg::LOG2_BLOCK)) << shift));
 
-  // rows of own cell q, slice my_sl of n_sl  ->  nine partial sums in registers  ->  parts[warp]
-  auto reduce_cell = [&](int q, int my_sl, int n_sl) {
-    float4 acc[9];
-#pragma unroll
-    for (int d = 0; d < 9; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int cx = bx0 + (int)compact1by1((uint32_t)q), cy = by0 + (int)compact1by1((uint32_t)q >> 1);
-    const int beg = cell_start[(key0 + q) << shift], end = cell_start[(key0 + q + 1) << shift];
-    const int zs = gridDim.y, tot_sl = n_sl * zs, g_sl = blockIdx.y * n_sl + my_sl;
-    const int len = end - beg, chunk = (len + tot_sl - 1) / tot_sl;
-    const int r0 = min(beg + g_sl * chunk, end), r1 = min(r0 + chunk, end);
-    for (int base_i = r0; base_i < r1; base_i += kWarp) {
-      const int nb = min(kWarp, r1 - base_i);
-      // lane j: the 3 + 3 separable target weights of row base_i + j (the tap arithmetic runs once per row)
-      float wx_m = 0.f, wx_0 = 0.f, wx_p = 0.f, wy_m = 0.f, wy_0 = 0.f, wy_p = 0.f;
-      int my_row = 0;
-      if (lane < nb) {
-        const int i = base_i + lane;
-        const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + (int64_t)i * stride));
-        const Taps t = make_taps(pxy.x, pxy.y, reso);
-        const float wx1 = (t.x0 + 1 < reso) ? t.wx1 : 0.f, wy1 = (t.y0 + 1 < reso) ? t.wy1 : 0.f;
-        if (t.x0 < cx) { wx_m = t.wx0; wx_0 = wx1; } else { wx_0 = t.wx0; wx_p = wx1; }
-        if (t.y0 < cy) { wy_m = t.wy0; wy_0 = wy1; } else { wy_0 = t.wy0; wy_p = wy1; }
-        my_row = perm ? perm[i] : i;
-      }
-      // U rows per sub-group per trip: all U row loads are issued before the FMAs (memory-level parallelism)
-      constexpr int U = (RPI > 1) ? 1 : 4;  // narrow rows already cover RPI rows per trip; fine cells hold ~4 rows
-      for (int t0 = 0; t0 < nb; t0 += RPI * U) {
-        float4 g[U];
-        float wx[U][3], wy[U][3];
-        bool act[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int j = t0 + u * RPI + sub;
-          act[u] = j < nb;
-          const int src = act[u] ? j : 0;
-          const int row = __shfl_sync(0xffffffffu, my_row, src);
-          wx[u][0] = __shfl_sync(0xffffffffu, wx_m, src); wx[u][1] = __shfl_sync(0xffffffffu, wx_0, src); wx[u][2] = __shfl_sync(0xffffffffu, wx_p, src);
-          wy[u][0] = __shfl_sync(0xffffffffu, wy_m, src); wy[u][1] = __shfl_sync(0xffffffffu, wy_0, src); wy[u][2] = __shfl_sync(0xffffffffu, wy_p, src);
-          g[u] = act[u] ? ld4(gbase + (int64_t)row * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (!act[u]) continue;
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const float w = __fmul_rn(wx[u][dx], wy[u][dy]);
-              float4& a = acc[dy * 3 + dx];
-              a.x += w * g[u].x; a.y += w * g[u].y; a.z += w * g[u].z; a.w += w * g[u].w;
-            }
-        }
-      }
-    }
-    // fold the RPI sub-rows of the warp (fixed xor tree)
-#pragma unroll
-    for (int off = LPR; off < kWarp; off <<= 1)
-#pragma unroll
-      for (int d = 0; d < 9; ++d) {
-        const float4 o = shfl_xor4(acc[d], off);
-        acc[d].x += o.x; acc[d].y += o.y; acc[d].z += o.z; acc[d].w += o.w;
-      }
-    if (sub == 0) {
-#pragma unroll
-      for (int d = 0; d < 9; ++d) *reinterpret_cast<float4*>(parts + (warp * 9 + d) * CW + l * 4) = acc[d];
-    }
-  };
-  // parts of n_cells own cells (n_sl slices each) -> stage, in slice order; cells flagged `skip_heavy` are left out
-  auto combine = [&](int q_first, int n_cells, int n_sl, bool skip_heavy) {
-    for (int idx = threadIdx.x; idx < n_cells * 9 * (C / 4); idx += kTileWarps * kWarp) {
-      const int c4i = idx % (C / 4);
-      const int d = (idx / (C / 4)) % 9;
-      const int crr = idx / (9 * (C / 4));
-      if (skip_heavy && cell_heavy[q_first + crr]) continue;
-      const int cgi = (c4i * 4) / CW, within = (c4i * 4) % CW;
-      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s2 = 0; s2 < n_sl; ++s2) {
-        const int w2 = (crr * n_sl + s2) * CGN + cgi;
-        const float4 o = *reinterpret_cast<const float4*>(parts + (w2 * 9 + d) * CW + within);
-        sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
-      }
-      *reinterpret_cast<float4*>(stage + ((q_first + crr) * 9 + d) * C + c4i * 4) = sum;
-    }
-  };
-
-  // heavy cells (a facade crossing the block) are deferred and then reduced by every warp of the CTA
-  if (threadIdx.x < NC) {
-    const int len = cell_start[(key0 + threadIdx.x + 1) << shift] - cell_start[(key0 + threadIdx.x) << shift];
-    cell_heavy[threadIdx.x] = (slices < RF && len > kHeavyRows * slices * (int)gridDim.y) ? 1 : 0;
-  }
+  for (int f = lane; f < Cfg::TILE_FLOATS / 4; f += kWarp) reinterpret_cast<float4*>(tile)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  if (p1 - p0 <= kHeavyBlock)
+    wtile_accumulate<C, TW>(tile, st_cell, st_w, st_row, grad_rows, reso, xyz, stride, perm, p0, p1, bx0, by0, lane);
   __syncthreads();
-  for (int q0 = 0; q0 < NC; q0 += cells_per_round) {
-    const int q = q0 + cr;
-    if (q < NC && !cell_heavy[q]) reduce_cell(q, sl, slices);
-    __syncthreads();
-    combine(q0, min(cells_per_round, NC - q0), slices, true);
-    __syncthreads();
-  }
-  for (int q = 0; q < NC; ++q) {
-    if (!cell_heavy[q]) continue;  // uniform across the CTA
-    reduce_cell(q, rest, RF);
-    __syncthreads();
-    combine(q, 1, RF, false);
-    __syncthreads();
-  }
-  // haloed output tile of the block: target (ly, lx) collects partial d = (dy, dx) of own cell (ly-1-dy, lx-1-dx)
-  float* dst = scratch + ((int64_t)blockIdx.y * gridDim.x + blk) * (int64_t)(TW * TW * C);
-  for (int idx = threadIdx.x; idx < TW * TW * (C / 4); idx += kTileWarps * kWarp) {
+  // region tile = sum of the private tiles that cover each haloed cell, in block order (by, bx)
+  float* dst = scratch + region * (int64_t)(Cfg::RWH * Cfg::RHH * C);
+  for (int idx = threadIdx.x; idx < Cfg::RWH * Cfg::RHH * (C / 4); idx += kTileWarps * kWarp) {
     const int c4i = idx % (C / 4), cellt = idx / (C / 4);
-    const int ly = cellt / TW, lx = cellt % TW;
+    const int ry = cellt / Cfg::RWH, rx = cellt % Cfg::RWH;
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+    for (int qy = 0; qy < 2; ++qy)
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int oy = ly - dy, ox = lx - dx;  // = (ly - 1) - (dy - 1)
-        if (ox >= 0 && ox < T && oy >= 0 && oy < T) {
-          const int qq = (int)(part1by1((uint32_t)ox) | (part1by1((uint32_t)oy) << 1));
-          const float4 o = *reinterpret_cast<const float4*>(stage + (qq * 9 + dy * 3 + dx) * C + c4i * 4);
+      for (int qx = 0; qx < 4; ++qx) {
+        const int lx = rx - qx * TW, ly = ry - qy * TW;
+        if (lx >= 0 && lx < TWH && ly >= 0 && ly < TWH) {
+          const int w2 = (qx & 1) | (qy << 1) | ((qx >> 1) << 2);
+          const float4 o = *reinterpret_cast<const float4*>(wt_smem + w2 * Cfg::TILE_FLOATS + (ly * TWH + lx) * C + c4i * 4);
           sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
         }
       }
@@ -506,14 +357,254 @@ sample_bwd_cell_kernel(const float* __restrict__ grad_rows, int reso, const floa
   }
 }
 
-// grad_plane[b, y, x, :] = sum of the block tiles that cover (x, y): own block plus the left/upper or
-// right/lower neighbours when the cell lies on a block edge; fixed order (by, then bx)
-template <int T>
+// Row-balanced pass over the heavy blocks: warp w of the grid owns the sorted positions [w * kHeavyBlock,
+// (w + 1) * kHeavyBlock).  A heavy block holds more rows than that, so at most two of them overlap a chunk:
+// one that entered from the left (slot 0, also when it covers the whole chunk) and one that starts inside and
+// leaves to the right (slot 1).  The overlap is accumulated into a private tile exactly as above and stored
+// to slots[chunk][slot]; chunks that only see light blocks return after reading two keys.
+template <int C, int TW>
+__global__ void __launch_bounds__(kTileWarps * kWarp)
+sample_bwd_wtile_heavy_kernel(const float* __restrict__ grad_rows, int64_t n_rows, int reso, const float* __restrict__ xyz,
+                              int64_t stride, const int32_t* __restrict__ perm, const int32_t* __restrict__ keys,
+                              const int32_t* __restrict__ cell_start, int shift, int log2_cells, float* __restrict__ slots) {
+  using Cfg = WTile<C, TW>;
+  extern __shared__ float wt_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tile = wt_smem + warp * Cfg::TILE_FLOATS;
+  int* st_cell = reinterpret_cast<int*>(wt_smem + kTileWarps * Cfg::TILE_FLOATS) + warp * Cfg::STAGE_WORDS;
+  float* st_w = reinterpret_cast<float*>(st_cell + 32 * 4);
+  int* st_row = st_cell + 32 * 8;
+  const int64_t chunk = (int64_t)blockIdx.x * kTileWarps + warp;
+  const int64_t first = chunk * kHeavyBlock;
+  if (first >= n_rows) return;
+  const int last = (int)min(first + (int64_t)kHeavyBlock, n_rows);
+  const int bshift = shift + Cfg::LOG2_BLOCK;  // sort key -> block of this level
+  const int blk_first = __ldg(keys + first) >> bshift, blk_last = __ldg(keys + last - 1) >> bshift;
+#pragma unroll 1
+  for (int slot = 0; slot < 2; ++slot) {
+    const int blk = slot == 0 ? blk_first : blk_last;
+    if (slot == 1 && blk_last == blk_first) break;
+    const int64_t key0 = (int64_t)blk << Cfg::LOG2_BLOCK;  // first cell of the block (level key incl. the image)
+    const int p0 = __ldg(cell_start + (key0 << shift)), p1 = __ldg(cell_start + ((key0 + (1 << Cfg::LOG2_BLOCK)) << shift));
+    if (p1 - p0 <= kHeavyBlock) continue;                       // light: done by its own warp
+    // a heavy first block that STARTS at the chunk start and leaves to the right is a slot-1 block
+    const int use_slot = (p0 < (int)first) ? 0 : 1;
+    const uint32_t code = (uint32_t)(key0 & ((1ll << log2_cells) - 1));
+    const int bx0 = (int)compact1by1(code), by0 = (int)compact1by1(code >> 1);
+    for (int f = lane; f < Cfg::TILE_FLOATS / 4; f += kWarp) reinterpret_cast<float4*>(tile)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    wtile_accumulate<C, TW>(tile, st_cell, st_w, st_row, grad_rows, reso, xyz, stride, perm, max(p0, (int)first), min(p1, last),
+                            bx0, by0, lane);
+    float* dst = slots + (chunk * 2 + use_slot) * (int64_t)Cfg::TILE_FLOATS;
+    for (int f = lane; f < Cfg::TILE_FLOATS / 4; f += kWarp) st4(dst + f * 4, reinterpret_cast<const float4*>(tile)[f]);
+    __syncwarp();
+  }
+}
+
+// one CTA per region: the slot tiles of its heavy blocks are added, in block and then chunk order, into the
+// region tile the light pass left in scratch (a single writer per region tile -> no races, fixed order)
+template <int C, int TW>
+__global__ void __launch_bounds__(kTileWarps * kWarp)
+sample_bwd_wtile_fix_kernel(const int32_t* __restrict__ cell_start, int shift, const float* __restrict__ slots,
+                            float* __restrict__ scratch) {
+  using Cfg = WTile<C, TW>;
+  constexpr int TWH = Cfg::TWH;
+  const int64_t region = blockIdx.x;
+  float* rt = scratch + region * (int64_t)(Cfg::RWH * Cfg::RHH * C);
+  for (int w = 0; w < kTileWarps; ++w) {
+    const int64_t key0 = (region << Cfg::LOG2_REGION) + ((int64_t)w << Cfg::LOG2_BLOCK);
+    const int p0 = __ldg(cell_start + (key0 << shift)), p1 = __ldg(cell_start + ((key0 + (1 << Cfg::LOG2_BLOCK)) << shift));
+    if (p1 - p0 <= kHeavyBlock) continue;  // uniform across the CTA
+    const int bx = (w & 1) | (((w >> 2) & 1) << 1), by = (w >> 1) & 1;
+    const int c0 = p0 / kHeavyBlock, c1 = (p1 - 1) / kHeavyBlock;
+    for (int idx = threadIdx.x; idx < Cfg::TILE_FLOATS / 4; idx += kTileWarps * kWarp) {
+      const int c4i = idx % (C / 4), cellt = idx / (C / 4);
+      const int ly = cellt / TWH, lx = cellt % TWH;
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ck = c0; ck <= c1; ++ck) {
+        const int slot = (ck * kHeavyBlock > p0) ? 0 : 1;
+        const float4 o = ld4(slots + ((int64_t)ck * 2 + slot) * Cfg::TILE_FLOATS + idx * 4);
+        sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+      }
+      float* d = rt + ((by * TW + ly) * Cfg::RWH + bx * TW + lx) * C + c4i * 4;
+      float4 v = *reinterpret_cast<const float4*>(d);
+      v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
+      st4(d, v);
+    }
+    __syncthreads();  // the halos of two heavy blocks of one region overlap
+  }
+}
+
+// grad_plane[b, y, x, :] = sum of the region tiles that cover (x, y): own region plus the left/upper or
+// right/lower neighbours when the cell lies on a region edge; fixed order (region row, then column).
+// Regions are RW x RH cells, enumerated in Morton order of (column, row) with the ROW bit first (the Morton
+// code of a cell continues with a y bit above a region's 2*log2(TW)+3 low bits).
+template <int TW>
 __global__ void __launch_bounds__(256)
-sample_bwd_merge_kernel(const float* __restrict__ scratch, int reso, int C, int log2_cells, int64_t n_cells, int zs,
+sample_bwd_merge_kernel(const float* __restrict__ scratch, int reso, int C, int log2_cells, int64_t n_cells,
                         float* __restrict__ grad_plane) {
-  constexpr int TW = T + 2;
-  constexpr int LOG2_T2 = (T == 8) ? 6 : ((T == 4) ? 4 : ((T == 2) ? 2 : 0));
+  constexpr int RW = 4 * TW, RH = 2 * TW, RWH = RW + 2, RHH = RH + 2;
+  constexpr int LOG2_REGION = (TW == 4) ? 7 : 5;
+  const int c4 = C / 4;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_cells * c4) return;
+  const int64_t cellid = gid / c4;
+  const int ch = (int)(gid - cellid * c4) * 4;
+  const int64_t img = cellid >> log2_cells;
+  const int rem = (int)(cellid - (img << log2_cells));
+  const int y = rem / reso, x = rem - y * reso;
+  const int nx = reso / RW, ny = reso / RH;
+  const int regions_log2 = log2_cells - LOG2_REGION;
+  const int qx_lo = max((x - 1 + RW) / RW - 1, 0), qx_hi = min((x + 1) / RW, nx - 1);
+  const int qy_lo = max((y - 1 + RH) / RH - 1, 0), qy_hi = min((y + 1) / RH, ny - 1);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int qy = qy_lo; qy <= qy_hi; ++qy)
+    for (int qx = qx_lo; qx <= qx_hi; ++qx) {
+      const int lx = x - qx * RW + 1, ly = y - qy * RH + 1;
+      if (lx < 0 || lx >= RWH || ly < 0 || ly >= RHH) continue;
+      const int64_t region = (img << regions_log2) + (part1by1((uint32_t)qy) | (part1by1((uint32_t)qx) << 1));
+      const float4 v = ld4(scratch + (region * (RWH * RHH) + ly * RWH + lx) * (int64_t)C + ch);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  st4(grad_plane + cellid * C + ch, acc);
+}
+
+// ---- G2, coarse levels (many rows per cell): row-balanced nine-partial walk -----------------------------
+// All points of one own cell (cx, cy) contribute to the same 3x3 target cells, with separable weights, so the
+// backward is a SEGMENTED SUM of weighted rows with nine outputs per cell.  As in t2h_segment.cu the work is
+// split over the rows: every group of LPR lanes walks kRows9 consecutive sorted positions of one channel
+// group (<= 128 channels: nine float4 accumulators per lane), finishes the cells that lie inside its chunk
+// (-> nine[cell][9][C]) and leaves the partials of the cells that cross a chunk border in scratch slots;
+// sample_bwd_nine_fix_kernel adds those in chunk order and zero-fills empty cells; sample_bwd_nine_gather_kernel
+// assembles grad_plane[t] = sum_d nine[t - d][d].  A facade with 20 000 points in one cell is walked by ~80
+// independent warps; no atomics, fixed summation order.
+template <int LPR> struct Rows9 { static constexpr int ROWS = (LPR == 32) ? 256 : 128; };
+
+template <int LPR>
+__global__ void __launch_bounds__(kTileWarps * kWarp)
+sample_bwd_nine_rows_kernel(const float* __restrict__ grad_rows, int64_t n_rows, int C, int reso,
+                            const float* __restrict__ xyz, int64_t stride, const int32_t* __restrict__ perm,
+                            const int32_t* __restrict__ keys, int shift, int morton, int log2_cells,
+                            float* __restrict__ nine, float* __restrict__ slots) {
+  constexpr int RPI = 32 / LPR, ROWS = Rows9<LPR>::ROWS, U = 8;
+  static_assert(LPR % U == 0, "a batch of LPR rows is consumed U rows at a time");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int64_t chunk = ((int64_t)blockIdx.x * kTileWarps + warp) * RPI + sub;
+  // every lane group walks its own chunk; groups past the end idle through the loop (the shuffles below are
+  // confined to a group but named by the full-warp mask)
+  const int64_t first = min(chunk * ROWS, n_rows);
+  const int64_t last = min(first + (int64_t)ROWS, n_rows);
+  const bool live = first < last;
+  const int ch0 = blockIdx.y * (LPR * 4) + l * 4;  // this lane's four channels
+
+  auto key_of = [&](int64_t i) { return __ldg(keys + i) >> shift; };
+  int cur = live ? key_of(first) : 0;
+  const bool cont_in = live && first > 0 && key_of(first - 1) == cur;
+  bool is_first = true;
+  int cx = 0, cy = 0;
+  auto decode = [&](int key) {
+    const uint32_t code = (uint32_t)key & ((1u << log2_cells) - 1u);
+    cell_decode(code, reso, morton, cx, cy);
+  };
+  decode(cur);
+  float4 acc[9];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto flush = [&](int slot) {
+    float* dst = slot < 0 ? nine + (int64_t)cur * 9 * C : slots + (chunk * 2 + slot) * 9 * (int64_t)C;
+#pragma unroll
+    for (int d = 0; d < 9; ++d) st4(dst + d * C + ch0, acc[d]);
+  };
+  auto fma4 = [](float4& a, float w, const float4& g) { a.x += w * g.x; a.y += w * g.y; a.z += w * g.z; a.w += w * g.w; };
+
+  // batches of LPR rows: lane l of the group resolves key, row index, tap origin and the four tap weights of
+  // row base + l ONCE; the group then consumes the batch row by row through group-wide shuffles
+  for (int64_t base = first; __any_sync(0xffffffffu, base < last); base += LPR) {
+    const int nb = (int)max((int64_t)0, min((int64_t)LPR, last - base));
+    int my_key = 0, my_x0 = 0, my_y0 = 0;
+    int64_t my_row = 0;
+    float w_nw = 0.f, w_ne = 0.f, w_sw = 0.f, w_se = 0.f;
+    if (l < nb) {
+      const int64_t p = base + l;
+      my_key = key_of(p);
+      my_row = perm ? (int64_t)__ldg(perm + p) : p;
+      const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + p * stride));
+      const Taps t = make_taps(pxy.x, pxy.y, reso);
+      const float wx1 = (t.x0 + 1 < reso) ? t.wx1 : 0.f, wy1 = (t.y0 + 1 < reso) ? t.wy1 : 0.f;
+      my_x0 = t.x0; my_y0 = t.y0;
+      w_nw = __fmul_rn(t.wx0, t.wy0); w_ne = __fmul_rn(wx1, t.wy0);
+      w_sw = __fmul_rn(t.wx0, wy1);   w_se = __fmul_rn(wx1, wy1);
+    }
+    for (int j0 = 0; j0 < LPR; j0 += U) {
+      float4 gq[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t row = __shfl_sync(0xffffffffu, my_row, j0 + u, LPR);
+        if (j0 + u < nb) gq[u] = ld4_stream(grad_rows + row * C + ch0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u;
+        const int k = __shfl_sync(0xffffffffu, my_key, j, LPR);
+        const int x0 = __shfl_sync(0xffffffffu, my_x0, j, LPR), y0 = __shfl_sync(0xffffffffu, my_y0, j, LPR);
+        const float a_nw = __shfl_sync(0xffffffffu, w_nw, j, LPR), a_ne = __shfl_sync(0xffffffffu, w_ne, j, LPR);
+        const float a_sw = __shfl_sync(0xffffffffu, w_sw, j, LPR), a_se = __shfl_sync(0xffffffffu, w_se, j, LPR);
+        if (j < nb) {
+          if (k != cur) {
+            flush(is_first && cont_in ? 0 : -1);
+            is_first = false;
+            cur = k;
+            decode(cur);
+#pragma unroll
+            for (int d = 0; d < 9; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          // the tap origin is the own cell or the one before it, per axis: four cases, four live partials each
+          const bool left = x0 < cx, up = y0 < cy;
+          if (up) {
+            if (left) { fma4(acc[0], a_nw, gq[u]); fma4(acc[1], a_ne, gq[u]); fma4(acc[3], a_sw, gq[u]); fma4(acc[4], a_se, gq[u]); }
+            else      { fma4(acc[1], a_nw, gq[u]); fma4(acc[2], a_ne, gq[u]); fma4(acc[4], a_sw, gq[u]); fma4(acc[5], a_se, gq[u]); }
+          } else {
+            if (left) { fma4(acc[3], a_nw, gq[u]); fma4(acc[4], a_ne, gq[u]); fma4(acc[6], a_sw, gq[u]); fma4(acc[7], a_se, gq[u]); }
+            else      { fma4(acc[4], a_nw, gq[u]); fma4(acc[5], a_ne, gq[u]); fma4(acc[7], a_sw, gq[u]); fma4(acc[8], a_se, gq[u]); }
+          }
+        }
+      }
+    }
+  }
+  if (!live) return;
+  const bool cont_out = last < n_rows && key_of(last) == cur;
+  flush(is_first && cont_in ? 0 : (cont_out ? 1 : -1));
+}
+
+// one warp per cell: empty -> zero partials; crossing a chunk border -> sum of the chunk partials in chunk order
+template <int ROWS>
+__global__ void __launch_bounds__(kTileWarps * kWarp)
+sample_bwd_nine_fix_kernel(const int32_t* __restrict__ cell_start, int64_t n_seg, int shift, int C,
+                           const float* __restrict__ slots, float* __restrict__ nine) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * kTileWarps + (threadIdx.x >> 5);
+  if (seg >= n_seg) return;
+  const int beg = __ldg(cell_start + (seg << shift)), end = __ldg(cell_start + ((seg + 1) << shift));
+  const int c0 = beg / ROWS, c1 = (end - 1) / ROWS;
+  if (beg < end && c0 == c1) return;
+  float* dst = nine + seg * 9 * (int64_t)C;
+  for (int e = lane; e < 9 * C / 4; e += kWarp) {
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beg < end)
+      for (int ck = c0; ck <= c1; ++ck) {
+        const int slot = (ck * ROWS > beg) ? 0 : 1;
+        const float4 o = ld4(slots + ((int64_t)ck * 2 + slot) * 9 * C + e * 4);
+        sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+      }
+    st4(dst + e * 4, sum);
+  }
+}
+
+// grad_plane[b, ty, tx, :] = sum over (dy, dx) of nine[cell (tx - dx, ty - dy)][(dy + 1) * 3 + dx + 1]
+__global__ void __launch_bounds__(256)
+sample_bwd_nine_gather_kernel(const float* __restrict__ nine, int reso, int C, int morton, int log2_cells, int64_t n_cells,
+                              float* __restrict__ grad_plane) {
   const int c4 = C / 4;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_cells * c4) return;
@@ -522,22 +613,18 @@ sample_bwd_merge_kernel(const float* __restrict__ scratch, int reso, int C, int 
   const int64_t cells = (int64_t)reso * reso;
   const int64_t img = cellid / cells;
   const int rem = (int)(cellid - img * cells);
-  const int y = rem / reso, x = rem - y * reso;
-  const int nblk = reso / T;
-  const int blocks_log2 = log2_cells - LOG2_T2;
-  const int bx_lo = max((x - 1 + T) / T - 1, 0) , bx_hi = min((x + 1) / T, nblk - 1);
-  const int by_lo = max((y - 1 + T) / T - 1, 0) , by_hi = min((y + 1) / T, nblk - 1);
+  const int ty = rem / reso, tx = rem - ty * reso;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int64_t n_blocks = n_cells >> LOG2_T2;
-  for (int z = 0; z < zs; ++z)
-    for (int by = by_lo; by <= by_hi; ++by)
-      for (int bx = bx_lo; bx <= bx_hi; ++bx) {
-        const int lx = x - bx * T + 1, ly = y - by * T + 1;
-        if (lx < 0 || lx >= TW || ly < 0 || ly >= TW) continue;
-        const int64_t blk = z * n_blocks + (img << blocks_log2) + (part1by1((uint32_t)bx) | (part1by1((uint32_t)by) << 1));
-        const float4 v = ld4(scratch + (blk * (TW * TW) + ly * TW + lx) * (int64_t)C + ch);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ox = tx - dx, oy = ty - dy;
+      if (ox < 0 || ox >= reso || oy < 0 || oy >= reso) continue;
+      const int64_t key = img * cells + cell_code((uint32_t)ox, (uint32_t)oy, reso, morton);
+      const float4 v = ld4(nine + (key * 9 + (dy + 1) * 3 + (dx + 1)) * (int64_t)C + ch);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   st4(grad_plane + cellid * C + ch, acc);
 }
 
@@ -652,145 +739,121 @@ extern "C" int t2h_bilinear_sample_fwd(const float* plane, int reso, int C, cons
   return T2H_OK;
 }
 
-// Block edge T for the tiled backward: the largest of {8, 4, 2, 1} that keeps ~<= 512 points per block
-// (coarse levels hold hundreds of points per cell; small blocks keep thousands of CTAs in flight)
-static inline int tiled_T(int reso, int C, int morton, int64_t n_points, int64_t n_seg) {
-  if (!morton || C < 32 || (C & (C - 1)) || C > 1024 || n_seg <= 0) return 0;   // C in {32, 64, ..., 1024}
-  const int64_t avg = n_points / n_seg > 0 ? n_points / n_seg : 1;
-  int T = C <= 512 ? 8 : 4;
-  while (T > 1 && ((int64_t)T * T * avg > 512 || T > reso)) T >>= 1;
-  return T;
-}
-
-extern "C" size_t t2h_bilinear_sample_bwd_workspace_bytes(int reso, int C, int64_t n_seg, int morton) {
-  if (!morton || n_seg <= 0) return 256;
-  // haloed block tiles: T = 1 blocks (C >= 512) carry a 3 x 3 tile per cell and up to 8 row splits;
-  // T >= 2 blocks at most 4 tile cells per cell
-  const size_t per_cell = C >= 512 ? 9 * 8 : (C >= 128 ? 4 * 8 : 36 * 8 / 16);
-  return (size_t)n_seg * per_cell * C * sizeof(float) + 256;
-}
-
-static inline int cell_zsplit(int64_t avg, int slices) {
-  int zs = 1;
-  while (zs < 8 && avg >= (int64_t)48 * slices * zs) zs *= 2;
-  return zs;
-}
-
-template <int C, int T>
-static int launch_cell(const float* grad_rows, int reso, const float* xyz, int64_t stride, const int32_t* perm,
-                       const int32_t* cell_start, int64_t n_points, int64_t n_seg, int shift, int log2_cells,
-                       float* scratch, float* grad_plane, cudaStream_t s) {
-  using Cfg = CellCfg<C, T>;
-  auto kern = sample_bwd_cell_kernel<C, T>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return T2H_ERR_CUDA;
-    }
-    configured = true;
-  }
-  // ~32 rows per warp on average: row slices inside the CTA first (bounded by the warps of a channel group),
-  // then ZS CTAs per block
+// Which G2 kernel serves a level.  Warp-private tiles need Morton keys, C in {32, 64, 128} and few rows per
+// cell (a warp walks a whole block of cells); the nine-partial walk needs Morton keys and C = 32, 64 or a
+// multiple of 128; everything else (row-major keys, C < 32) takes the 3x3 gather.
+enum { G2_GATHER = 0, G2_WTILE = 1, G2_NINE = 2 };
+static inline int g2_mode(int reso, int C, int morton, int64_t n_points, int64_t n_seg) {
+  if (!morton || n_seg <= 0) return G2_GATHER;
+  const bool nine_ok = C == 32 || C == 64 || (C % 128 == 0 && C <= 1024);
   const int64_t avg = n_points / n_seg;
-  int slices = 1;
-  while (slices < Cfg::RF && avg >= 48 * slices) slices *= 2;
-  const int zs = cell_zsplit(avg, slices);
-  const int64_t blocks = n_seg / (T * T);
-  kern<<<dim3((unsigned)blocks, (unsigned)zs), kTileWarps * kWarp, Cfg::SMEM, s>>>(grad_rows, reso, xyz, stride, perm, cell_start, shift, log2_cells, slices, scratch);
+  const int tw = C == 128 ? 2 : 4;
+  if ((C == 32 || C == 64 || C == 128) && avg < 32 && reso >= 4 * tw) return G2_WTILE;
+  return nine_ok ? G2_NINE : G2_GATHER;
+}
+static inline int nine_rows(int C) { return C >= 128 ? 256 : 128; }
+static inline size_t align256s(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" size_t t2h_bilinear_sample_bwd_workspace_bytes(int reso, int C, int64_t n_points, int64_t n_seg, int morton) {
+  switch (g2_mode(reso, C, morton, n_points, n_seg)) {
+    case G2_WTILE: {
+      const int tw = C == 128 ? 2 : 4;
+      const int64_t regions = n_seg / (8 * tw * tw);
+      const int64_t chunks = (n_points + kHeavyBlock - 1) / kHeavyBlock;
+      return align256s((size_t)regions * (4 * tw + 2) * (2 * tw + 2) * C * sizeof(float)) +
+             (size_t)chunks * 2 * (tw + 2) * (tw + 2) * C * sizeof(float) + 256;
+    }
+    case G2_NINE: {
+      const int64_t chunks = (n_points + nine_rows(C) - 1) / nine_rows(C);
+      return align256s((size_t)n_seg * 9 * C * sizeof(float)) + (size_t)chunks * 2 * 9 * C * sizeof(float) + 256;
+    }
+    default: return 256;
+  }
+}
+
+template <int C, int TW>
+static int launch_wtile(const float* grad_rows, int64_t n_points, int reso, const float* xyz, int64_t stride,
+                        const int32_t* perm, const int32_t* keys, const int32_t* cell_start, int64_t n_seg, int shift,
+                        int log2_cells, float* scratch, float* grad_plane, cudaStream_t s) {
+  using Cfg = WTile<C, TW>;
+  auto kern = sample_bwd_wtile_kernel<C, TW>;
+  auto heavy = sample_bwd_wtile_heavy_kernel<C, TW>;
+  // per device and idempotent; set on every launch so that the entry point keeps no state
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return T2H_ERR_CUDA;
+  }
+  const int64_t regions = n_seg >> Cfg::LOG2_REGION;
+  float* slots = (float*)((char*)scratch + align256s((size_t)regions * Cfg::RWH * Cfg::RHH * C * sizeof(float)));
+  kern<<<(unsigned)regions, kTileWarps * kWarp, Cfg::SMEM, s>>>(grad_rows, reso, xyz, stride, perm, cell_start, shift, log2_cells, scratch);
   T2H_CHECK_LAUNCH();
+  const int64_t chunks = (n_points + kHeavyBlock - 1) / kHeavyBlock;
+  if (chunks > 0) {
+    heavy<<<(unsigned)((chunks + kTileWarps - 1) / kTileWarps), kTileWarps * kWarp, Cfg::SMEM, s>>>(
+        grad_rows, n_points, reso, xyz, stride, perm, keys, cell_start, shift, log2_cells, slots);
+    T2H_CHECK_LAUNCH();
+    sample_bwd_wtile_fix_kernel<C, TW><<<(unsigned)regions, kTileWarps * kWarp, 0, s>>>(cell_start, shift, slots, scratch);
+    T2H_CHECK_LAUNCH();
+  }
   const int64_t threads = n_seg * (C / 4);
-  sample_bwd_merge_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(scratch, reso, C, log2_cells, n_seg, zs, grad_plane);
+  sample_bwd_merge_kernel<TW><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(scratch, reso, C, log2_cells, n_seg, grad_plane);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
 
-template <int C, int T>
-static int launch_tiled(const float* grad_rows, int reso, const float* xyz, int64_t stride, const int32_t* perm,
-                        const int32_t* cell_start, int64_t n_seg, int shift, int log2_cells, float* scratch,
-                        float* grad_plane, cudaStream_t s) {
-  using Cfg = TileCfg<C, T>;
-  auto kern = sample_bwd_tiled_kernel<C, T>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return T2H_ERR_CUDA;
-    }
-    configured = true;
+template <int LPR>
+static int launch_nine(const float* grad_rows, int64_t n_points, int reso, int C, const float* xyz, int64_t stride,
+                       const int32_t* perm, const int32_t* keys, const int32_t* cell_start, int64_t n_seg, int shift,
+                       int morton, int log2_cells, float* nine, float* slots, float* grad_plane, cudaStream_t s) {
+  constexpr int ROWS = Rows9<LPR>::ROWS, RPI = 32 / LPR;
+  const int64_t chunks = (n_points + ROWS - 1) / ROWS;
+  if (chunks > 0) {
+    const int64_t warps = (chunks + RPI - 1) / RPI;
+    const dim3 grid((unsigned)((warps + kTileWarps - 1) / kTileWarps), (unsigned)(C / (LPR * 4)));
+    sample_bwd_nine_rows_kernel<LPR><<<grid, kTileWarps * kWarp, 0, s>>>(grad_rows, n_points, C, reso, xyz, stride, perm, keys,
+                                                                        shift, morton, log2_cells, nine, slots);
+    T2H_CHECK_LAUNCH();
   }
-  const int64_t blocks = n_seg / (T * T);
-  kern<<<(unsigned)blocks, kTileWarps * kWarp, Cfg::SMEM, s>>>(grad_rows, reso, xyz, stride, perm, cell_start, shift, log2_cells, scratch);
+  sample_bwd_nine_fix_kernel<ROWS><<<(unsigned)((n_seg + kTileWarps - 1) / kTileWarps), kTileWarps * kWarp, 0, s>>>(
+      cell_start, n_seg, shift, C, slots, nine);
   T2H_CHECK_LAUNCH();
   const int64_t threads = n_seg * (C / 4);
-  sample_bwd_merge_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(scratch, reso, C, log2_cells, n_seg, 1, grad_plane);
+  sample_bwd_nine_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(nine, reso, C, morton, log2_cells, n_seg, grad_plane);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
 
 extern "C" int t2h_bilinear_sample_bwd(const float* grad_rows, int64_t n_points, int reso, int C,
                                        const float* xyz_sorted, int64_t point_stride, const int32_t* perm,
-                                       const int32_t* cell_start, int64_t n_seg, int shift, int morton,
-                                       void* workspace, size_t workspace_bytes, float* grad_plane,
+                                       const int32_t* row_keys, const int32_t* cell_start, int64_t n_seg, int shift,
+                                       int morton, void* workspace, size_t workspace_bytes, float* grad_plane,
                                        t2h_stream_t stream) {
-  if (!grad_rows || !xyz_sorted || !cell_start || !grad_plane || reso <= 0 || point_stride < 2 || (point_stride & 1) ||
-      n_points < 0 || n_seg < 0 ||
+  if (!cell_start || !grad_plane || reso <= 0 || point_stride < 2 || (point_stride & 1) || n_points < 0 || n_seg < 0 ||
+      (n_points > 0 && (!grad_rows || !xyz_sorted)) || n_points > INT32_MAX ||
       shift < 0 || (shift & 1) || (shift && !morton) || n_seg % ((int64_t)reso * reso))
     return T2H_ERR_INVALID_ARGUMENT;
   if (morton && (reso & (reso - 1))) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  {
-    const int T = tiled_T(reso, C, morton, n_points, n_seg);
-    static const int force_gather = []() { const char* e = getenv("T2H_SAMPLE_BWD_GATHER"); return e ? atoi(e) : 0; }();
-    static const int mode = []() { const char* e = getenv("T2H_SAMPLE_BWD_MODE"); return e ? atoi(e) : 0; }();  // ablation
-    if (morton && workspace && !force_gather && mode != 1 && C >= 32 && !(C & (C - 1)) && C <= 1024) {
-      // cell-parallel register accumulation; block edge T with T*T*C <= 1024 floats x 9 partials of staging
-      if (workspace_bytes < t2h_bilinear_sample_bwd_workspace_bytes(reso, C, n_seg, morton)) return T2H_ERR_WORKSPACE_TOO_SMALL;
-      int l2c = 0;
-      while ((1 << l2c) < reso) ++l2c;
-      l2c *= 2;
-      cudaStream_t st = (cudaStream_t)stream;
-      float* scr = (float*)workspace;
-#define T2H_CELL(CC, TT) \
-  if (reso >= TT) return launch_cell<CC, TT>(grad_rows, reso, xyz_sorted, point_stride, perm, cell_start, n_points, n_seg, shift, l2c, scr, grad_plane, st)
-      switch (C) {
-        case 32: T2H_CELL(32, 4); break;
-        case 64: T2H_CELL(64, 4); break;
-        case 128: T2H_CELL(128, 2); break;
-        case 256: T2H_CELL(256, 2); break;
-        case 512: T2H_CELL(512, 1); break;
-        case 1024: T2H_CELL(1024, 1); break;
-        default: break;
-      }
-#undef T2H_CELL
-    }
-    // scatter tile with per-point shared-memory updates (kept for ablation: T2H_SAMPLE_BWD_MODE=1)
-    if (T == 8 && workspace && !force_gather && mode == 1) {
-      if (workspace_bytes < t2h_bilinear_sample_bwd_workspace_bytes(reso, C, n_seg, morton)) return T2H_ERR_WORKSPACE_TOO_SMALL;
-      int l2c = 0;
-      while ((1 << l2c) < reso) ++l2c;
-      l2c *= 2;
-      cudaStream_t st = (cudaStream_t)stream;
-      float* scr = (float*)workspace;
-#define T2H_TILED(CC, TT) return launch_tiled<CC, TT>(grad_rows, reso, xyz_sorted, point_stride, perm, cell_start, n_seg, shift, l2c, scr, grad_plane, st)
-#define T2H_TILED_C(CC)                                             \
-  case CC:                                                          \
-    if (T == 8) { if constexpr (CC <= 512) T2H_TILED(CC, 8); }     \
-    if (T == 4) T2H_TILED(CC, 4);                                   \
-    if (T == 2) T2H_TILED(CC, 2);                                   \
-    T2H_TILED(CC, 1);
-      switch (C) {
-        T2H_TILED_C(32)
-        T2H_TILED_C(64)
-        T2H_TILED_C(128)
-        T2H_TILED_C(256)
-        T2H_TILED_C(512)
-        T2H_TILED_C(1024)
-        default: break;
-      }
-#undef T2H_TILED_C
-#undef T2H_TILED
-    }
+  cudaStream_t s = (cudaStream_t)stream;
+  int log2_cells = 0;
+  while ((1 << log2_cells) < reso) ++log2_cells;
+  log2_cells *= 2;
+  const int mode = (workspace && row_keys) ? g2_mode(reso, C, morton, n_points, n_seg) : G2_GATHER;
+  if (mode != G2_GATHER && workspace_bytes < t2h_bilinear_sample_bwd_workspace_bytes(reso, C, n_points, n_seg, morton))
+    return T2H_ERR_WORKSPACE_TOO_SMALL;
+  if (mode == G2_WTILE) {
+    float* scr = (float*)workspace;
+    if (C == 32) return launch_wtile<32, 4>(grad_rows, n_points, reso, xyz_sorted, point_stride, perm, row_keys, cell_start, n_seg, shift, log2_cells, scr, grad_plane, s);
+    if (C == 64) return launch_wtile<64, 4>(grad_rows, n_points, reso, xyz_sorted, point_stride, perm, row_keys, cell_start, n_seg, shift, log2_cells, scr, grad_plane, s);
+    return launch_wtile<128, 2>(grad_rows, n_points, reso, xyz_sorted, point_stride, perm, row_keys, cell_start, n_seg, shift, log2_cells, scr, grad_plane, s);
+  }
+  if (mode == G2_NINE) {
+    float* nine = (float*)workspace;
+    float* slots = (float*)((char*)workspace + align256s((size_t)n_seg * 9 * C * sizeof(float)));
+    if (C == 32) return launch_nine<8>(grad_rows, n_points, reso, C, xyz_sorted, point_stride, perm, row_keys, cell_start, n_seg, shift, morton, log2_cells, nine, slots, grad_plane, s);
+    if (C == 64) return launch_nine<16>(grad_rows, n_points, reso, C, xyz_sorted, point_stride, perm, row_keys, cell_start, n_seg, shift, morton, log2_cells, nine, slots, grad_plane, s);
+    return launch_nine<32>(grad_rows, n_points, reso, C, xyz_sorted, point_stride, perm, row_keys, cell_start, n_seg, shift, morton, log2_cells, nine, slots, grad_plane, s);
   }
   // gather fallback (row-major keys, odd channel counts): ~9 neighbour cells are scanned per plane cell;
   // split the scan over several warps on coarse levels
@@ -798,10 +861,6 @@ extern "C" int t2h_bilinear_sample_bwd(const float* grad_rows, int64_t n_points,
   int wps = 1;
   while (wps < kSampleWarps && avg >= 4 * wps) wps *= 2;
   const unsigned blocks = (unsigned)((n_seg * wps + kSampleWarps - 1) / kSampleWarps);
-  cudaStream_t s = (cudaStream_t)stream;
-  int log2_cells = 0;
-  while ((1 << log2_cells) < reso) ++log2_cells;
-  log2_cells *= 2;
 #define T2H_SBWD(W) sample_bwd_kernel<RS, W><<<blocks, kSampleWarps * kWarp, 0, s>>>( \
       grad_rows, reso, xyz_sorted, point_stride, perm, cell_start, n_seg, shift, morton, log2_cells, grad_plane)
   T2H_DISPATCH_ROWSHAPE(C, {

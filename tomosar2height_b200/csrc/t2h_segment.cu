@@ -1,21 +1,31 @@
-// Deterministic segmented reductions over cell-sorted points (S1 / S2 of SURVEY §2.2).
+// Deterministic, ROW-BALANCED segmented reductions over cell-sorted points (S1 / S2 of SURVEY §2.2).
 //
 // Replace torch_scatter.scatter_max + gather (pointnet.py:92-99) and torch_scatter.scatter_mean
 // (pointnet.py:101-111, alto.py:76-88, alto.py:187-197) and their autograd backwards.
-// One warp owns one cell (segment); a row of C floats is spread over LPR lanes as float4s, so a
-// warp consumes RPI = 32/LPR rows per iteration with fully coalesced 16-byte accesses.  No
-// atomics: the order of every floating-point sum is fixed by the (stable) sort.
+//
+// Work is split over the ROWS, not over the cells: every group of LPR lanes (a row of C floats = LPR
+// lanes x CH float4) walks its own chunk of kChunk consecutive sorted positions, so a facade cell with
+// thousands of points costs exactly as much per row as a cell with one.  A cell that lies completely
+// inside a chunk is finished by its walker and written straight to the plane.  A cell that crosses a
+// chunk border leaves one partial per chunk in a scratch slot (slot 0: the cell entered the chunk from
+// the left, slot 1: it starts here and leaves to the right); a second "fix-up" launch visits every cell,
+// adds the partials of the crossing ones in chunk order and zero-fills the empty ones.  No atomics: the
+// order of every floating-point sum is fixed by the (stable) sort and the chunk grid.
+// The backward passes and the gather-back are pure row-parallel maps (one plane row looked up per point).
 #include "t2h_common.cuh"
 
 namespace t2h {
 
-constexpr int kSegWarps = 8;  // warps (= segments) per CTA
+constexpr int kSegWarps = 8;  // warps per CTA
+constexpr int kChunk = 32;    // sorted positions per walker (sub-group) chunk
 
 struct SegGeom {
   const int32_t* perm;        // sorted position -> row (nullptr: identity)
   const int32_t* tie;         // sorted position -> original point index, for argmax ties when the
                               // sorted order inside a segment is not the point order (nullptr: it is)
+  const int32_t* keys;        // sorted position -> finest-level sort key
   const int32_t* cell_start;  // finest-level table
+  int64_t n_rows;
   int64_t n_seg;
   int shift;   // 2k for level r = R >> k
   int morton;
@@ -32,30 +42,130 @@ __device__ __forceinline__ int64_t plane_row(const SegGeom& g, int64_t seg) {
   return (b << g.log2_cells) + (int64_t)iy * g.reso + ix;
 }
 
-// Cells with more than kHeavyMax rows (a facade in a clustered tile holds thousands of points) are not walked by
-// their one warp -- that warp would run long after the rest of the grid has finished -- but deferred and
-// processed by all eight warps of the CTA, partial results combined through shared memory.  The (value,
-// original point index) order that decides the argmax is total, so the combination order does not matter.
-constexpr int kHeavyMax = 128;
+__device__ __forceinline__ int level_key(const SegGeom& g, int64_t i) { return __ldg(g.keys + i) >> g.shift; }
 
+// ---- S2 forward: segment sum / mean -----------------------------------------------------------------
+// scratch: [n_chunks][2][C] floats (raw sums of the border cells of every chunk)
 template <class RS>
 __global__ void __launch_bounds__(kSegWarps * kWarp)
-seg_max_fwd_kernel(const float* __restrict__ rows, SegGeom g, float* __restrict__ pooled,
-                   float* __restrict__ plane, int32_t* __restrict__ arg) {
+seg_reduce_rows_kernel(const float* __restrict__ rows, SegGeom g, int mean, float* __restrict__ plane,
+                       float* __restrict__ scratch) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  constexpr bool DEFER = C <= 256;  // 64 * C bytes of shared memory for the partial results
-  __shared__ float hv_val[DEFER ? kSegWarps * C : 1];
-  __shared__ int hv_pos[DEFER ? kSegWarps * C : 1];
-  __shared__ int hv_beg[kSegWarps], hv_len[kSegWarps];
+  constexpr int U = CH >= 4 ? 2 : 4;  // rows in flight per lane
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + warp;
-  const bool valid = seg < g.n_seg;
   const int sub = lane / LPR, l = lane % LPR;
-  int beg = 0, end = 0;
-  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
-  const bool heavy = DEFER && valid && end - beg > kHeavyMax;
-  if (DEFER && lane == 0) { hv_len[warp] = heavy ? end - beg : 0; hv_beg[warp] = beg; }
+  const int64_t chunk = ((int64_t)blockIdx.x * kSegWarps + warp) * RPI + sub;
+  const int64_t first = chunk * kChunk;
+  if (first >= g.n_rows) return;
+  const int64_t last = min(first + (int64_t)kChunk, g.n_rows);
 
+  int cur = level_key(g, first);
+  const bool cont_in = first > 0 && level_key(g, first - 1) == cur;  // the first cell entered from the left
+  bool is_first = true;
+  int cnt = 0;
+  float4 acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto flush = [&](int slot) {  // slot < 0: the cell is complete -> plane
+    if (slot < 0) {
+      const float inv = mean ? __fdiv_rn(1.0f, (float)cnt) : 1.0f;  // one division, <= 1 ulp from sum / count
+      float* dst = plane + plane_row(g, cur) * C + l * 4;
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        st4(dst + c * LPR * 4, make_float4(acc[c].x * inv, acc[c].y * inv, acc[c].z * inv, acc[c].w * inv));
+    } else {
+      float* dst = scratch + (chunk * 2 + slot) * C + l * 4;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) st4(dst + c * LPR * 4, acc[c]);
+    }
+  };
+
+  for (int64_t i = first; i < last; i += U) {
+    int k[U];
+    float4 v[U][CH];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = min(i + u, last - 1);
+      k[u] = level_key(g, p);
+      const int64_t row = g.perm ? (int64_t)__ldg(g.perm + p) : p;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) v[u][c] = ld4(rows + row * C + (c * LPR + l) * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u >= last) break;
+      if (k[u] != cur) {
+        flush(is_first && cont_in ? 0 : -1);
+        is_first = false;
+        cur = k[u];
+        cnt = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ++cnt;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        acc[c].x += v[u][c].x; acc[c].y += v[u][c].y; acc[c].z += v[u][c].z; acc[c].w += v[u][c].w;
+      }
+    }
+  }
+  const bool cont_out = last < g.n_rows && level_key(g, last) == cur;
+  flush(is_first && cont_in ? 0 : (cont_out ? 1 : -1));
+}
+
+// every cell: empty -> zero row; crossing a chunk border -> sum of its chunk partials in chunk order
+template <class RS>
+__global__ void __launch_bounds__(kSegWarps * kWarp)
+seg_reduce_fix_kernel(SegGeom g, int mean, const float* __restrict__ scratch, float* __restrict__ plane) {
+  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int64_t seg = ((int64_t)blockIdx.x * kSegWarps + warp) * RPI + sub;
+  if (seg >= g.n_seg) return;
+  const int beg = __ldg(g.cell_start + (seg << g.shift)), end = __ldg(g.cell_start + ((seg + 1) << g.shift));
+  const int c0 = beg / kChunk, c1 = (end - 1) / kChunk;
+  if (beg < end && c0 == c1) return;  // finished by its walker
+  float4 acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (beg < end) {
+    for (int ck = c0; ck <= c1; ++ck) {
+      const int slot = (ck * kChunk > beg) ? 0 : 1;
+      const float* src = scratch + ((int64_t)ck * 2 + slot) * C + l * 4;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float4 o = ld4(src + c * LPR * 4);
+        acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
+      }
+    }
+    const float inv = mean ? __fdiv_rn(1.0f, (float)(end - beg)) : 1.0f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { acc[c].x *= inv; acc[c].y *= inv; acc[c].z *= inv; acc[c].w *= inv; }
+  }
+  float* dst = plane + plane_row(g, seg) * C + l * 4;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) st4(dst + c * LPR * 4, acc[c]);
+}
+
+// ---- S1 forward: segment max + argmax ---------------------------------------------------------------
+// scratch: values [n_chunks][2][C] floats, then positions [n_chunks][2][C] int32 (sorted positions)
+template <class RS>
+__global__ void __launch_bounds__(kSegWarps * kWarp)
+seg_max_rows_kernel(const float* __restrict__ rows, SegGeom g, float* __restrict__ plane, int32_t* __restrict__ arg,
+                    float* __restrict__ s_val, int32_t* __restrict__ s_pos) {
+  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
+  constexpr int U = CH >= 4 ? 2 : 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int64_t chunk = ((int64_t)blockIdx.x * kSegWarps + warp) * RPI + sub;
+  const int64_t first = chunk * kChunk;
+  if (first >= g.n_rows) return;
+  const int64_t last = min(first + (int64_t)kChunk, g.n_rows);
+
+  int cur = level_key(g, first);
+  const bool cont_in = first > 0 && level_key(g, first - 1) == cur;
+  bool is_first = true;
   float best[CH][4];
   int bpos[CH][4];
   auto reset = [&]() {
@@ -64,402 +174,189 @@ seg_max_fwd_kernel(const float* __restrict__ rows, SegGeom g, float* __restrict_
 #pragma unroll
       for (int k = 0; k < 4; ++k) { best[c][k] = -FLT_MAX; bpos[c][k] = INT32_MAX; }
   };
-  // does candidate (ov, op) beat (bv, bp)?  larger value; equal values -> smaller original point index
-  // (= smaller sorted position when the sorted order inside the segment is the point order)
-  auto beats = [&](float ov, int op, float bv, int bp) -> bool {
-    if (ov > bv) return true;
-    if (ov == bv && op != INT32_MAX && bp != INT32_MAX) return g.tie ? (g.tie[op] < g.tie[bp]) : (op < bp);
-    return false;
-  };
-  auto scan = [&](int first, int last, int step) {
-    for (int i = first; i < last; i += step) {
-      const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
-      const float* src = rows + row * C + l * 4;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        float4 v = ld4(src + c * LPR * 4);
-        const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // strict >: the first row wins ties (rows of one fine cell are in point order); inside a
-          // coarser segment equal values are resolved by the original point index
-          bool take = e[k] > best[c][k];
-          if (g.tie && e[k] == best[c][k] && bpos[c][k] != INT32_MAX) take = g.tie[i] < g.tie[bpos[c][k]];
-          if (take) { best[c][k] = e[k]; bpos[c][k] = i; }
-        }
-      }
-    }
-  };
-  auto merge_subs = [&]() {  // the RPI sub-rows of the warp
-#pragma unroll
-    for (int off = LPR; off < kWarp; off <<= 1) {
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float ov = __shfl_xor_sync(0xffffffffu, best[c][k], off);
-          const int op = __shfl_xor_sync(0xffffffffu, bpos[c][k], off);
-          if (beats(ov, op, best[c][k], bpos[c][k])) { best[c][k] = ov; bpos[c][k] = op; }
-        }
-    }
-  };
-  // plane / arg of segment `sg` (written by the sub-row 0 lanes when `writer`); best becomes the pooled value
-  auto emit = [&](int64_t sg, bool empty, bool writer) {
-    const int64_t prow = plane_row(g, sg);
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      float4 v;
-      int4 a;
-      int* ap = &a.x;
-      float* vp = &v.x;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool none = empty || bpos[c][k] == INT32_MAX;
-        vp[k] = none ? 0.0f : best[c][k];
-        ap[k] = none ? -1 : (g.perm ? g.perm[bpos[c][k]] : bpos[c][k]);
-        best[c][k] = vp[k];
-      }
-      if (writer && sub == 0) {
-        const int64_t o = prow * C + (c * LPR + l) * 4;
-        if (plane) st4(plane + o, v);
-        *reinterpret_cast<int4*>(arg + o) = a;
-      }
-    }
-  };
-  auto gather_back = [&](int first, int last, int step) {
-    for (int i = first; i < last; i += step) {
-      const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
-      float* dst = pooled + row * C + l * 4;
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        st4(dst + c * LPR * 4, make_float4(best[c][0], best[c][1], best[c][2], best[c][3]));
-    }
-  };
-
-  if (valid && !heavy) {
-    reset();
-    scan(beg + sub, end, RPI);
-    merge_subs();
-    emit(seg, beg >= end, true);
-    if (pooled) gather_back(beg + sub, end, RPI);
-  }
-  if constexpr (DEFER) {
-    __syncthreads();
-    for (int w = 0; w < kSegWarps; ++w) {
-      const int hl = hv_len[w];
-      if (hl == 0) continue;  // uniform across the CTA
-      const int hb = hv_beg[w];
-      reset();
-      scan(hb + warp * RPI + sub, hb + hl, kSegWarps * RPI);
-      merge_subs();
-      if (sub == 0) {
-#pragma unroll
-        for (int c = 0; c < CH; ++c)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            hv_val[warp * C + (c * LPR + l) * 4 + k] = best[c][k];
-            hv_pos[warp * C + (c * LPR + l) * 4 + k] = bpos[c][k];
-          }
-      }
-      __syncthreads();
-      // every warp folds the eight partials (it needs the result for the gather-back of its rows)
-      for (int q = 0; q < kSegWarps; ++q) {
-        if (q == warp) continue;
-#pragma unroll
-        for (int c = 0; c < CH; ++c)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float ov = hv_val[q * C + (c * LPR + l) * 4 + k];
-            const int op = hv_pos[q * C + (c * LPR + l) * 4 + k];
-            if (beats(ov, op, best[c][k], bpos[c][k])) { best[c][k] = ov; bpos[c][k] = op; }
-          }
-      }
-      emit((int64_t)blockIdx.x * kSegWarps + w, false, warp == 0);
-      if (pooled) gather_back(hb + warp * RPI + sub, hb + hl, kSegWarps * RPI);
-      __syncthreads();  // the partial buffers are free again
-    }
-  }
-}
-
-template <class RS>
-__global__ void __launch_bounds__(kSegWarps * kWarp)
-seg_max_bwd_kernel(const float* __restrict__ grad_pooled, const float* __restrict__ grad_plane, SegGeom g,
-                   const int32_t* __restrict__ arg, float* __restrict__ grad_rows) {
-  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  constexpr bool DEFER = C <= 256;
-  __shared__ float4 hv_sum[DEFER ? kSegWarps * (C / 4) : 1];
-  __shared__ int hv_beg[kSegWarps], hv_len[kSegWarps];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + warp;
-  const bool valid = seg < g.n_seg;
-  const int sub = lane / LPR, l = lane % LPR;
-  int beg = 0, end = 0;
-  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
-  const bool heavy = DEFER && valid && end - beg > kHeavyMax;
-  if (DEFER && lane == 0) { hv_len[warp] = heavy ? end - beg : 0; hv_beg[warp] = beg; }
-
-  float4 acc[CH];
-  auto reset = [&]() {
-#pragma unroll
-    for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  auto sum_rows = [&](int first, int last, int step) {  // pooled-gradient rows, then the RPI sub-rows of the warp
-    for (int i = first; i < last; i += step) {
-      const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
-      const float* src = grad_pooled + row * C + l * 4;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        float4 v = ld4(src + c * LPR * 4);
-        acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
-      }
-    }
-#pragma unroll
-    for (int off = LPR; off < kWarp; off <<= 1)
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        float4 o = shfl_xor4(acc[c], off);
-        acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
-      }
-  };
-  // add the plane gradient, then route the total to the saved argmax row of every channel
-  auto route = [&](int64_t sg, int first, int last, int step) {
-    const int64_t prow = plane_row(g, sg);
-    int4 a[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int64_t o = prow * C + (c * LPR + l) * 4;
-      a[c] = *reinterpret_cast<const int4*>(arg + o);
-      if (grad_plane) {
-        float4 v = ld4(grad_plane + o);
-        acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
-      }
-    }
-    for (int i = first; i < last; i += step) {
-      const int row32 = g.perm ? g.perm[i] : i;
-      float* dst = grad_rows + (int64_t)row32 * C + l * 4;
+  reset();
+  auto flush = [&](int slot) {
+    if (slot < 0) {
+      const int64_t o = plane_row(g, cur) * C + l * 4;
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         float4 v;
-        v.x = a[c].x == row32 ? acc[c].x : 0.f;
-        v.y = a[c].y == row32 ? acc[c].y : 0.f;
-        v.z = a[c].z == row32 ? acc[c].z : 0.f;
-        v.w = a[c].w == row32 ? acc[c].w : 0.f;
-        st4(dst + c * LPR * 4, v);
+        int4 a;
+        float* vp = &v.x;
+        int* ap = &a.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool none = bpos[c][k] == INT32_MAX;
+          vp[k] = none ? 0.0f : best[c][k];
+          ap[k] = none ? -1 : (g.perm ? __ldg(g.perm + bpos[c][k]) : bpos[c][k]);
+        }
+        if (plane) st4(plane + o + c * LPR * 4, v);
+        *reinterpret_cast<int4*>(arg + o + c * LPR * 4) = a;
+      }
+    } else {
+      const int64_t o = (chunk * 2 + slot) * C + l * 4;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        st4(s_val + o + c * LPR * 4, make_float4(best[c][0], best[c][1], best[c][2], best[c][3]));
+        *reinterpret_cast<int4*>(s_pos + o + c * LPR * 4) = make_int4(bpos[c][0], bpos[c][1], bpos[c][2], bpos[c][3]);
       }
     }
   };
 
-  if (valid && !heavy && beg < end) {
-    reset();
-    if (grad_pooled) sum_rows(beg + sub, end, RPI);
-    route(seg, beg + sub, end, RPI);
-  }
-  if constexpr (DEFER) {
-    __syncthreads();
-    for (int w = 0; w < kSegWarps; ++w) {
-      const int hl = hv_len[w];
-      if (hl == 0) continue;  // uniform across the CTA
-      const int hb = hv_beg[w];
-      reset();
-      if (grad_pooled) {
-        // contiguous slice per warp, partial sums added in warp order: a fixed order, like the light path
-        const int slice = (hl + kSegWarps - 1) / kSegWarps;
-        const int my_beg = min(hb + warp * slice, hb + hl), my_end = min(my_beg + slice, hb + hl);
-        sum_rows(my_beg + sub, my_end, RPI);
-        if (sub == 0) {
+  for (int64_t i = first; i < last; i += U) {
+    int k[U];
+    float4 v[U][CH];
 #pragma unroll
-          for (int c = 0; c < CH; ++c) hv_sum[warp * (C / 4) + c * LPR + l] = acc[c];
-        }
-        __syncthreads();
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = min(i + u, last - 1);
+      k[u] = level_key(g, p);
+      const int64_t row = g.perm ? (int64_t)__ldg(g.perm + p) : p;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) v[u][c] = ld4(rows + row * C + (c * LPR + l) * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u >= last) break;
+      if (k[u] != cur) {
+        flush(is_first && cont_in ? 0 : -1);
+        is_first = false;
+        cur = k[u];
         reset();
-        for (int q = 0; q < kSegWarps; ++q)
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const float4 o = hv_sum[q * (C / 4) + c * LPR + l];
-            acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
-          }
       }
-      route((int64_t)blockIdx.x * kSegWarps + w, hb + warp * RPI + sub, hb + hl, kSegWarps * RPI);
-      __syncthreads();  // hv_sum is free again
-    }
-  }
-}
-
-constexpr int kHeavy = 64;  // rows; longer segments are processed by the whole CTA (skewed tiles)
-
-// acc += rows[beg + sub, beg + sub + RPI, ...) ; two rows in flight per lane
-template <class RS>
-__device__ __forceinline__ void accum_range(const float* __restrict__ rows, const int32_t* __restrict__ perm, int beg, int end,
-                                            int sub, int l, float4 (&acc)[RS::CH]) {
-  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  int i = beg + sub;
-  for (; i + RPI < end; i += 2 * RPI) {
-    const int64_t r0 = perm ? (int64_t)perm[i] : (int64_t)i;
-    const int64_t r1 = perm ? (int64_t)perm[i + RPI] : (int64_t)(i + RPI);
-    float4 v0[CH], v1[CH];
+      const int pos = (int)(i + u);
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      v0[c] = ld4(rows + r0 * C + (c * LPR + l) * 4);
-      v1[c] = ld4(rows + r1 * C + (c * LPR + l) * 4);
-    }
+      for (int c = 0; c < CH; ++c) {
+        const float e[4] = {v[u][c].x, v[u][c].y, v[u][c].z, v[u][c].w};
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      acc[c].x += v0[c].x; acc[c].y += v0[c].y; acc[c].z += v0[c].z; acc[c].w += v0[c].w;
-      acc[c].x += v1[c].x; acc[c].y += v1[c].y; acc[c].z += v1[c].z; acc[c].w += v1[c].w;
-    }
-  }
-  for (; i < end; i += RPI) {
-    const int64_t r0 = perm ? (int64_t)perm[i] : (int64_t)i;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      float4 v = ld4(rows + r0 * C + (c * LPR + l) * 4);
-      acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
-    }
-  }
-}
-
-// sum the RPI sub-rows of a warp (fixed xor tree)
-template <class RS>
-__device__ __forceinline__ void warp_combine(float4 (&acc)[RS::CH]) {
-#pragma unroll
-  for (int off = RS::LPR; off < kWarp; off <<= 1)
-#pragma unroll
-    for (int c = 0; c < RS::CH; ++c) {
-      float4 o = shfl_xor4(acc[c], off);
-      acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
-    }
-}
-
-// Segment sum / mean.  WPS warps cooperate on one segment (coarse levels hold hundreds of points per
-// cell): each warp reduces a contiguous slice of the segment's rows, the slices are combined through
-// shared memory in slice order, so the summation order stays fixed.  With WPS == 1 (fine levels) a
-// segment longer than kHeavy rows -- a facade in a clustered tile -- is deferred and reduced by all
-// eight warps of the CTA the same way.
-template <class RS, int WPS>
-__global__ void __launch_bounds__(kSegWarps * kWarp)
-seg_reduce_fwd_kernel(const float* __restrict__ rows, SegGeom g, int mean, float* __restrict__ plane) {
-  constexpr int LPR = RS::LPR, CH = RS::CH, C = RS::C;
-  constexpr int SEGS = kSegWarps / WPS;  // segments per CTA
-  __shared__ float4 part_sum[kSegWarps * (C / 4)];
-  __shared__ int hv_beg[kSegWarps], hv_len[kSegWarps];
-  __shared__ long long hv_row[kSegWarps];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t seg = (int64_t)blockIdx.x * SEGS + warp / WPS;
-  const int part = warp % WPS;
-  const bool valid = seg < g.n_seg;
-  const int sub = lane / LPR, l = lane % LPR;
-  int beg = 0, end = 0;
-  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
-  const int len = end - beg;
-
-  auto finish = [&](float4 (&acc)[CH], int n_rows, int64_t prow) {
-    const float inv = mean ? __fdiv_rn(1.0f, (float)max(n_rows, 1)) : 1.0f;  // one division, <= 1 ulp from sum / count
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      float4 v = acc[c];
-      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-      st4(plane + prow * C + (c * LPR + l) * 4, v);
-    }
-  };
-  // slices of `n_parts` warps -> part 0, in slice order
-  auto combine_parts = [&](float4 (&acc)[CH], int first_warp, int n_parts, int my_part) {
-    if (sub == 0 && my_part > 0) {
-#pragma unroll
-      for (int c = 0; c < CH; ++c) part_sum[warp * (C / 4) + c * LPR + l] = acc[c];
-    }
-    __syncthreads();
-    if (my_part == 0 && sub == 0) {
-      for (int q = 1; q < n_parts; ++q)
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const float4 o = part_sum[(first_warp + q) * (C / 4) + c * LPR + l];
-          acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
+        for (int q = 0; q < 4; ++q) {
+          // strict >: the first row wins ties (rows of one fine cell are in point order); inside a
+          // coarser segment equal values are resolved by the original point index
+          bool take = e[q] > best[c][q];
+          if (g.tie && e[q] == best[c][q] && bpos[c][q] != INT32_MAX) take = __ldg(g.tie + pos) < __ldg(g.tie + bpos[c][q]);
+          if (take) { best[c][q] = e[q]; bpos[c][q] = pos; }
         }
+      }
     }
-  };
-
-  float4 acc[CH];
-#pragma unroll
-  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  // light segments: the WPS warps of the group; heavy ones (skewed tiles): deferred to the whole CTA
-  const int group = warp / WPS;
-  const bool heavy = WPS < kSegWarps && valid && len > kHeavy * WPS;
-  if (lane == 0 && part == 0) {
-    hv_len[group] = heavy ? len : 0;
-    hv_beg[group] = beg;
-    hv_row[group] = valid ? plane_row(g, seg) : 0;
   }
-  if (valid && !heavy) {
-    const int slice = (len + WPS - 1) / WPS;
-    const int my_beg = min(beg + part * slice, end), my_end = min(my_beg + slice, end);
-    accum_range<RS>(rows, g.perm, my_beg, my_end, sub, l, acc);
-    warp_combine<RS>(acc);
-  }
-  if (WPS > 1) combine_parts(acc, warp - part, WPS, part);  // contains the CTA barrier
-  else __syncthreads();
-  if (valid && !heavy && part == 0 && sub == 0) finish(acc, len, plane_row(g, seg));
-  if (WPS == kSegWarps) return;
-  for (int w = 0; w < SEGS; ++w) {
-    const int hl = hv_len[w];
-    if (hl == 0) continue;  // uniform across the CTA
-    const int hb = hv_beg[w], slice = (hl + kSegWarps - 1) / kSegWarps;
-    const int my_beg = min(hb + warp * slice, hb + hl), my_end = min(my_beg + slice, hb + hl);
-    __syncthreads();        // part_sum is free again
-#pragma unroll
-    for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    accum_range<RS>(rows, g.perm, my_beg, my_end, sub, l, acc);
-    warp_combine<RS>(acc);
-    combine_parts(acc, 0, kSegWarps, warp);
-    if (warp == 0 && sub == 0) finish(acc, hl, hv_row[w]);
-  }
+  const bool cont_out = last < g.n_rows && level_key(g, last) == cur;
+  flush(is_first && cont_in ? 0 : (cont_out ? 1 : -1));
 }
 
 template <class RS>
 __global__ void __launch_bounds__(kSegWarps * kWarp)
-seg_broadcast_kernel(const float* __restrict__ plane, SegGeom g, int mean, float* __restrict__ rows) {
-  // Light cells: one warp writes the cell's rows (CTA z = 0 only).  Cells with more than kHeavyMax rows are
-  // deferred: all eight warps of the CTA -- and, on coarse levels, the gridDim.y CTAs that share the cell
-  // group -- write interleaved row slices, so a facade's thousands of rows do not hang on one warp.
+seg_max_fix_kernel(SegGeom g, const float* __restrict__ s_val, const int32_t* __restrict__ s_pos,
+                   float* __restrict__ plane, int32_t* __restrict__ arg) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
-  __shared__ int hv_beg[kSegWarps], hv_len[kSegWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t seg = (int64_t)blockIdx.x * kSegWarps + warp;
-  const bool valid = seg < g.n_seg;
   const int sub = lane / LPR, l = lane % LPR;
-  int beg = 0, end = 0;
-  if (valid) { beg = g.cell_start[seg << g.shift]; end = g.cell_start[(seg + 1) << g.shift]; }
-  const bool heavy = valid && end - beg > kHeavyMax;
-  if (lane == 0) { hv_len[warp] = heavy ? end - beg : 0; hv_beg[warp] = beg; }
-
-  auto write_rows = [&](int64_t sg, int n_rows, int first, int last, int step) {
-    const float inv = mean ? __fdiv_rn(1.0f, (float)n_rows) : 1.0f;
-    const int64_t prow = plane_row(g, sg);
-    float4 v[CH];
+  const int64_t seg = ((int64_t)blockIdx.x * kSegWarps + warp) * RPI + sub;
+  if (seg >= g.n_seg) return;
+  const int beg = __ldg(g.cell_start + (seg << g.shift)), end = __ldg(g.cell_start + ((seg + 1) << g.shift));
+  const int c0 = beg / kChunk, c1 = (end - 1) / kChunk;
+  if (beg < end && c0 == c1) return;
+  const int64_t o = plane_row(g, seg) * C + l * 4;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      v[c] = ld4(plane + prow * C + (c * LPR + l) * 4);
-      v[c].x *= inv; v[c].y *= inv; v[c].z *= inv; v[c].w *= inv;
-    }
-    for (int i = first; i < last; i += step) {
-      const int64_t row = g.perm ? (int64_t)g.perm[i] : (int64_t)i;
+  for (int c = 0; c < CH; ++c) {
+    float best[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int bpos[4] = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
+    if (beg < end) {
+      for (int ck = c0; ck <= c1; ++ck) {
+        const int slot = (ck * kChunk > beg) ? 0 : 1;
+        const int64_t so = ((int64_t)ck * 2 + slot) * C + (c * LPR + l) * 4;
+        const float4 ov4 = ld4(s_val + so);
+        const int4 op4 = __ldg(reinterpret_cast<const int4*>(s_pos + so));
+        const float ov[4] = {ov4.x, ov4.y, ov4.z, ov4.w};
+        const int op[4] = {op4.x, op4.y, op4.z, op4.w};
 #pragma unroll
-      for (int c = 0; c < CH; ++c) st4(rows + row * C + (c * LPR + l) * 4, v[c]);
+        for (int q = 0; q < 4; ++q) {
+          // partials arrive in ascending position order: strict > keeps the earliest; explicit ranks for coarse levels
+          bool take = ov[q] > best[q];
+          if (g.tie && ov[q] == best[q] && op[q] != INT32_MAX && bpos[q] != INT32_MAX)
+            take = __ldg(g.tie + op[q]) < __ldg(g.tie + bpos[q]);
+          if (take) { best[q] = ov[q]; bpos[q] = op[q]; }
+        }
+      }
     }
-  };
-  if (valid && !heavy && beg < end && blockIdx.y == 0) write_rows(seg, end - beg, beg + sub, end, RPI);
-  __syncthreads();
-  const int slot = (int)blockIdx.y * kSegWarps + warp, n_slots = (int)gridDim.y * kSegWarps;
-  for (int w = 0; w < kSegWarps; ++w) {
-    const int hl = hv_len[w];
-    if (hl == 0) continue;
-    const int hb = hv_beg[w];
-    write_rows((int64_t)blockIdx.x * kSegWarps + w, hl, hb + slot * RPI + sub, hb + hl, n_slots * RPI);
+    float4 v;
+    int4 a;
+    float* vp = &v.x;
+    int* ap = &a.x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool none = bpos[q] == INT32_MAX;
+      vp[q] = none ? 0.0f : best[q];
+      ap[q] = none ? -1 : (g.perm ? __ldg(g.perm + bpos[q]) : bpos[q]);
+    }
+    if (plane) st4(plane + o + c * LPR * 4, v);
+    *reinterpret_cast<int4*>(arg + o + c * LPR * 4) = a;
   }
 }
 
-static int check_geom(const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso) {
-  if (!cell_start || n_seg < 0 || shift < 0 || shift > 30 || (shift & 1) || C <= 0 || reso <= 0) return T2H_ERR_INVALID_ARGUMENT;
+// ---- row-parallel maps: every point looks up the plane row of its cell ------------------------------
+// A warp owns 32 consecutive sorted positions per pass: lane j resolves (plane row, 1/count, row) of position
+// j once, the RPI sub-groups fetch them by shuffle.
+//   MODE 0: rows[row] = plane[cell] (* 1/count when mean)       -- S2 backward, gather-back of pool_local
+//   MODE 1: rows[row, c] = (arg[cell, c] == row) ? tot[cell, c] (+ extra[cell, c]) : 0   -- S1 backward
+template <class RS, int MODE>
+__global__ void __launch_bounds__(kSegWarps * kWarp)
+seg_rowmap_kernel(const float* __restrict__ plane, const float* __restrict__ extra, const int32_t* __restrict__ arg,
+                  SegGeom g, int mean, float* __restrict__ rows) {
+  constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int64_t first = ((int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5)) * 32;
+  if (first >= g.n_rows) return;
+  const int npts = (int)min((int64_t)32, g.n_rows - first);
+  int64_t my_prow = 0;
+  int my_row = 0;
+  float my_inv = 1.0f;
+  if (lane < npts) {
+    const int64_t i = first + lane;
+    const int64_t seg = level_key(g, i);
+    my_prow = plane_row(g, seg);
+    my_row = g.perm ? __ldg(g.perm + i) : (int)i;
+    if (mean) {
+      const int n = __ldg(g.cell_start + ((seg + 1) << g.shift)) - __ldg(g.cell_start + (seg << g.shift));
+      my_inv = __fdiv_rn(1.0f, (float)n);
+    }
+  }
+  for (int t0 = 0; t0 < npts; t0 += RPI) {
+    const int j = t0 + sub;
+    const bool act = j < npts;
+    const int src = act ? j : 0;
+    const int64_t prow = __shfl_sync(0xffffffffu, my_prow, src);
+    const int row = __shfl_sync(0xffffffffu, my_row, src);
+    const float inv = __shfl_sync(0xffffffffu, my_inv, src);
+    if (!act) continue;
+    const float* p = plane + prow * C + l * 4;
+    float* dst = rows + (int64_t)row * C + l * 4;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 v = ld4(p + c * LPR * 4);
+      if (MODE == 0) {
+        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      } else {
+        if (extra) {
+          const float4 e = ld4(extra + prow * C + (c * LPR + l) * 4);
+          v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+        }
+        const int4 a = __ldg(reinterpret_cast<const int4*>(arg + prow * C + (c * LPR + l) * 4));
+        v.x = a.x == row ? v.x : 0.f;
+        v.y = a.y == row ? v.y : 0.f;
+        v.z = a.z == row ? v.z : 0.f;
+        v.w = a.w == row ? v.w : 0.f;
+      }
+      st4_stream(dst + c * LPR * 4, v);
+    }
+  }
+}
+
+static int check_geom(const int32_t* row_keys, const int32_t* cell_start, int64_t n_rows, int64_t n_seg, int shift, int C,
+                      int morton, int reso) {
+  if (!cell_start || n_rows < 0 || n_seg < 0 || shift < 0 || shift > 30 || (shift & 1) || C <= 0 || reso <= 0)
+    return T2H_ERR_INVALID_ARGUMENT;
+  if (n_rows > 0 && !row_keys) return T2H_ERR_INVALID_ARGUMENT;
+  if (n_rows > INT32_MAX) return T2H_ERR_UNSUPPORTED_SHAPE;  // positions are int32 (cell_start is)
   if (shift && !morton) return T2H_ERR_INVALID_ARGUMENT;  // only Morton keys nest across levels
   if (morton && ((reso & (reso - 1)) || n_seg % ((int64_t)reso * reso))) return T2H_ERR_INVALID_ARGUMENT;
   return T2H_OK;
@@ -471,81 +368,121 @@ static inline int log2_cells_of(int reso) {
   return 2 * l;
 }
 
-static inline unsigned seg_blocks(int64_t n_seg) { return (unsigned)((n_seg + kSegWarps - 1) / kSegWarps); }
-
-// warps per segment from the mean segment length: ~8+ rows per warp, at most the whole CTA
-static inline int warps_per_segment(int64_t n_rows, int64_t n_seg) {
-  const int64_t avg = n_seg > 0 ? n_rows / n_seg : 0;
-  int wps = 1;
-  while (wps < kSegWarps && avg >= 8 * wps) wps *= 2;
-  return wps;
+static inline int64_t n_chunks_of(int64_t n_rows) { return (n_rows + kChunk - 1) / kChunk; }
+static inline unsigned blocks_for(int64_t items, int per_warp) {
+  const int64_t warps = (items + per_warp - 1) / per_warp;
+  return (unsigned)((warps + kSegWarps - 1) / kSegWarps);
 }
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace t2h
 
 using namespace t2h;
 
-extern "C" int t2h_seg_max_fwd(const float* rows, const int32_t* perm, const int32_t* tie_rank,
-                               const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
-                               float* pooled, float* plane, int32_t* arg, t2h_stream_t stream) {
-  int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
-  if (st) return st;
-  if (!rows || !arg) return T2H_ERR_INVALID_ARGUMENT;
-  if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, tie_rank, cell_start, n_seg, shift, morton, reso, log2_cells_of(reso)};
-  T2H_DISPATCH_ROWSHAPE(C, seg_max_fwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
-                               rows, g, pooled, plane, arg));
-  T2H_CHECK_LAUNCH();
-  return T2H_OK;
+extern "C" size_t t2h_seg_workspace_bytes(int64_t n_rows, int64_t n_seg, int C) {
+  // chunk-border partials: values + positions (max), or sums (mean); plus one (n_seg, C) plane of segment
+  // sums for the backward of the max
+  const size_t slots = (size_t)n_chunks_of(n_rows > 0 ? n_rows : 0) * 2 * (size_t)C;
+  return align256(slots * sizeof(float)) + align256(slots * sizeof(int32_t)) + align256((size_t)(n_seg > 0 ? n_seg : 0) * C * sizeof(float)) + 256;
 }
 
-extern "C" int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane, const int32_t* perm,
-                               const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
-                               const int32_t* arg, float* grad_rows, t2h_stream_t stream) {
-  int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
+extern "C" int t2h_seg_max_fwd(const float* rows, int64_t n_rows, const int32_t* perm, const int32_t* tie_rank,
+                               const int32_t* row_keys, const int32_t* cell_start, int64_t n_seg, int shift, int C,
+                               int morton, int reso, void* workspace, size_t workspace_bytes, float* pooled, float* plane,
+                               int32_t* arg, t2h_stream_t stream) {
+  int st = check_geom(row_keys, cell_start, n_rows, n_seg, shift, C, morton, reso);
   if (st) return st;
-  if (!arg || !grad_rows || (!grad_pooled && !grad_plane)) return T2H_ERR_INVALID_ARGUMENT;
+  if ((n_rows > 0 && !rows) || !arg || (pooled && !plane)) return T2H_ERR_INVALID_ARGUMENT;
   if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso, log2_cells_of(reso)};
-  T2H_DISPATCH_ROWSHAPE(C, seg_max_bwd_kernel<RS><<<seg_blocks(n_seg), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
-                               grad_pooled, grad_plane, g, arg, grad_rows));
-  T2H_CHECK_LAUNCH();
-  return T2H_OK;
-}
-
-extern "C" int t2h_seg_reduce_fwd(const float* rows, int64_t n_rows, const int32_t* perm, const int32_t* cell_start,
-                                  int64_t n_seg, int shift, int C, int morton, int reso, int mean, float* plane,
-                                  t2h_stream_t stream) {
-  int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
-  if (st) return st;
-  if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
-  if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso, log2_cells_of(reso)};
-  const int wps = warps_per_segment(n_rows, n_seg);
-  const unsigned blocks = (unsigned)((n_seg * wps + kSegWarps - 1) / kSegWarps);
+  if (!workspace || workspace_bytes < t2h_seg_workspace_bytes(n_rows, n_seg, C)) return T2H_ERR_WORKSPACE_TOO_SMALL;
+  SegGeom g{perm, tie_rank, row_keys, cell_start, n_rows, n_seg, shift, morton, reso, log2_cells_of(reso)};
+  const size_t slots = (size_t)n_chunks_of(n_rows) * 2 * (size_t)C;
+  float* s_val = (float*)workspace;
+  int32_t* s_pos = (int32_t*)((char*)workspace + align256(slots * sizeof(float)));
   cudaStream_t s = (cudaStream_t)stream;
   T2H_DISPATCH_ROWSHAPE(C, {
-    if (wps == 1) seg_reduce_fwd_kernel<RS, 1><<<blocks, kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane);
-    else if (wps == 2) seg_reduce_fwd_kernel<RS, 2><<<blocks, kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane);
-    else if (wps == 4) seg_reduce_fwd_kernel<RS, 4><<<blocks, kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane);
-    else seg_reduce_fwd_kernel<RS, 8><<<blocks, kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane);
+    if (n_rows > 0)
+      seg_max_rows_kernel<RS><<<blocks_for(n_chunks_of(n_rows), RS::RPI), kSegWarps * kWarp, 0, s>>>(rows, g, plane, arg, s_val, s_pos);
+    seg_max_fix_kernel<RS><<<blocks_for(n_seg, RS::RPI), kSegWarps * kWarp, 0, s>>>(g, s_val, s_pos, plane, arg);
+    if (pooled && n_rows > 0)
+      seg_rowmap_kernel<RS, 0><<<blocks_for(n_rows, 32), kSegWarps * kWarp, 0, s>>>(plane, nullptr, nullptr, g, 0, pooled);
   });
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
 
-extern "C" int t2h_seg_broadcast(const float* plane, const int32_t* perm, const int32_t* cell_start, int64_t n_seg,
-                                 int shift, int C, int morton, int reso, int mean, float* rows,
-                                 t2h_stream_t stream) {
-  int st = check_geom(cell_start, n_seg, shift, C, morton, reso);
+extern "C" int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane, int64_t n_rows, const int32_t* perm,
+                               const int32_t* row_keys, const int32_t* cell_start, int64_t n_seg, int shift, int C,
+                               int morton, int reso, const int32_t* arg, void* workspace, size_t workspace_bytes,
+                               float* grad_rows, t2h_stream_t stream) {
+  int st = check_geom(row_keys, cell_start, n_rows, n_seg, shift, C, morton, reso);
   if (st) return st;
-  if (!rows || !plane) return T2H_ERR_INVALID_ARGUMENT;
-  if (n_seg == 0) return T2H_OK;
-  SegGeom g{perm, nullptr, cell_start, n_seg, shift, morton, reso, log2_cells_of(reso)};
-  // coarse levels (few cells, many rows each): four CTAs share every group of cells for its heavy ones
-  const dim3 grid(seg_blocks(n_seg), n_seg < 16384 ? 4 : 1);
-  T2H_DISPATCH_ROWSHAPE(C, seg_broadcast_kernel<RS><<<grid, kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
-                               plane, g, mean, rows));
+  if (!arg || (n_rows > 0 && !grad_rows) || (!grad_pooled && !grad_plane)) return T2H_ERR_INVALID_ARGUMENT;
+  if (n_seg == 0 || n_rows == 0) return T2H_OK;
+  SegGeom g{perm, nullptr, row_keys, cell_start, n_rows, n_seg, shift, morton, reso, log2_cells_of(reso)};
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* tot = grad_plane;
+  const float* extra = nullptr;
+  if (grad_pooled) {
+    if (!workspace || workspace_bytes < t2h_seg_workspace_bytes(n_rows, n_seg, C)) return T2H_ERR_WORKSPACE_TOO_SMALL;
+    const size_t slots = (size_t)n_chunks_of(n_rows) * 2 * (size_t)C;
+    float* scratch = (float*)workspace;
+    float* sums = (float*)((char*)workspace + align256(slots * sizeof(float)) + align256(slots * sizeof(int32_t)));
+    T2H_DISPATCH_ROWSHAPE(C, {
+      seg_reduce_rows_kernel<RS><<<blocks_for(n_chunks_of(n_rows), RS::RPI), kSegWarps * kWarp, 0, s>>>(grad_pooled, g, 0, sums, scratch);
+      seg_reduce_fix_kernel<RS><<<blocks_for(n_seg, RS::RPI), kSegWarps * kWarp, 0, s>>>(g, 0, scratch, sums);
+    });
+    tot = sums;
+    extra = grad_plane;
+  }
+  T2H_DISPATCH_ROWSHAPE(C, (seg_rowmap_kernel<RS, 1><<<blocks_for(n_rows, 32), kSegWarps * kWarp, 0, s>>>(tot, extra, arg, g, 0, grad_rows)));
   T2H_CHECK_LAUNCH();
   return T2H_OK;
+}
+
+extern "C" int t2h_seg_reduce_fwd(const float* rows, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
+                                  const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                                  int mean, void* workspace, size_t workspace_bytes, float* plane, t2h_stream_t stream) {
+  int st = check_geom(row_keys, cell_start, n_rows, n_seg, shift, C, morton, reso);
+  if (st) return st;
+  if ((n_rows > 0 && !rows) || !plane) return T2H_ERR_INVALID_ARGUMENT;
+  if (n_seg == 0) return T2H_OK;
+  if (!workspace || workspace_bytes < t2h_seg_workspace_bytes(n_rows, n_seg, C)) return T2H_ERR_WORKSPACE_TOO_SMALL;
+  SegGeom g{perm, nullptr, row_keys, cell_start, n_rows, n_seg, shift, morton, reso, log2_cells_of(reso)};
+  float* scratch = (float*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  T2H_DISPATCH_ROWSHAPE(C, {
+    if (n_rows > 0)
+      seg_reduce_rows_kernel<RS><<<blocks_for(n_chunks_of(n_rows), RS::RPI), kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane, scratch);
+    seg_reduce_fix_kernel<RS><<<blocks_for(n_seg, RS::RPI), kSegWarps * kWarp, 0, s>>>(g, mean, scratch, plane);
+  });
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" int t2h_seg_broadcast(const float* plane, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
+                                 const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                                 int mean, float* rows, t2h_stream_t stream) {
+  int st = check_geom(row_keys, cell_start, n_rows, n_seg, shift, C, morton, reso);
+  if (st) return st;
+  if ((n_rows > 0 && !rows) || !plane) return T2H_ERR_INVALID_ARGUMENT;
+  if (n_seg == 0 || n_rows == 0) return T2H_OK;
+  SegGeom g{perm, nullptr, row_keys, cell_start, n_rows, n_seg, shift, morton, reso, log2_cells_of(reso)};
+  T2H_DISPATCH_ROWSHAPE(C, (seg_rowmap_kernel<RS, 0><<<blocks_for(n_rows, 32), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
+                               plane, nullptr, nullptr, g, mean, rows)));
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+/* ---- aliases named in SURVEY.md §8(b): the mean-scatter pair ---------------------------------------- */
+extern "C" int t2h_seg_mean_fwd(const float* rows, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
+                                const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                                void* workspace, size_t workspace_bytes, float* plane, t2h_stream_t stream) {
+  return t2h_seg_reduce_fwd(rows, n_rows, perm, row_keys, cell_start, n_seg, shift, C, morton, reso, 1, workspace,
+                            workspace_bytes, plane, stream);
+}
+extern "C" int t2h_seg_mean_bwd(const float* grad_plane, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
+                                const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
+                                float* grad_rows, t2h_stream_t stream) {
+  return t2h_seg_broadcast(grad_plane, n_rows, perm, row_keys, cell_start, n_seg, shift, C, morton, reso, 1, grad_rows, stream);
 }

@@ -22,28 +22,23 @@ from . import _lib
 
 def _bytes(name, a):
     """algorithmic bytes of one call from its positional ctypes arguments (see include/t2h.h)."""
-    if name == "t2h_seg_max_fwd":
-        n_seg, C = a[4], a[6]
-        rows = _bytes.n_rows
-        return 4 * rows * C + 4 * rows + (4 * rows * C if a[9] else 0) + (4 * n_seg * C if a[10] else 0) + 4 * n_seg * C
-    if name == "t2h_seg_max_bwd":
-        n_seg, C = a[4], a[6]
-        rows = _bytes.n_rows
+    if name == "t2h_seg_max_fwd":   # rows, n_rows, perm, tie, keys, cell_start, n_seg, shift, C, morton, reso, ws, ws_bytes, pooled, plane, arg
+        rows, n_seg, C = a[1], a[6], a[8]
+        return 4 * rows * C + 4 * rows + (4 * rows * C if a[13] else 0) + (4 * n_seg * C if a[14] else 0) + 4 * n_seg * C
+    if name == "t2h_seg_max_bwd":   # g_pooled, g_plane, n_rows, perm, keys, cell_start, n_seg, shift, C, ...
+        rows, n_seg, C = a[2], a[6], a[8]
         return 4 * rows * C + 4 * n_seg * C + 4 * rows * C
-    if name == "t2h_seg_reduce_fwd":
-        n_seg, C = a[4], a[6]
-        rows = _bytes.n_rows
+    if name == "t2h_seg_reduce_fwd":  # rows, n_rows, perm, keys, cell_start, n_seg, shift, C, ...
+        rows, n_seg, C = a[1], a[5], a[7]
         return 4 * rows * C + 4 * rows + 4 * n_seg * C
-    if name == "t2h_seg_broadcast":
-        n_seg, C = a[3], a[5]
-        rows = _bytes.n_rows
+    if name == "t2h_seg_broadcast":   # plane, n_rows, perm, keys, cell_start, n_seg, shift, C, ...
+        rows, n_seg, C = a[1], a[5], a[7]
         return 4 * rows * C + 4 * rows + 4 * n_seg * C
     if name == "t2h_bilinear_sample_fwd":
         reso, C, n, n_per = a[1], a[2], a[7], a[8]
         return 4 * max(n // max(n_per, 1), 1) * reso * reso * C + 8 * n + 4 * n * C
     if name == "t2h_bilinear_sample_bwd":
-        reso, C, n_seg = a[2], a[3], a[8]  # (workspace args follow)
-        rows = _bytes.n_rows
+        rows, reso, C, n_seg = a[1], a[2], a[3], a[9]  # g, n, reso, C, xyz, stride, perm, keys, cell_start, n_seg, ...
         return 4 * rows * C + 8 * rows + 4 * n_seg * C
     if name in ("t2h_upsample_bilinear_fwd", "t2h_upsample_bilinear_bwd"):
         B, h, w, C, oh, ow = a[1:7]

@@ -40,7 +40,7 @@ class CellLevel:
     otherwise it maps sorted position -> row.
     """
 
-    __slots__ = ("topo", "reso", "shift", "morton", "perm", "tie", "cell_start", "xyz_sorted", "B", "N", "n_seg",
+    __slots__ = ("topo", "reso", "shift", "morton", "perm", "tie", "keys", "cell_start", "xyz_sorted", "B", "N", "n_seg",
                  "n_points", "tile_ids")
 
     def __init__(self, topo, reso, shift, perm, tie=None):
@@ -52,6 +52,7 @@ class CellLevel:
         # argmax ties go to the smallest ORIGINAL point index; inside one sort key the stable sort
         # already guarantees that, a coarser segment (shift > 0) needs the explicit rank
         self.tie = tie if tie is not None else (topo.perm if shift > 0 else None)
+        self.keys = topo.keys_sorted   # sort key of every sorted position; this level's segment = key >> shift
         self.cell_start = topo.cell_start
         self.xyz_sorted = topo.xyz_sorted
         self.B, self.N = topo.B, topo.N
@@ -172,7 +173,9 @@ def sort_keys(keys: torch.Tensor, n_keys: int):
     return keys_sorted, perm, cell_start
 
 
+@torch.library.custom_op("t2h::gather_rows", mutates_args=())
 def gather_rows(rows: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """out[i] = rows[perm[i]] for a permutation ``perm``; differentiable (the backward is ``scatter_rows``)."""
     _lib.require_cuda_f32(rows, "gather_rows")
     rows = rows.contiguous()
     out = torch.empty_like(rows)
@@ -180,7 +183,9 @@ def gather_rows(rows: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@torch.library.custom_op("t2h::scatter_rows", mutates_args=())
 def scatter_rows(rows: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """out[perm[i]] = rows[i] for a permutation ``perm``; differentiable (the backward is ``gather_rows``)."""
     _lib.require_cuda_f32(rows, "scatter_rows")
     rows = rows.contiguous()
     out = torch.empty_like(rows)
@@ -188,10 +193,28 @@ def scatter_rows(rows: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@gather_rows.register_fake
+def _(rows, perm):
+    return torch.empty_like(rows)
+
+
+@scatter_rows.register_fake
+def _(rows, perm):
+    return torch.empty_like(rows)
+
+
+def _perm_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[1])
+
+
+gather_rows.register_autograd(lambda ctx, g: (scatter_rows(g.contiguous(), ctx.saved_tensors[0]), None), setup_context=_perm_setup)
+scatter_rows.register_autograd(lambda ctx, g: (gather_rows(g.contiguous(), ctx.saved_tensors[0]), None), setup_context=_perm_setup)
+
+
 class IndexLevel:
     """Level descriptor for an arbitrary (B, 1, N) int64 index (torch_scatter-style API)."""
 
-    __slots__ = ("reso", "shift", "morton", "perm", "tie", "cell_start", "xyz_sorted", "B", "N", "n_seg", "dim_size",
+    __slots__ = ("reso", "shift", "morton", "perm", "tie", "keys", "cell_start", "xyz_sorted", "B", "N", "n_seg", "dim_size",
                  "n_points", "tile_ids")
 
     def __init__(self, index: torch.Tensor, dim_size: int, check: bool = True):
@@ -206,7 +229,7 @@ class IndexLevel:
         _lib.call("t2h_index_keys", _lib.ptr(index), n, N, dim_size, _lib.ptr(keys), _lib.ptr(flag))
         if check and int(flag.item()) != 0:
             raise IndexError(f"scatter index out of range [0, {dim_size})")
-        _, self.perm, self.cell_start = sort_keys(keys, B * dim_size)
+        self.keys, self.perm, self.cell_start = sort_keys(keys, B * dim_size)
         self.reso, self.shift, self.morton = 1, 0, 0
         self.xyz_sorted, self.tie = None, None
         self.B, self.N, self.dim_size = B, N, dim_size
