@@ -228,6 +228,26 @@ int t2h_conv3x3_wgrad_f16(const float* grad_out, const uint32_t* g_absmax, const
                           const uint32_t* x_absmax, int B, int H, int W, int cin, int cout, int relu_in,
                           void* workspace, size_t workspace_bytes, float* grad_w, float* grad_b,
                           t2h_stream_t stream);
+/* ---- f2: scene inference either side of the forward.  dataset.py:234,243-278 + utils/crop_cloud.py:21-29
+ *      (strict 2-D crop, normalisation with the local z minimum, float cast, re-crop) and generator.py:139-154
+ *      (flip, blend window, accumulation into the float64 scene rasters).
+ * `points`: the scene cloud (n, 3) float64, binned by stride-sized cells so that a tile's candidates are a few
+ * contiguous row ranges; `items`: work items of <= 1024 candidates, 16 bytes each {int32 tile, int32 count,
+ * int64 first_row}; `tile_xy` (n_tiles, 2) float64 tile anchors (lower-left corner).
+ *   t2h_tile_count: item_count[i] = survivors of both crops; tile_zmin[t] = order-preserving code of min z over the
+ *                   first-crop survivors (initialise to all ones; an integer atomicMin, deterministic)
+ *   t2h_tile_write: survivors as (x, y, z, 0) float32 rows in candidate order, item i starting at item_offset[i]
+ *   t2h_blend_accumulate: for every raster pixel of the batch's bounding box, in tile order:
+ *                   dsm += (double) heights[b, S-1-i, j] * wx[j] * wy[i];  weight += wx[j] * wy[i]            */
+int t2h_tile_count(const double* points, const void* items, int64_t n_items, const double* tile_xy, double patch,
+                   int32_t* item_count, uint64_t* tile_zmin, t2h_stream_t stream);
+int t2h_tile_write(const double* points, const void* items, int64_t n_items, const double* tile_xy, double patch,
+                   double z_scale, const int64_t* item_offset, const uint64_t* tile_zmin, float* out_xyz0,
+                   t2h_stream_t stream);
+int t2h_blend_accumulate(const float* heights, int n_tiles, int S, const int32_t* t_row, const int32_t* l_col,
+                         const double* wx, const double* wy, int r0, int c0, int box_rows, int box_cols, int n_rows,
+                         int n_cols, double* dsm, double* weight, t2h_stream_t stream);
+
 /* bias gradient: out[c] = sum_r g[r, c], two-stage and deterministic */
 size_t t2h_colsum_workspace_bytes(int64_t rows, int n);
 int t2h_colsum(const float* g, int64_t ld_g, int64_t rows, int n, void* workspace,

@@ -44,3 +44,69 @@ def test_scene_generation_matches_oracle():
     # not bitwise: the fp16x3 GEMMs scale their operands by the maximum of the whole batch, so a tile's result
     # depends (at fp32 rounding level) on which other tiles share its batch
     assert (merged[covered.cuda()] - dsm[covered.cuda()]).abs().max().item() <= 1e-5 * scale.item()
+
+
+def test_crop_tiles_matches_oracle():
+    """t2h_tile_count / t2h_tile_write against the pinned CPU restatement of crop_pc_2d + normalisation + re-crop:
+    same survivors per tile (strict inequalities, points exactly on a tile edge), coordinates to float32 rounding
+    (the kernel evaluates (p - min) / patch directly, the reference the algebraically equal 4x4 matrix product)."""
+    import numpy as np
+    import os
+    from conftest import GOLDEN
+    from oracle.generator import crop_normalize_tile
+    from tomosar2height_b200.generator import SceneGenerator
+    v = np.load(os.path.join(GOLDEN, "scene_vectors.npz"))
+    pts = torch.from_numpy(v["crop_points"])
+    lo, hi = [386000.0, 5820000.0], [386300.0, 5820260.0]
+    gen = SceneGenerator(None, lo, hi, (-33.7, 156.5), patch_size=128.0, stride=64.0, pixel_size=1.0)
+    flat, counts = gen.crop_tiles(pts.cuda(), gen.anchors)
+    assert flat.shape == (sum(counts), 4) and float(flat[:, 3].abs().max()) == 0.0
+    start = 0
+    for (x0, y0), n in zip(gen.anchors, counts):
+        idx, norm = crop_normalize_tile(pts, x0, y0, 128.0, 156.5 + 33.7)
+        assert n == (0 if norm is None else norm.shape[0]), (x0, y0)
+        if n:
+            got = flat[start:start + n, :3].cpu().double()
+            order_g = np.lexsort((got[:, 2].numpy(), got[:, 1].numpy(), got[:, 0].numpy()))
+            ref = norm.double()
+            order_r = np.lexsort((ref[:, 2].numpy(), ref[:, 1].numpy(), ref[:, 0].numpy()))
+            assert (got[order_g] - ref[order_r]).abs().max().item() <= 2.0 ** -22   # a few float32 ulps of values < 1
+        start += n
+    # the two golden tiles come from the REAL reference code path
+    for k in range(2):
+        x0, y0 = (float(c) for c in v[f"crop_anchor_{k}"])
+        t = gen.anchors.index((x0, y0)) if (x0, y0) in gen.anchors else None
+        if t is not None:
+            assert counts[t] == v[f"crop_norm_{k}"].shape[0]
+
+
+def test_blend_accumulate_matches_reference_bitwise():
+    """t2h_blend_accumulate against DSMGenerator.generate_dsm itself (golden scene from the real reference):
+    flip, float64 window product and accumulation in tile order are bit-identical, also across batch boundaries."""
+    import numpy as np
+    import os
+    from conftest import GOLDEN
+    from tomosar2height_b200 import _lib
+    from tomosar2height_b200.generator import SceneGenerator, blend_vectors
+    v = np.load(os.path.join(GOLDEN, "scene_vectors.npz"))
+    tiles = torch.from_numpy(v["scene_tiles"]).cuda()
+    anchors = [tuple(float(c) for c in a) for a in v["scene_anchors"]]
+    gen = SceneGenerator(None, [386000.0, 5820000.0], [386300.0, 5820260.0], (-33.7, 156.5), patch_size=128.0,
+                         stride=64.0, pixel_size=1.0)
+    S = 128
+    wx, wy = blend_vectors(S, S, device="cuda")
+    for per_batch in (1, 4, 6):
+        dsm = torch.zeros(gen.n_rows, gen.n_cols, dtype=torch.float64, device="cuda")
+        weight = torch.zeros_like(dsm)
+        for k in range(0, len(anchors), per_batch):
+            win = [gen.raster_window(*a) for a in anchors[k:k + per_batch]]
+            rows, cols = [w[0] for w in win], [w[1] for w in win]
+            t_rows = torch.tensor(rows, dtype=torch.int32, device="cuda")
+            l_cols = torch.tensor(cols, dtype=torch.int32, device="cuda")
+            _lib.call("t2h_blend_accumulate", _lib.ptr(tiles[k:k + per_batch].contiguous()), len(win), S, _lib.ptr(t_rows),
+                      _lib.ptr(l_cols), _lib.ptr(wx), _lib.ptr(wy), min(rows), min(cols), max(rows) + S - min(rows),
+                      max(cols) + S - min(cols), gen.n_rows, gen.n_cols, _lib.ptr(dsm), _lib.ptr(weight))
+        got = gen.finalize(dsm, weight).cpu().numpy()
+        ref = v["scene_dsm"]
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        assert np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)]), per_batch

@@ -105,3 +105,30 @@ def test_explicit_bilinear_matches_aten():
     for size in (16, 31, 32, 50):
         want = F.interpolate(plane, size=size, mode="bilinear", align_corners=True)
         torch.testing.assert_close(oracle.upsample_bilinear_align(plane, size), want, rtol=1e-12, atol=1e-12)
+
+
+def test_scene_pieces_match_reference(golden_dir):
+    """oracle/generator.py against outputs of the REAL reference functions (tests/golden/make_golden_scene.py):
+    blend windows, strict crop + normalisation, raster index arithmetic, flip / window / accumulate / clamp."""
+    import math
+    from oracle.generator import blend_window, crop_normalize_tile, raster_col_row, accumulate_scene
+    v = np.load(os.path.join(golden_dir, "scene_vectors.npz"))
+    for tag, shape, hb in (("w128", (128, 128), (0.5, 0.5)), ("w512", (512, 512), (0.5, 0.5)), ("w9x7", (9, 7), (0.3, 0.5)),
+                           ("w16", (16, 16), (0.0, 0.25))):
+        assert np.array_equal(blend_window(*shape, hb).numpy(), v["window_" + tag]), tag
+    pts = torch.from_numpy(v["crop_points"])
+    for k in range(2):
+        x0, y0 = v[f"crop_anchor_{k}"]
+        idx, norm = crop_normalize_tile(pts, float(x0), float(y0), 128.0, 156.5 - (-33.7))
+        assert np.array_equal(idx.numpy(), v[f"crop_index_{k}"])       # strict inequalities, both crops
+        assert np.array_equal(norm.numpy(), v[f"crop_norm_{k}"])       # same matrix path -> bit-exact float32
+    for (x, y), (col, row) in zip(v["raster_query_xy"], v["raster_query_colrow"]):
+        assert raster_col_row(float(x), float(y), 386000.0, 5820260.0, 1.0) == (int(col), int(row))
+    assert tuple(v["raster_shape"]) == (math.floor(260.0 / 1.0), math.floor(300.0 / 1.0))
+    tiles = [torch.from_numpy(t) for t in v["scene_tiles"]]
+    dsm, weight = accumulate_scene(tiles, [tuple(a) for a in v["scene_anchors"]], (386000.0, 5820000.0),
+                                   (386300.0, 5820260.0), 128.0, 1.0)
+    got = torch.maximum(dsm / weight, torch.tensor(0., dtype=torch.float64)).numpy()
+    ref = v["scene_dsm"]
+    assert np.array_equal(np.isnan(got), np.isnan(ref))                # uncovered pixels stay NaN
+    assert np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])    # same additions in the same order

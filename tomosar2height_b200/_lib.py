@@ -14,11 +14,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libt2h.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["t2h_topology.cu", "t2h_segment.cu", "t2h_sample.cu", "t2h_linear.cu"]
+SOURCES = ["t2h_topology.cu", "t2h_segment.cu", "t2h_sample.cu", "t2h_scene.cu", "t2h_linear.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
-_p, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+_p, _i32, _i64, _sz, _f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_double
 
 # name -> argtypes (every function returns int unless listed in _RESTYPE)
 SIGNATURES = {
@@ -42,6 +42,9 @@ SIGNATURES = {
     "t2h_bilinear_sample_fwd": [_p, _i32, _i32, _p, _i64, _p, _p, _i64, _i64, _p, _p],
     "t2h_bilinear_sample_bwd_workspace_bytes": [_i32, _i32, _i64, _i64, _i32],
     "t2h_bilinear_sample_bwd": [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _p, _sz, _p, _p],
+    "t2h_tile_count": [_p, _p, _i64, _p, _f64, _p, _p],
+    "t2h_tile_write": [_p, _p, _i64, _p, _f64, _f64, _p, _p, _p],
+    "t2h_blend_accumulate": [_p, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_upsample_bilinear_fwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_upsample_bilinear_bwd": [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_split_tf32": [_p, _i64, _p, _p, _p],

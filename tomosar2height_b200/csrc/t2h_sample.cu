@@ -234,7 +234,9 @@ struct WTile {
   static constexpr int LOG2_REGION = (TW == 4) ? 7 : 5;   // log2(8 * TW * TW)
   static constexpr int LOG2_BLOCK = (TW == 4) ? 4 : 2;
   static constexpr int STAGE_WORDS = 32 * 9;              // per warp: 32 rows x (4 tap cells, 4 weights, row)
-  static constexpr int SMEM = (kTileWarps * TILE_FLOATS + kTileWarps * STAGE_WORDS) * 4;
+  static constexpr int SMEM = (kTileWarps * TILE_FLOATS + kTileWarps * STAGE_WORDS) * 4;  // private tiles + staging
+  static constexpr int CS = (C == 64) ? 32 : C;                                          // channels per assembly pass
+  static constexpr int SMEM_REGION = SMEM + RWH * RHH * CS * 4;                           // + the region tile (light pass)
 };
 
 // rows [r0, r1) of the sorted order (all inside the block whose haloed tile origin is (bx0 - 1, by0 - 1)) -> tile.
@@ -247,7 +249,7 @@ __device__ __forceinline__ void wtile_accumulate(float* __restrict__ tile, int* 
                                                  int r0, int r1, int bx0, int by0, int lane) {
   using Cfg = WTile<C, TW>;
   constexpr int LPR = Cfg::LPR, TAPS = Cfg::TAPS, TWH = Cfg::TWH;
-  constexpr int U = 8;
+  constexpr int U = 4;
   const int sub = lane / LPR, l = lane % LPR;
   const float* gbase = grad_rows + l * 4;
   for (int base_i = r0; base_i < r1; base_i += kWarp) {
@@ -331,29 +333,53 @@ sample_bwd_wtile_kernel(const float* __restrict__ grad_rows, int reso, const flo
   const int64_t key0 = (img << log2_cells) + rcode + ((int64_t)warp << Cfg::LOG2_BLOCK);
   const int p0 = __ldg(cell_start + (key0 << shift)), p1 = __ldg(cell_start + ((key0 + (1 << Cfg::LOG2_BLOCK)) << shift));
 
-  for (int f = lane; f < Cfg::TILE_FLOATS / 4; f += kWarp) reinterpret_cast<float4*>(tile)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncwarp();
-  if (p1 - p0 <= kHeavyBlock)
+  const bool mine = p1 > p0 && p1 - p0 <= kHeavyBlock;  // empty and heavy blocks contribute nothing here
+  if (mine) {
+    for (int f = lane; f < Cfg::TILE_FLOATS / 4; f += kWarp) reinterpret_cast<float4*>(tile)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
     wtile_accumulate<C, TW>(tile, st_cell, st_w, st_row, grad_rows, reso, xyz, stride, perm, p0, p1, bx0, by0, lane);
-  __syncthreads();
-  // region tile = sum of the private tiles that cover each haloed cell, in block order (by, bx)
+  }
+  // region tile = sum of the private tiles, added in four phases: the blocks of one phase (same row, columns two
+  // apart) do not overlap, so every region cell has one writer per phase and a fixed order of additions.
+  // Assembled CS channels at a time to bound the shared memory of the wide variants.
+  constexpr int CS = Cfg::CS;
+  float* rt = wt_smem + Cfg::SMEM / 4;  // [RHH][RWH][CS], behind the private tiles and the staging arrays
   float* dst = scratch + region * (int64_t)(Cfg::RWH * Cfg::RHH * C);
-  for (int idx = threadIdx.x; idx < Cfg::RWH * Cfg::RHH * (C / 4); idx += kTileWarps * kWarp) {
-    const int c4i = idx % (C / 4), cellt = idx / (C / 4);
-    const int ry = cellt / Cfg::RWH, rx = cellt % Cfg::RWH;
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int cs0 = 0; cs0 < C; cs0 += CS) {
+    __syncthreads();
+    for (int f = threadIdx.x; f < Cfg::RWH * Cfg::RHH * (CS / 4); f += kTileWarps * kWarp)
+      reinterpret_cast<float4*>(rt)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+#pragma unroll 1
+    for (int phase = 0; phase < 4; ++phase) {
+      if (mine && ((bx & 1) | (by << 1)) == phase) {
+        // a tile row (TWH cells x CS channels) is contiguous in the region tile too
 #pragma unroll
-    for (int qy = 0; qy < 2; ++qy)
-#pragma unroll
-      for (int qx = 0; qx < 4; ++qx) {
-        const int lx = rx - qx * TW, ly = ry - qy * TW;
-        if (lx >= 0 && lx < TWH && ly >= 0 && ly < TWH) {
-          const int w2 = (qx & 1) | (qy << 1) | ((qx >> 1) << 2);
-          const float4 o = *reinterpret_cast<const float4*>(wt_smem + w2 * Cfg::TILE_FLOATS + (ly * TWH + lx) * C + c4i * 4);
-          sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+        for (int ly = 0; ly < TWH; ++ly) {
+          float* drow = rt + ((by * TW + ly) * Cfg::RWH + bx * TW) * CS;
+          const float* srow = tile + ly * TWH * C + cs0;
+          for (int f = lane; f < TWH * (CS / 4); f += kWarp) {
+            const int cellx = f / (CS / 4), c4i = f % (CS / 4);
+            float4* d = reinterpret_cast<float4*>(drow + f * 4);
+            const float4 o = *reinterpret_cast<const float4*>(srow + cellx * C + c4i * 4);
+            float4 v = *d;
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            *d = v;
+          }
         }
       }
-    st4(dst + (int64_t)cellt * C + c4i * 4, sum);
+      __syncthreads();
+    }
+    if (CS == C) {
+      for (int f = threadIdx.x; f < Cfg::RWH * Cfg::RHH * (C / 4); f += kTileWarps * kWarp)
+        st4(dst + f * 4, reinterpret_cast<const float4*>(rt)[f]);
+    } else {
+      for (int f = threadIdx.x; f < Cfg::RWH * Cfg::RHH * (CS / 4); f += kTileWarps * kWarp) {
+        const int c4i = f % (CS / 4), cellt = f / (CS / 4);
+        st4(dst + (int64_t)cellt * C + cs0 + c4i * 4, reinterpret_cast<const float4*>(rt)[f]);
+      }
+    }
   }
 }
 
@@ -411,9 +437,12 @@ sample_bwd_wtile_fix_kernel(const int32_t* __restrict__ cell_start, int shift, c
   constexpr int TWH = Cfg::TWH;
   const int64_t region = blockIdx.x;
   float* rt = scratch + region * (int64_t)(Cfg::RWH * Cfg::RHH * C);
+  __shared__ int bounds[kTileWarps + 1];  // the nine block boundaries, fetched in parallel
+  if (threadIdx.x <= kTileWarps)
+    bounds[threadIdx.x] = __ldg(cell_start + (((region << Cfg::LOG2_REGION) + ((int64_t)threadIdx.x << Cfg::LOG2_BLOCK)) << shift));
+  __syncthreads();
   for (int w = 0; w < kTileWarps; ++w) {
-    const int64_t key0 = (region << Cfg::LOG2_REGION) + ((int64_t)w << Cfg::LOG2_BLOCK);
-    const int p0 = __ldg(cell_start + (key0 << shift)), p1 = __ldg(cell_start + ((key0 + (1 << Cfg::LOG2_BLOCK)) << shift));
+    const int p0 = bounds[w], p1 = bounds[w + 1];
     if (p1 - p0 <= kHeavyBlock) continue;  // uniform across the CTA
     const int bx = (w & 1) | (((w >> 2) & 1) << 1), by = (w >> 1) & 1;
     const int c0 = p0 / kHeavyBlock, c1 = (p1 - 1) / kHeavyBlock;
@@ -488,26 +517,24 @@ sample_bwd_nine_rows_kernel(const float* __restrict__ grad_rows, int64_t n_rows,
                             float* __restrict__ nine, float* __restrict__ slots) {
   constexpr int RPI = 32 / LPR, ROWS = Rows9<LPR>::ROWS, U = 8;
   static_assert(LPR % U == 0, "a batch of LPR rows is consumed U rows at a time");
+  // per warp: the resolved rows of the current batch -- {key, row, class, -} and the four tap weights
+  __shared__ int4 st_meta[kTileWarps][32];
+  __shared__ float4 st_w[kTileWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR;
   const int64_t chunk = ((int64_t)blockIdx.x * kTileWarps + warp) * RPI + sub;
-  // every lane group walks its own chunk; groups past the end idle through the loop (the shuffles below are
-  // confined to a group but named by the full-warp mask)
+  // every lane group walks its own chunk; groups past the end idle through the batch loop
   const int64_t first = min(chunk * ROWS, n_rows);
   const int64_t last = min(first + (int64_t)ROWS, n_rows);
   const bool live = first < last;
   const int ch0 = blockIdx.y * (LPR * 4) + l * 4;  // this lane's four channels
+  const int4* meta = &st_meta[warp][sub * LPR];
+  const float4* wts = &st_w[warp][sub * LPR];
 
   auto key_of = [&](int64_t i) { return __ldg(keys + i) >> shift; };
   int cur = live ? key_of(first) : 0;
   const bool cont_in = live && first > 0 && key_of(first - 1) == cur;
   bool is_first = true;
-  int cx = 0, cy = 0;
-  auto decode = [&](int key) {
-    const uint32_t code = (uint32_t)key & ((1u << log2_cells) - 1u);
-    cell_decode(code, reso, morton, cx, cy);
-  };
-  decode(cur);
   float4 acc[9];
 #pragma unroll
   for (int d = 0; d < 9; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -518,56 +545,49 @@ sample_bwd_nine_rows_kernel(const float* __restrict__ grad_rows, int64_t n_rows,
   };
   auto fma4 = [](float4& a, float w, const float4& g) { a.x += w * g.x; a.y += w * g.y; a.z += w * g.z; a.w += w * g.w; };
 
-  // batches of LPR rows: lane l of the group resolves key, row index, tap origin and the four tap weights of
-  // row base + l ONCE; the group then consumes the batch row by row through group-wide shuffles
+  // batches of LPR rows: lane l of the group resolves key, row index, tap class and the four tap weights of row
+  // base + l ONCE (the coordinate arithmetic is ~40 instructions) and parks them in shared memory; the group then
+  // consumes the batch row by row with two broadcast loads per row
   for (int64_t base = first; __any_sync(0xffffffffu, base < last); base += LPR) {
     const int nb = (int)max((int64_t)0, min((int64_t)LPR, last - base));
-    int my_key = 0, my_x0 = 0, my_y0 = 0;
-    int64_t my_row = 0;
-    float w_nw = 0.f, w_ne = 0.f, w_sw = 0.f, w_se = 0.f;
+    __syncwarp();  // the previous batch has been consumed
     if (l < nb) {
       const int64_t p = base + l;
-      my_key = key_of(p);
-      my_row = perm ? (int64_t)__ldg(perm + p) : p;
+      const int key = key_of(p);
+      const int row = perm ? __ldg(perm + p) : (int)p;
       const float2 pxy = __ldg(reinterpret_cast<const float2*>(xyz + p * stride));
       const Taps t = make_taps(pxy.x, pxy.y, reso);
       const float wx1 = (t.x0 + 1 < reso) ? t.wx1 : 0.f, wy1 = (t.y0 + 1 < reso) ? t.wy1 : 0.f;
-      my_x0 = t.x0; my_y0 = t.y0;
-      w_nw = __fmul_rn(t.wx0, t.wy0); w_ne = __fmul_rn(wx1, t.wy0);
-      w_sw = __fmul_rn(t.wx0, wy1);   w_se = __fmul_rn(wx1, wy1);
+      int cx, cy;
+      cell_decode((uint32_t)key & ((1u << log2_cells) - 1u), reso, morton, cx, cy);
+      // the tap origin is the own cell or the one before it, per axis
+      st_meta[warp][lane] = make_int4(key, row, (t.x0 < cx ? 1 : 0) | (t.y0 < cy ? 2 : 0), 0);
+      st_w[warp][lane] = make_float4(__fmul_rn(t.wx0, t.wy0), __fmul_rn(wx1, t.wy0), __fmul_rn(t.wx0, wy1), __fmul_rn(wx1, wy1));
     }
-    for (int j0 = 0; j0 < LPR; j0 += U) {
+    __syncwarp();
+    for (int j0 = 0; j0 < nb; j0 += U) {
       float4 gq[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t row = __shfl_sync(0xffffffffu, my_row, j0 + u, LPR);
-        if (j0 + u < nb) gq[u] = ld4_stream(grad_rows + row * C + ch0);
-      }
+      for (int u = 0; u < U; ++u)
+        if (j0 + u < nb) gq[u] = ld4_stream(grad_rows + (int64_t)meta[j0 + u].y * C + ch0);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int j = j0 + u;
-        const int k = __shfl_sync(0xffffffffu, my_key, j, LPR);
-        const int x0 = __shfl_sync(0xffffffffu, my_x0, j, LPR), y0 = __shfl_sync(0xffffffffu, my_y0, j, LPR);
-        const float a_nw = __shfl_sync(0xffffffffu, w_nw, j, LPR), a_ne = __shfl_sync(0xffffffffu, w_ne, j, LPR);
-        const float a_sw = __shfl_sync(0xffffffffu, w_sw, j, LPR), a_se = __shfl_sync(0xffffffffu, w_se, j, LPR);
-        if (j < nb) {
-          if (k != cur) {
-            flush(is_first && cont_in ? 0 : -1);
-            is_first = false;
-            cur = k;
-            decode(cur);
+        if (j0 + u >= nb) break;
+        const int4 m = meta[j0 + u];
+        const float4 w = wts[j0 + u];
+        if (m.x != cur) {
+          flush(is_first && cont_in ? 0 : -1);
+          is_first = false;
+          cur = m.x;
 #pragma unroll
-            for (int d = 0; d < 9; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          // the tap origin is the own cell or the one before it, per axis: four cases, four live partials each
-          const bool left = x0 < cx, up = y0 < cy;
-          if (up) {
-            if (left) { fma4(acc[0], a_nw, gq[u]); fma4(acc[1], a_ne, gq[u]); fma4(acc[3], a_sw, gq[u]); fma4(acc[4], a_se, gq[u]); }
-            else      { fma4(acc[1], a_nw, gq[u]); fma4(acc[2], a_ne, gq[u]); fma4(acc[4], a_sw, gq[u]); fma4(acc[5], a_se, gq[u]); }
-          } else {
-            if (left) { fma4(acc[3], a_nw, gq[u]); fma4(acc[4], a_ne, gq[u]); fma4(acc[6], a_sw, gq[u]); fma4(acc[7], a_se, gq[u]); }
-            else      { fma4(acc[4], a_nw, gq[u]); fma4(acc[5], a_ne, gq[u]); fma4(acc[7], a_sw, gq[u]); fma4(acc[8], a_se, gq[u]); }
-          }
+          for (int d = 0; d < 9; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // four cases, four live partials each (acc index = 3 * (target row - cy + 1) + (target column - cx + 1))
+        switch (m.z) {
+          case 3:  fma4(acc[0], w.x, gq[u]); fma4(acc[1], w.y, gq[u]); fma4(acc[3], w.z, gq[u]); fma4(acc[4], w.w, gq[u]); break;
+          case 2:  fma4(acc[1], w.x, gq[u]); fma4(acc[2], w.y, gq[u]); fma4(acc[4], w.z, gq[u]); fma4(acc[5], w.w, gq[u]); break;
+          case 1:  fma4(acc[3], w.x, gq[u]); fma4(acc[4], w.y, gq[u]); fma4(acc[6], w.z, gq[u]); fma4(acc[7], w.w, gq[u]); break;
+          default: fma4(acc[4], w.x, gq[u]); fma4(acc[5], w.y, gq[u]); fma4(acc[7], w.z, gq[u]); fma4(acc[8], w.w, gq[u]); break;
         }
       }
     }
@@ -577,28 +597,34 @@ sample_bwd_nine_rows_kernel(const float* __restrict__ grad_rows, int64_t n_rows,
   flush(is_first && cont_in ? 0 : (cont_out ? 1 : -1));
 }
 
-// one warp per cell: empty -> zero partials; crossing a chunk border -> sum of the chunk partials in chunk order
+// one thread per (cell, float4 of its 9 x C partials): empty -> zero; crossing a chunk border -> sum of the chunk
+// partials in chunk order, four loads in flight
 template <int ROWS>
-__global__ void __launch_bounds__(kTileWarps * kWarp)
+__global__ void __launch_bounds__(256)
 sample_bwd_nine_fix_kernel(const int32_t* __restrict__ cell_start, int64_t n_seg, int shift, int C,
                            const float* __restrict__ slots, float* __restrict__ nine) {
-  const int lane = threadIdx.x & 31;
-  const int64_t seg = (int64_t)blockIdx.x * kTileWarps + (threadIdx.x >> 5);
-  if (seg >= n_seg) return;
+  const int per_cell = 9 * C / 4;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_seg * per_cell) return;
+  const int64_t seg = gid / per_cell;
+  const int e = (int)(gid - seg * per_cell);
   const int beg = __ldg(cell_start + (seg << shift)), end = __ldg(cell_start + ((seg + 1) << shift));
   const int c0 = beg / ROWS, c1 = (end - 1) / ROWS;
   if (beg < end && c0 == c1) return;
-  float* dst = nine + seg * 9 * (int64_t)C;
-  for (int e = lane; e < 9 * C / 4; e += kWarp) {
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (beg < end)
-      for (int ck = c0; ck <= c1; ++ck) {
-        const int slot = (ck * ROWS > beg) ? 0 : 1;
-        const float4 o = ld4(slots + ((int64_t)ck * 2 + slot) * 9 * C + e * 4);
-        sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (beg < end)
+    for (int ck = c0; ck <= c1; ck += 4) {
+      float4 o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cq = min(ck + q, c1);
+        o[q] = ld4(slots + ((int64_t)cq * 2 + ((cq * ROWS > beg) ? 0 : 1)) * 9 * C + e * 4);
       }
-    st4(dst + e * 4, sum);
-  }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (ck + q <= c1) { sum.x += o[q].x; sum.y += o[q].y; sum.z += o[q].z; sum.w += o[q].w; }
+    }
+  st4(nine + seg * 9 * (int64_t)C + e * 4, sum);
 }
 
 // grad_plane[b, ty, tx, :] = sum over (dy, dx) of nine[cell (tx - dx, ty - dy)][(dy + 1) * 3 + dx + 1]
@@ -779,14 +805,14 @@ static int launch_wtile(const float* grad_rows, int64_t n_points, int reso, cons
   auto kern = sample_bwd_wtile_kernel<C, TW>;
   auto heavy = sample_bwd_wtile_heavy_kernel<C, TW>;
   // per device and idempotent; set on every launch so that the entry point keeps no state
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess ||
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_REGION) != cudaSuccess ||
       cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
     (void)cudaGetLastError();
     return T2H_ERR_CUDA;
   }
   const int64_t regions = n_seg >> Cfg::LOG2_REGION;
   float* slots = (float*)((char*)scratch + align256s((size_t)regions * Cfg::RWH * Cfg::RHH * C * sizeof(float)));
-  kern<<<(unsigned)regions, kTileWarps * kWarp, Cfg::SMEM, s>>>(grad_rows, reso, xyz, stride, perm, cell_start, shift, log2_cells, scratch);
+  kern<<<(unsigned)regions, kTileWarps * kWarp, Cfg::SMEM_REGION, s>>>(grad_rows, reso, xyz, stride, perm, cell_start, shift, log2_cells, scratch);
   T2H_CHECK_LAUNCH();
   const int64_t chunks = (n_points + kHeavyBlock - 1) / kHeavyBlock;
   if (chunks > 0) {
@@ -815,8 +841,8 @@ static int launch_nine(const float* grad_rows, int64_t n_points, int reso, int C
                                                                         shift, morton, log2_cells, nine, slots);
     T2H_CHECK_LAUNCH();
   }
-  sample_bwd_nine_fix_kernel<ROWS><<<(unsigned)((n_seg + kTileWarps - 1) / kTileWarps), kTileWarps * kWarp, 0, s>>>(
-      cell_start, n_seg, shift, C, slots, nine);
+  const int64_t fix_threads = n_seg * (9 * C / 4);
+  sample_bwd_nine_fix_kernel<ROWS><<<(unsigned)((fix_threads + 255) / 256), 256, 0, s>>>(cell_start, n_seg, shift, C, slots, nine);
   T2H_CHECK_LAUNCH();
   const int64_t threads = n_seg * (C / 4);
   sample_bwd_nine_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(nine, reso, C, morton, log2_cells, n_seg, grad_plane);

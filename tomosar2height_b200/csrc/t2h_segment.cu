@@ -114,38 +114,91 @@ seg_reduce_rows_kernel(const float* __restrict__ rows, SegGeom g, int mean, floa
   flush(is_first && cont_in ? 0 : (cont_out ? 1 : -1));
 }
 
-// every cell: empty -> zero row; crossing a chunk border -> sum of its chunk partials in chunk order
+// every cell: empty -> zero row; crossing a chunk border -> sum of its chunk partials in chunk order.
+// Lane j of a warp inspects cell base + j (two coalesced loads); only the flagged cells -- a small minority on
+// fine levels -- are then worked on, RPI at a time by the lane groups, with kFixUnroll partials in flight.
+constexpr int kFixUnroll = 4;
+constexpr int kLongList = 16;  // partials; longer lists are reduced by the whole warp
+
 template <class RS>
 __global__ void __launch_bounds__(kSegWarps * kWarp)
-seg_reduce_fix_kernel(SegGeom g, int mean, const float* __restrict__ scratch, float* __restrict__ plane) {
+seg_reduce_fix_kernel(SegGeom g, int mean, int cpw, const float* __restrict__ scratch, float* __restrict__ plane) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR;
-  const int64_t seg = ((int64_t)blockIdx.x * kSegWarps + warp) * RPI + sub;
-  if (seg >= g.n_seg) return;
-  const int beg = __ldg(g.cell_start + (seg << g.shift)), end = __ldg(g.cell_start + ((seg + 1) << g.shift));
-  const int c0 = beg / kChunk, c1 = (end - 1) / kChunk;
-  if (beg < end && c0 == c1) return;  // finished by its walker
-  float4 acc[CH];
+  const int64_t base = ((int64_t)blockIdx.x * kSegWarps + warp) * cpw;  // cpw cells per warp (coarse levels: fewer)
+  if (base >= g.n_seg) return;
+  int my_beg = 0, my_end = 0;
+  bool need = false;
+  if (lane < cpw && base + lane < g.n_seg) {
+    my_beg = __ldg(g.cell_start + ((base + lane) << g.shift));
+    my_end = __ldg(g.cell_start + ((base + lane + 1) << g.shift));
+    need = my_beg < my_end && my_beg / kChunk != (my_end - 1) / kChunk;
+    if (my_beg == my_end) {  // empty cell (the common case on fine levels): its own lane writes the zero row
+      float* z = plane + plane_row(g, base + lane) * C;
+      for (int c4 = 0; c4 < C / 4; ++c4) st4(z + c4 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+  // a cell with a long list of partials (a facade: thousands of rows) is summed by ALL lane groups of the warp,
+  // each taking a contiguous part of the list, combined in group order; the others one cell per group
+  const bool is_long = need && (my_end - 1) / kChunk - my_beg / kChunk >= kLongList;
+  const unsigned flagged = __ballot_sync(0xffffffffu, need && !is_long);
+  const unsigned longs = __ballot_sync(0xffffffffu, is_long);
+  auto sum_range = [&](float4 (&acc)[CH], int beg, int ca, int cb) {  // partials of chunks [ca, cb] of the cell starting at beg
+    for (int ck = ca; ck <= cb; ck += kFixUnroll) {
+      float4 o[kFixUnroll][CH];
 #pragma unroll
-  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (beg < end) {
-    for (int ck = c0; ck <= c1; ++ck) {
-      const int slot = (ck * kChunk > beg) ? 0 : 1;
-      const float* src = scratch + ((int64_t)ck * 2 + slot) * C + l * 4;
+      for (int q = 0; q < kFixUnroll; ++q) {
+        const int cq = min(ck + q, cb);
+        const float* sp = scratch + ((int64_t)cq * 2 + ((cq * kChunk > beg) ? 0 : 1)) * C + l * 4;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) o[q][c] = ld4(sp + c * LPR * 4);
+      }
+#pragma unroll
+      for (int q = 0; q < kFixUnroll; ++q)
+        if (ck + q <= cb) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) { acc[c].x += o[q][c].x; acc[c].y += o[q][c].y; acc[c].z += o[q][c].z; acc[c].w += o[q][c].w; }
+        }
+    }
+  };
+  auto finish = [&](float4 (&acc)[CH], int beg, int end, int64_t seg) {
+    const float inv = mean ? __fdiv_rn(1.0f, (float)(end - beg)) : 1.0f;
+    float* dst = plane + plane_row(g, seg) * C + l * 4;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) st4(dst + c * LPR * 4, make_float4(acc[c].x * inv, acc[c].y * inv, acc[c].z * inv, acc[c].w * inv));
+  };
+  const int cnt = __popc(flagged);
+  for (int t0 = 0; t0 < cnt; t0 += RPI) {
+    const int k = t0 + sub;
+    const bool act = k < cnt;
+    const int src = act ? (int)__fns(flagged, 0, k + 1) : 0;
+    const int beg = __shfl_sync(0xffffffffu, my_beg, src), end = __shfl_sync(0xffffffffu, my_end, src);
+    if (!act) continue;
+    float4 acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sum_range(acc, beg, beg / kChunk, (end - 1) / kChunk);
+    finish(acc, beg, end, base + src);
+  }
+  for (unsigned rest = longs; rest; rest &= rest - 1) {
+    const int src = __ffs(rest) - 1;
+    const int beg = __shfl_sync(0xffffffffu, my_beg, src), end = __shfl_sync(0xffffffffu, my_end, src);
+    const int c0 = beg / kChunk, c1 = (end - 1) / kChunk;
+    const int per = (c1 - c0 + RPI) / RPI;  // chunks per lane group
+    float4 acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sum_range(acc, beg, c0 + sub * per, min(c0 + (sub + 1) * per - 1, c1));
+#pragma unroll
+    for (int off = LPR; off < kWarp; off <<= 1)
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        const float4 o = ld4(src + c * LPR * 4);
+        const float4 o = shfl_xor4(acc[c], off);
         acc[c].x += o.x; acc[c].y += o.y; acc[c].z += o.z; acc[c].w += o.w;
       }
-    }
-    const float inv = mean ? __fdiv_rn(1.0f, (float)(end - beg)) : 1.0f;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) { acc[c].x *= inv; acc[c].y *= inv; acc[c].z *= inv; acc[c].w *= inv; }
+    if (sub == 0) finish(acc, beg, end, base + src);
   }
-  float* dst = plane + plane_row(g, seg) * C + l * 4;
-#pragma unroll
-  for (int c = 0; c < CH; ++c) st4(dst + c * LPR * 4, acc[c]);
 }
 
 // ---- S1 forward: segment max + argmax ---------------------------------------------------------------
@@ -244,51 +297,109 @@ seg_max_rows_kernel(const float* __restrict__ rows, SegGeom g, float* __restrict
 
 template <class RS>
 __global__ void __launch_bounds__(kSegWarps * kWarp)
-seg_max_fix_kernel(SegGeom g, const float* __restrict__ s_val, const int32_t* __restrict__ s_pos,
+seg_max_fix_kernel(SegGeom g, int cpw, const float* __restrict__ s_val, const int32_t* __restrict__ s_pos,
                    float* __restrict__ plane, int32_t* __restrict__ arg) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR;
-  const int64_t seg = ((int64_t)blockIdx.x * kSegWarps + warp) * RPI + sub;
-  if (seg >= g.n_seg) return;
-  const int beg = __ldg(g.cell_start + (seg << g.shift)), end = __ldg(g.cell_start + ((seg + 1) << g.shift));
-  const int c0 = beg / kChunk, c1 = (end - 1) / kChunk;
-  if (beg < end && c0 == c1) return;
-  const int64_t o = plane_row(g, seg) * C + l * 4;
-#pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    float best[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
-    int bpos[4] = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
-    if (beg < end) {
-      for (int ck = c0; ck <= c1; ++ck) {
-        const int slot = (ck * kChunk > beg) ? 0 : 1;
-        const int64_t so = ((int64_t)ck * 2 + slot) * C + (c * LPR + l) * 4;
-        const float4 ov4 = ld4(s_val + so);
-        const int4 op4 = __ldg(reinterpret_cast<const int4*>(s_pos + so));
-        const float ov[4] = {ov4.x, ov4.y, ov4.z, ov4.w};
-        const int op[4] = {op4.x, op4.y, op4.z, op4.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          // partials arrive in ascending position order: strict > keeps the earliest; explicit ranks for coarse levels
-          bool take = ov[q] > best[q];
-          if (g.tie && ov[q] == best[q] && op[q] != INT32_MAX && bpos[q] != INT32_MAX)
-            take = __ldg(g.tie + op[q]) < __ldg(g.tie + bpos[q]);
-          if (take) { best[q] = ov[q]; bpos[q] = op[q]; }
-        }
+  const int64_t base = ((int64_t)blockIdx.x * kSegWarps + warp) * cpw;
+  if (base >= g.n_seg) return;
+  int my_beg = 0, my_end = 0;
+  bool need = false;
+  if (lane < cpw && base + lane < g.n_seg) {
+    my_beg = __ldg(g.cell_start + ((base + lane) << g.shift));
+    my_end = __ldg(g.cell_start + ((base + lane + 1) << g.shift));
+    need = my_beg < my_end && my_beg / kChunk != (my_end - 1) / kChunk;
+    if (my_beg == my_end) {  // empty cell: value 0, arg -1, written by its own lane
+      const int64_t z = plane_row(g, base + lane) * C;
+      for (int c4 = 0; c4 < C / 4; ++c4) {
+        if (plane) st4(plane + z + c4 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        *reinterpret_cast<int4*>(arg + z + c4 * 4) = make_int4(-1, -1, -1, -1);
       }
     }
+  }
+  const bool is_long = need && (my_end - 1) / kChunk - my_beg / kChunk >= kLongList;
+  const unsigned flagged = __ballot_sync(0xffffffffu, need && !is_long);
+  const unsigned longs = __ballot_sync(0xffffffffu, is_long);
+  // does candidate (ov, op) beat (bv, bp)?  larger value; equal values -> earlier original point
+  auto beats = [&](float ov, int op, float bv, int bp) -> bool {
+    if (ov > bv) return true;
+    if (ov == bv && op != INT32_MAX && bp != INT32_MAX) return g.tie ? (__ldg(g.tie + op) < __ldg(g.tie + bp)) : (op < bp);
+    return false;
+  };
+  auto max_range = [&](float (&best)[4], int (&bpos)[4], int c, int beg, int ca, int cb) {
+    for (int ck = ca; ck <= cb; ck += kFixUnroll) {
+      float4 ov4[kFixUnroll];
+      int4 op4[kFixUnroll];
+#pragma unroll
+      for (int q = 0; q < kFixUnroll; ++q) {
+        const int cq = min(ck + q, cb);
+        const int64_t so = ((int64_t)cq * 2 + ((cq * kChunk > beg) ? 0 : 1)) * C + (c * LPR + l) * 4;
+        ov4[q] = ld4(s_val + so);
+        op4[q] = __ldg(reinterpret_cast<const int4*>(s_pos + so));
+      }
+#pragma unroll
+      for (int q = 0; q < kFixUnroll; ++q) {
+        if (ck + q > cb) break;
+        const float ov[4] = {ov4[q].x, ov4[q].y, ov4[q].z, ov4[q].w};
+        const int op[4] = {op4[q].x, op4[q].y, op4[q].z, op4[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (beats(ov[e], op[e], best[e], bpos[e])) { best[e] = ov[e]; bpos[e] = op[e]; }
+      }
+    }
+  };
+  auto emit = [&](const float (&best)[4], const int (&bpos)[4], int c, int64_t seg) {
+    const int64_t o = plane_row(g, seg) * C + (c * LPR + l) * 4;
     float4 v;
     int4 a;
     float* vp = &v.x;
     int* ap = &a.x;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const bool none = bpos[q] == INT32_MAX;
-      vp[q] = none ? 0.0f : best[q];
-      ap[q] = none ? -1 : (g.perm ? __ldg(g.perm + bpos[q]) : bpos[q]);
+    for (int e = 0; e < 4; ++e) {
+      const bool none = bpos[e] == INT32_MAX;
+      vp[e] = none ? 0.0f : best[e];
+      ap[e] = none ? -1 : (g.perm ? __ldg(g.perm + bpos[e]) : bpos[e]);
     }
-    if (plane) st4(plane + o + c * LPR * 4, v);
-    *reinterpret_cast<int4*>(arg + o + c * LPR * 4) = a;
+    if (plane) st4(plane + o, v);
+    *reinterpret_cast<int4*>(arg + o) = a;
+  };
+  const int cnt = __popc(flagged);
+  for (int t0 = 0; t0 < cnt; t0 += RPI) {
+    const int k = t0 + sub;
+    const bool act = k < cnt;
+    const int src = act ? (int)__fns(flagged, 0, k + 1) : 0;
+    const int beg = __shfl_sync(0xffffffffu, my_beg, src), end = __shfl_sync(0xffffffffu, my_end, src);
+    if (!act) continue;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float best[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+      int bpos[4] = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
+      max_range(best, bpos, c, beg, beg / kChunk, (end - 1) / kChunk);
+      emit(best, bpos, c, base + src);
+    }
+  }
+  for (unsigned rest = longs; rest; rest &= rest - 1) {
+    const int src = __ffs(rest) - 1;
+    const int beg = __shfl_sync(0xffffffffu, my_beg, src), end = __shfl_sync(0xffffffffu, my_end, src);
+    const int c0 = beg / kChunk, c1 = (end - 1) / kChunk;
+    const int per = (c1 - c0 + RPI) / RPI;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float best[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+      int bpos[4] = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
+      max_range(best, bpos, c, beg, c0 + sub * per, min(c0 + (sub + 1) * per - 1, c1));
+      // the (value, original point) order is total, so the combination order does not matter
+#pragma unroll
+      for (int off = LPR; off < kWarp; off <<= 1)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best[e], off);
+          const int op = __shfl_xor_sync(0xffffffffu, bpos[e], off);
+          if (beats(ov, op, best[e], bpos[e])) { best[e] = ov; bpos[e] = op; }
+        }
+      if (sub == 0) emit(best, bpos, c, base + src);
+    }
   }
 }
 
@@ -374,6 +485,13 @@ static inline unsigned blocks_for(int64_t items, int per_warp) {
   return (unsigned)((warps + kSegWarps - 1) / kSegWarps);
 }
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+// cells inspected per warp of a fix-up launch: 32 on fine levels (most cells need nothing), fewer on coarse
+// levels (every cell sums several partials) so that the launch still fills the machine
+static inline int fix_cells_per_warp(int64_t n_seg, int rpi) {
+  int cpw = 32;
+  while (cpw > rpi && n_seg / cpw < 8192) cpw >>= 1;
+  return cpw;
+}
 
 }  // namespace t2h
 
@@ -403,7 +521,8 @@ extern "C" int t2h_seg_max_fwd(const float* rows, int64_t n_rows, const int32_t*
   T2H_DISPATCH_ROWSHAPE(C, {
     if (n_rows > 0)
       seg_max_rows_kernel<RS><<<blocks_for(n_chunks_of(n_rows), RS::RPI), kSegWarps * kWarp, 0, s>>>(rows, g, plane, arg, s_val, s_pos);
-    seg_max_fix_kernel<RS><<<blocks_for(n_seg, RS::RPI), kSegWarps * kWarp, 0, s>>>(g, s_val, s_pos, plane, arg);
+    const int cpw = fix_cells_per_warp(n_seg, RS::RPI);
+    seg_max_fix_kernel<RS><<<blocks_for(n_seg, cpw), kSegWarps * kWarp, 0, s>>>(g, cpw, s_val, s_pos, plane, arg);
     if (pooled && n_rows > 0)
       seg_rowmap_kernel<RS, 0><<<blocks_for(n_rows, 32), kSegWarps * kWarp, 0, s>>>(plane, nullptr, nullptr, g, 0, pooled);
   });
@@ -430,7 +549,8 @@ extern "C" int t2h_seg_max_bwd(const float* grad_pooled, const float* grad_plane
     float* sums = (float*)((char*)workspace + align256(slots * sizeof(float)) + align256(slots * sizeof(int32_t)));
     T2H_DISPATCH_ROWSHAPE(C, {
       seg_reduce_rows_kernel<RS><<<blocks_for(n_chunks_of(n_rows), RS::RPI), kSegWarps * kWarp, 0, s>>>(grad_pooled, g, 0, sums, scratch);
-      seg_reduce_fix_kernel<RS><<<blocks_for(n_seg, RS::RPI), kSegWarps * kWarp, 0, s>>>(g, 0, scratch, sums);
+      const int cpw = fix_cells_per_warp(n_seg, RS::RPI);
+      seg_reduce_fix_kernel<RS><<<blocks_for(n_seg, cpw), kSegWarps * kWarp, 0, s>>>(g, 0, cpw, scratch, sums);
     });
     tot = sums;
     extra = grad_plane;
@@ -454,7 +574,8 @@ extern "C" int t2h_seg_reduce_fwd(const float* rows, int64_t n_rows, const int32
   T2H_DISPATCH_ROWSHAPE(C, {
     if (n_rows > 0)
       seg_reduce_rows_kernel<RS><<<blocks_for(n_chunks_of(n_rows), RS::RPI), kSegWarps * kWarp, 0, s>>>(rows, g, mean, plane, scratch);
-    seg_reduce_fix_kernel<RS><<<blocks_for(n_seg, RS::RPI), kSegWarps * kWarp, 0, s>>>(g, mean, scratch, plane);
+    const int cpw = fix_cells_per_warp(n_seg, RS::RPI);
+    seg_reduce_fix_kernel<RS><<<blocks_for(n_seg, cpw), kSegWarps * kWarp, 0, s>>>(g, mean, cpw, scratch, plane);
   });
   T2H_CHECK_LAUNCH();
   return T2H_OK;

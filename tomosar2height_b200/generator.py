@@ -41,7 +41,28 @@ def linear_blend_weight(n_rows, n_cols, half_blend=(0.5, 0.5), min_weight=1e-3, 
     return wx * wy
 
 
+def blend_vectors(n_rows, n_cols, half_blend=(0.5, 0.5), min_weight=1e-3, device="cpu"):
+    """The two 1-D ramps of generator.py:85-113: (wx over the columns, wy over the rows); the window is wy[:, None] * wx."""
+    wx = torch.ones(n_cols, dtype=torch.float64, device=device)
+    wy = torch.ones(n_rows, dtype=torch.float64, device=device)
+    ix, iy = math.floor(n_rows * half_blend[0]), math.floor(n_cols * half_blend[1])
+    if ix > 0:
+        wx[:ix] = torch.linspace(min_weight, 1, ix, dtype=torch.float64, device=device)
+        wx[-ix:] = torch.linspace(1, min_weight, ix, dtype=torch.float64, device=device)
+    if iy > 0:
+        wy[:iy] = torch.linspace(min_weight, 1, iy, dtype=torch.float64, device=device)
+        wy[-iy:] = torch.linspace(1, min_weight, iy, dtype=torch.float64, device=device)
+    return wx, wy
+
+
 class SceneGenerator:
+    """DSMGenerator.generate_dsm (generator.py:115-165) with the scene resident in HBM.
+
+    One sort bins the cloud by stride-sized cells; ONE pair of kernels crops and normalises the points of every
+    tile of the scene (t2h_tile_count / t2h_tile_write) with a single host read of the per-tile counts; the tiles
+    then run through the model in ragged batches (views of that one buffer, no per-tile host work) and every batch
+    is flipped, windowed and accumulated into the float64 rasters by t2h_blend_accumulate."""
+
     def __init__(self, model, scene_min, scene_max, z_bound, patch_size=512.0, stride=256.0, pixel_size=1.0,
                  half_blend=(0.5, 0.5), tiles_per_batch=4):
         self.model = model
@@ -66,60 +87,92 @@ class SceneGenerator:
         cy = ((pts64[:, 1] - self.b) / self.stride).floor().clamp(0, ny - 1).long()
         order = torch.argsort(cy * nx + cx, stable=True)
         starts = torch.searchsorted((cy * nx + cx)[order], torch.arange(nx * ny + 1, device=pts64.device))
-        return pts64[order], starts.tolist(), nx, ny
+        return pts64[order].contiguous(), starts.tolist(), nx, ny
 
-    def _tile_points(self, binned, starts, nx, ny, x0, y0):
-        """Strictly inside (x0, x0+patch) x (y0, y0+patch), normalised to the open unit square (fp32)."""
-        x1, y1 = x0 + self.patch, y0 + self.patch
-        cx0 = min(max(int(math.floor((x0 - self.l) / self.stride)), 0), nx - 1)
-        cx1 = min(max(int(math.floor((x1 - self.l) / self.stride)), 0), nx - 1)
-        cy0 = min(max(int(math.floor((y0 - self.b) / self.stride)), 0), ny - 1)
-        cy1 = min(max(int(math.floor((y1 - self.b) / self.stride)), 0), ny - 1)
-        parts = [binned[starts[cy * nx + cx0]:starts[cy * nx + cx1 + 1]] for cy in range(cy0, cy1 + 1)]
-        cand = torch.cat(parts, 0) if len(parts) > 1 else parts[0]
-        keep = (cand[:, 0] > x0) & (cand[:, 0] < x1) & (cand[:, 1] > y0) & (cand[:, 1] < y1)
-        pts = cand[keep]
-        if pts.shape[0] == 0:
-            return None
-        z_shift = pts[:, 2].min()  # z_shift: 'local_min'
-        norm = torch.stack([(pts[:, 0] - x0) / self.patch, (pts[:, 1] - y0) / self.patch,
-                            (pts[:, 2] - z_shift) / self.z_scale], 1).float()
-        inside = (norm[:, 0] > 0) & (norm[:, 0] < 1) & (norm[:, 1] > 0) & (norm[:, 1] < 1)  # dataset.py:278
-        norm = norm[inside]
-        return norm if norm.shape[0] > 0 else None
+    def _work_items(self, todo, starts, nx, ny):
+        """Candidate row ranges of every tile (the bin cells it overlaps), cut into <= 1024-row work items."""
+        items = []
+        for t, (x0, y0) in enumerate(todo):
+            x1, y1 = x0 + self.patch, y0 + self.patch
+            cx0 = min(max(int(math.floor((x0 - self.l) / self.stride)), 0), nx - 1)
+            cx1 = min(max(int(math.floor((x1 - self.l) / self.stride)), 0), nx - 1)
+            cy0 = min(max(int(math.floor((y0 - self.b) / self.stride)), 0), ny - 1)
+            cy1 = min(max(int(math.floor((y1 - self.b) / self.stride)), 0), ny - 1)
+            for cy in range(cy0, cy1 + 1):
+                first, last = starts[cy * nx + cx0], starts[cy * nx + cx1 + 1]
+                for f in range(first, last, 1024):
+                    items.append((t, min(1024, last - f), f & 0xFFFFFFFF, f >> 32))
+        return items
+
+    def crop_tiles(self, points, todo):
+        """Strict crop + normalisation of every tile in ``todo`` (a list of anchors) in two launches.
+        Returns (flat (P, 4) fp32 rows (x, y, z, 0), per-tile counts as a python list)."""
+        from . import _lib
+        dev = points.device
+        binned, starts, nx, ny = self._bin(points.double())
+        items = self._work_items(todo, starts, nx, ny)
+        n_items, n_tiles = len(items), len(todo)
+        if n_items == 0:
+            return torch.empty(0, 4, device=dev), [0] * n_tiles
+        items_h = torch.tensor(items, dtype=torch.int64)
+        items_d = items_h.to(torch.int32).to(dev).contiguous()  # {tile, count, first_lo, first_hi}: 16 bytes per item
+        tile_xy = torch.tensor(todo, dtype=torch.float64, device=dev).contiguous()
+        item_count = torch.empty(n_items, dtype=torch.int32, device=dev)
+        zmin = torch.full((n_tiles,), -1, dtype=torch.int64, device=dev)
+        _lib.call("t2h_tile_count", _lib.ptr(binned), _lib.ptr(items_d), n_items, _lib.ptr(tile_xy), self.patch,
+                  _lib.ptr(item_count), _lib.ptr(zmin))
+        counts64 = item_count.long()
+        item_offset = (counts64.cumsum(0) - counts64).contiguous()
+        per_tile = torch.zeros(n_tiles, dtype=torch.int64, device=dev).index_add_(0, items_h[:, 0].to(dev), counts64)
+        counts = per_tile.tolist()  # the one host read of the scene
+        out = torch.empty(sum(counts), 4, dtype=torch.float32, device=dev)
+        _lib.call("t2h_tile_write", _lib.ptr(binned), _lib.ptr(items_d), n_items, _lib.ptr(tile_xy), self.patch, self.z_scale,
+                  _lib.ptr(item_offset), _lib.ptr(zmin), _lib.ptr(out))
+        return out, counts
+
+    def raster_window(self, x0, y0):
+        """generator.py:139-154 with RasterData.query_col_row (io_raster.py:123-131): (t_row, l_col) of a tile."""
+        l_col = math.floor((x0 + self.px / 2 - self.l) / self.px)
+        t_row = math.floor((self.t - (y0 + self.patch - self.px / 2)) / self.px)
+        return t_row, l_col
 
     @torch.no_grad()
     def generate(self, points, tile_range=None):
         """points (P, 3) world coordinates on the device (float64 recommended for geo-coordinates).
         Returns (dsm (n_rows, n_cols) float64, weight float64); with ``tile_range`` the un-normalised
         partial sums of that block of tiles (sum the partials of all ranks, then ``finalize``)."""
+        from . import _lib
         dev = points.device
-        binned, starts, nx, ny = self._bin(points.double())
+        todo = list(self.anchors if tile_range is None else [self.anchors[i] for i in tile_range])
+        flat, counts = self.crop_tiles(points, todo)
         dsm = torch.zeros(self.n_rows, self.n_cols, dtype=torch.float64, device=dev)
         weight = torch.zeros_like(dsm)
-        n_px = int(round(self.patch / self.px))
-        window = linear_blend_weight(n_px, n_px, self.half_blend, device=dev)
-        todo = list(self.anchors if tile_range is None else [self.anchors[i] for i in tile_range])
+        S = int(round(self.patch / self.px))
+        wx, wy = blend_vectors(S, S, self.half_blend, device=dev)
+        # non-empty tiles in anchor order (empty tiles are skipped: generator.py:133), their point ranges, windows
+        live = [t for t, c in enumerate(counts) if c > 0]
+        starts, acc = [], 0
+        for c in counts:
+            starts.append(acc)
+            acc += c
+        win = [self.raster_window(*todo[t]) for t in live]
+        t_rows = torch.tensor([w[0] for w in win], dtype=torch.int32, device=dev)
+        l_cols = torch.tensor([w[1] for w in win], dtype=torch.int32, device=dev)
+        bounds = torch.tensor([starts[t] for t in live] + [0], dtype=torch.int64, device=dev)
         self.model.eval()
-        for k in range(0, len(todo), self.tiles_per_batch):
-            batch, clouds = [], []
-            for (x0, y0) in todo[k:k + self.tiles_per_batch]:
-                pts = self._tile_points(binned, starts, nx, ny, x0, y0)
-                if pts is not None:  # empty tiles are skipped (generator.py:133)
-                    batch.append((x0, y0))
-                    clouds.append(pts)
-            if not batch:
-                continue
-            heights = self.model(input_cloud=RaggedCloud.from_list(clouds))[0]  # (B, S, S, 1)
-            for (x0, y0), h in zip(batch, heights):
-                h_grid = h.flip(0).squeeze(-1).double()  # generator.py:147
-                # generator.py:139-154 with RasterData.query_col_row (io_raster.py:123-131)
-                l_col = math.floor((x0 + self.px / 2 - self.l) / self.px)
-                r_col = math.floor((x0 + self.patch - self.px / 2 - self.l) / self.px)
-                b_row = math.floor((self.t - (y0 + self.px / 2)) / self.px)
-                t_row = math.floor((self.t - (y0 + self.patch - self.px / 2)) / self.px)
-                dsm[t_row:b_row + 1, l_col:r_col + 1] += h_grid * window
-                weight[t_row:b_row + 1, l_col:r_col + 1] += window
+        for k in range(0, len(live), self.tiles_per_batch):
+            tiles = live[k:k + self.tiles_per_batch]
+            nb = len(tiles)
+            p0, p1 = starts[tiles[0]], starts[tiles[-1]] + counts[tiles[-1]]
+            # live tiles are contiguous in the flat buffer (empty ones hold no rows); offsets relative to the batch
+            offsets = torch.cat([bounds[k:k + nb] - p0, bounds.new_tensor([p1 - p0])])
+            heights = self.model(input_cloud=RaggedCloud(flat[p0:p1], offsets))[0]  # (B, S, S, 1)
+            rows = [w[0] for w in win[k:k + nb]]
+            cols = [w[1] for w in win[k:k + nb]]
+            r0, c0 = min(rows), min(cols)
+            _lib.call("t2h_blend_accumulate", _lib.ptr(heights.contiguous()), nb, S, _lib.ptr(t_rows[k:k + nb]),
+                      _lib.ptr(l_cols[k:k + nb]), _lib.ptr(wx), _lib.ptr(wy), r0, c0, max(rows) + S - r0, max(cols) + S - c0,
+                      self.n_rows, self.n_cols, _lib.ptr(dsm), _lib.ptr(weight))
         if tile_range is not None:
             return dsm, weight
         return self.finalize(dsm, weight), weight
