@@ -155,3 +155,15 @@ def test_absmax_registry_never_returns_a_stale_entry():
     b = a.clone()
     reg.put(a, slot)
     assert reg.get(b) is None                         # equal contents, different storage
+
+
+def test_ctypes_signatures_have_the_arity_of_the_header():
+    """A missing argtype (e.g. the trailing stream) makes ctypes pass a 64-bit handle as a C int."""
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "t2h.h")).read(), flags=re.S)
+    seen = 0
+    for m in re.finditer(r"\b(?:int|size_t|const char\*)\s+(t2h_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        n = 0 if args in ("void", "") else len(args.split(","))
+        assert n == len(_lib.SIGNATURES[name]), (name, n, len(_lib.SIGNATURES[name]))
+        seen += 1
+    assert seen == len(_lib.SIGNATURES)
