@@ -70,3 +70,67 @@ def test_flat_gradients_are_views_of_one_buffer():
     assert net.weight.grad.data_ptr() == flat.flat.data_ptr()
     flat.zero_()
     assert float(net.weight.grad.abs().sum()) == 0.0 and flat.nbytes == 15 * 4
+
+
+def test_flat_gradients_survive_zero_grad_set_to_none():
+    """The reference trainer calls optimizer.zero_grad() (trainer.py:89), whose default sets every .grad to None:
+    FlatGradients must notice and re-home the gradients instead of reducing a stale buffer."""
+    net = torch.nn.Linear(4, 3)
+    flat = FlatGradients(net)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    net(torch.ones(2, 4)).sum().backward()
+    opt.zero_grad()                                   # set_to_none=True: grads leave the buffer
+    assert net.weight.grad is None
+    net(torch.ones(2, 4)).sum().backward()           # autograd allocates fresh gradients outside the buffer
+    assert net.weight.grad.data_ptr() != flat.flat.data_ptr()
+    want = torch.cat([p.grad.flatten().clone() for p in net.parameters()])
+    assert flat.verify() == 2                         # both re-homed, values carried over
+    assert net.weight.grad.data_ptr() == flat.flat.data_ptr()
+    assert torch.equal(flat.flat, want)
+    flat.all_reduce()                                 # single process: a no-op, but it verifies first
+    assert flat.verify() == 0
+    opt.zero_grad()
+    flat.zero_()                                      # None grads are re-homed as zeros
+    assert net.bias.grad is not None and float(flat.flat.abs().sum()) == 0.0
+
+
+def _trainer_worker(rank, world, port, out):
+    """Trainer.train_step accumulation (trainer.py:70-89) on CPU stand-ins: grads summed over ranks once per
+    optimizer step, identical parameters afterwards."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tomosar2height_b200.trainer import Trainer
+
+        class Toy(torch.nn.Module):   # same call signature / outputs as TomoSAR2Height.forward
+            def __init__(self):
+                super().__init__()
+                torch.manual_seed(0)
+                self.fc = torch.nn.Linear(3, 16)
+
+            def forward(self, input_cloud=None, input_image=None):
+                return self.fc(input_cloud.mean(1)).view(-1, 4, 4, 1), None
+
+        model = Toy()
+        opt = torch.optim.SGD(model.parameters(), lr=0.5)
+        tr = Trainer(model, opt, micro_batch=2, use_cuda_graph=False, optimize_every=3)
+        g = torch.Generator().manual_seed(rank)
+        stepped_at = []
+        for k in range(6):
+            cloud = torch.rand(1, 10, 3, generator=g)
+            loss, stepped = tr.train_step({"inputs": cloud, "dsm": torch.ones(1, 4, 4)})
+            if stepped:
+                stepped_at.append(k)
+        out[rank] = (stepped_at, model.fc.weight.detach().clone())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_accumulates_and_reduces_once_per_step():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_trainer_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0][0] == out[1][0] == [2, 5]              # an optimizer step every 3 tiles per rank
+    assert torch.allclose(out[0][1], out[1][1])          # replicas stay identical: gradients were summed over ranks

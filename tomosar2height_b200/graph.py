@@ -34,6 +34,7 @@ class GraphedTrainStep:
                 loss_fn(model, *self.static_inputs).backward()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._grad_homes = [(p, p.grad.data_ptr()) for p in model.parameters() if p.requires_grad and p.grad is not None]
         self.graph = torch.cuda.CUDAGraph()
         _linear.capture_mode = True
         try:
@@ -45,6 +46,12 @@ class GraphedTrainStep:
             _linear.capture_mode = False
 
     def __call__(self, *inputs):
+        # the graph accumulates into the gradient tensors that existed at capture time: a parameter whose .grad was
+        # replaced since (optimizer.zero_grad(set_to_none=True)) would silently get no update
+        for p, ptr in self._grad_homes:
+            if p.grad is None or p.grad.data_ptr() != ptr:
+                raise RuntimeError("GraphedTrainStep: a parameter's .grad was replaced after capture (use "
+                                   "FlatGradients.zero_() / zero_grad(set_to_none=False) between optimizer steps)")
         for s, t in zip(self.static_inputs, inputs):
             s.copy_(t, non_blocking=True)
         self.graph.replay()

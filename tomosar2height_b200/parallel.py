@@ -18,24 +18,54 @@ def shard_tiles(n_tiles: int, rank: int, world: int):
 
 class FlatGradients:
     """Re-homes every parameter's ``.grad`` into one contiguous buffer so that the whole model is
-    reduced by ONE collective (NCCL picks NVLS / NVSwitch on a B200 box)."""
+    reduced by ONE collective (NCCL picks NVLS / NVSwitch on a B200 box).
+
+    The buffer only stays the gradients' home while nobody replaces ``p.grad``: ``optimizer.zero_grad()`` (the
+    reference calls it, trainer.py:89) defaults to ``set_to_none=True`` and would silently detach every gradient
+    from the buffer.  Use ``zero_()`` / ``zero_grad()`` of this class instead; ``all_reduce`` re-checks the
+    homes (``verify``) and re-installs them, carrying over gradients that were accumulated elsewhere."""
 
     def __init__(self, module: torch.nn.Module):
         self.params = [p for p in module.parameters() if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        self._views = []
         offset = 0
         for p in self.params:
             n = p.numel()
             # as_strided keeps the parameter's own (e.g. channels_last) strides
-            p.grad = self.flat[offset:offset + n].as_strided(p.shape, p.stride())
+            view = self.flat[offset:offset + n].as_strided(p.shape, p.stride())
+            self._views.append(view)
+            p.grad = view
             offset += n
 
     def zero_(self):
+        self.verify()
         self.flat.zero_()
 
+    zero_grad = zero_
+
+    def verify(self):
+        """Every ``p.grad`` must still be its view of the flat buffer.  A gradient that was set to None is
+        re-homed (its slice zeroed); one that was re-allocated elsewhere is copied in and re-homed.
+        Returns the number of gradients that had to be repaired."""
+        repaired = 0
+        for p, view in zip(self.params, self._views):
+            g = p.grad
+            if g is not None and g.data_ptr() == view.data_ptr() and g.stride() == view.stride():
+                continue
+            with torch.no_grad():
+                if g is None:
+                    view.zero_()
+                else:
+                    view.copy_(g)
+            p.grad = view
+            repaired += 1
+        return repaired
+
     def all_reduce(self, async_op=False):
+        self.verify()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
         return None
