@@ -11,6 +11,9 @@ from .encoder import encoder_dict  # noqa: F401
 from .block import ResnetBlockFC  # noqa: F401
 from .config import berlin_config, munich_config, Config, to_config  # noqa: F401
 from .topology import RaggedCloud  # noqa: F401
+from .adapters import load_config, ChunkCloud, write_raster, read_raster  # noqa: F401
+from .trainer import Trainer  # noqa: F401
+from .generator import SceneGenerator  # noqa: F401
 
 
 def install_as_reference():
