@@ -53,19 +53,23 @@ int t2h_cell_index(const float* xy, int64_t n_points, int64_t point_stride, int 
 
 /* ---- topology (replaces the 10-12 index recomputations per forward: pointnet.py:70,
  *      alto.py:80,190) ------------------------------------------------------------------- */
-/* keys[i] = b*reso^2 + code(ix,iy), cell coordinates clamped to [0, reso-1]; b = i / n_per_batch */
+/* keys[i] = b*reso^2 + code(ix,iy) with (ix, iy) = trunc(x*reso), trunc(y*reso) as coordinate2index computes them;
+ * b = i / n_per_batch.  The reference does not clamp (it relies on the crop of dataset.py:278 and fails in
+ * torch_scatter otherwise): a point outside [0, 1)^2 (or NaN) is binned into the nearest border cell and
+ * *range_flag (nullable device word) is set non-zero, so that the caller can raise like the reference would. */
 int t2h_xy_keys(const float* xyz, int64_t n_points, int64_t point_stride, int64_t n_per_batch,
-                int reso, int morton, int32_t* keys, t2h_stream_t stream);
+                int reso, int morton, int32_t* keys, int32_t* range_flag, t2h_stream_t stream);
 /* ragged batches (tiles with different point counts, flat cloud + offsets[n_tiles + 1] on the device):
  * b = the tile whose range [offsets[b], offsets[b+1]) holds point i */
 int t2h_xy_keys_ragged(const float* xyz, int64_t n_points, int64_t point_stride, const int64_t* offsets,
-                       int n_tiles, int reso, int morton, int32_t* keys, t2h_stream_t stream);
+                       int n_tiles, int reso, int morton, int32_t* keys, int32_t* range_flag, t2h_stream_t stream);
 /* keys[i] = b*dim_size + index[i]; *flag set non-zero if an index is outside [0, dim_size) */
 int t2h_index_keys(const int64_t* index, int64_t n_points, int64_t n_per_batch, int64_t dim_size,
                    int32_t* keys, int32_t* flag, t2h_stream_t stream);
 size_t t2h_sort_workspace_bytes(int64_t n_points);
-/* stable sort by key; writes keys_sorted[n], perm[n] (sorted position -> input position) and
- * cell_start[n_keys + 1] (first sorted position of every key; cell_start[n_keys] = n) */
+/* stable sort by key (hand-written LSD radix sort, 8 bits per pass over the ceil(log2 n_keys) key bits: per-tile digit
+ * histograms, per-digit scan, warp-ranked stable scatter); writes keys_sorted[n], perm[n] (sorted position -> input
+ * position) and cell_start[n_keys + 1] (first sorted position of every key; cell_start[n_keys] = n; nullable) */
 int t2h_sort_by_cell(const int32_t* keys, int64_t n_points, int64_t n_keys, void* workspace,
                      size_t workspace_bytes, int32_t* keys_sorted, int32_t* perm,
                      int32_t* cell_start, t2h_stream_t stream);

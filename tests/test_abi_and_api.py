@@ -47,7 +47,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.t2h_seg_reduce_fwd(None, 8, None, None, None, 8, 0, 32, 0, 4, 1, None, 0, None, None) == 1
     assert lib.t2h_seg_mean_fwd(None, 8, None, None, None, 8, 0, 32, 0, 4, None, 0, None, None) == 1
     assert lib.t2h_seg_workspace_bytes(1 << 20, 1 << 16, 32) >= (1 << 20) // 32 * 2 * 32 * 8
-    assert lib.t2h_xy_keys(None, 0, 3, 1, 100, 1, None, None) == 1
+    assert lib.t2h_xy_keys(None, 0, 3, 1, 100, 1, None, None, None) == 1
 
 
 @pytest.mark.parametrize("name", list(CASES) + ["berlin_full", "berlin_image_full", "munich_full", "munich_image_full"])

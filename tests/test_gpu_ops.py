@@ -306,3 +306,39 @@ def test_determinism(T):
         outs.append((plane.clone(), x.grad.clone()))
     for p, gq in outs[1:]:
         assert torch.equal(p, outs[0][0]) and torch.equal(gq, outs[0][1]), "bitwise run-to-run determinism"
+
+
+@pytest.mark.parametrize("n,n_keys", [(1, 5), (33, 2), (5000, 1), (100000, 255), (100000, 257), (1 << 20, 4 * 65536),
+                                      (300000, (1 << 24) + 3), (70001, (1 << 31) - 2)])
+def test_radix_sort_matches_torch_stable_sort(n, n_keys):
+    """The hand-written LSD radix sort (t2h_sort_by_cell): keys sorted, STABLE (equal keys keep input order),
+    cell_start = exclusive histogram scan; 1 to 4 eight-bit passes."""
+    from tomosar2height_b200.topology import sort_keys
+    g = torch.Generator().manual_seed(n % 1000 + 1)
+    keys = torch.randint(0, min(n_keys, 1 << 31) , (n,), generator=g, dtype=torch.int64)
+    keys[: n // 3] = keys[0]  # long runs of equal keys
+    k32 = keys.to(torch.int32).cuda()
+    keys_sorted, perm, cell_start = sort_keys(k32, n_keys, with_cell_start=n_keys <= 4 * 65536)
+    want_k, want_p = torch.sort(keys, stable=True)
+    assert torch.equal(keys_sorted.cpu().long(), want_k)
+    assert torch.equal(perm.cpu().long(), want_p)
+    if n_keys <= 4 * 65536:
+        hist = torch.bincount(keys, minlength=n_keys)
+        want = torch.cat([torch.zeros(1, dtype=torch.long), hist.cumsum(0)])
+        assert torch.equal(cell_start.cpu().long(), want)
+
+
+def test_out_of_range_points_are_flagged():
+    """coordinate2index does not clamp and torch_scatter would fail on such an index; the topology bins the point
+    into a border cell (no kernel can run out of bounds) and raises on request."""
+    from tomosar2height_b200.topology import Topology
+    cloud = synthetic_cloud(1, 500, seed=2)
+    ok = Topology(cloud.cuda(), 32, check_range=True)
+    assert int(ok.range_flag.item()) == 0
+    for bad in (1.0, -1e-3, float("nan")):
+        c = cloud.clone()
+        c[0, 7, 0] = bad
+        t = Topology(c.cuda(), 32)
+        assert int(t.range_flag.item()) == 1 and int(t.cell_start[-1]) == 500
+        with pytest.raises(IndexError):
+            Topology(c.cuda(), 32, check_range=True)

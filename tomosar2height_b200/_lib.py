@@ -25,8 +25,8 @@ SIGNATURES = {
     "t2h_abi_version": [],
     "t2h_status_string": [_i32],
     "t2h_cell_index": [_p, _i64, _i64, _i32, _p, _p],
-    "t2h_xy_keys": [_p, _i64, _i64, _i64, _i32, _i32, _p, _p],
-    "t2h_xy_keys_ragged": [_p, _i64, _i64, _p, _i32, _i32, _i32, _p, _p],
+    "t2h_xy_keys": [_p, _i64, _i64, _i64, _i32, _i32, _p, _p, _p],
+    "t2h_xy_keys_ragged": [_p, _i64, _i64, _p, _i32, _i32, _i32, _p, _p, _p],
     "t2h_index_keys": [_p, _i64, _i64, _i64, _p, _p, _p],
     "t2h_sort_workspace_bytes": [_i64],
     "t2h_sort_by_cell": [_p, _i64, _i64, _p, _sz, _p, _p, _p, _p],
@@ -130,8 +130,16 @@ def load():
     return _lib
 
 
+_seen = threading.local()  # device of the tensors handed to the pending call
+
+
 def ptr(t):
-    return None if t is None else t.data_ptr()
+    """raw device pointer of a tensor argument (None -> NULL); remembers the tensor's device for ``call``"""
+    if t is None:
+        return None
+    if t.is_cuda:
+        _seen.device = t.device.index
+    return t.data_ptr()
 
 
 def stream():
@@ -148,6 +156,13 @@ def call(name: str, *args):
     """Invoke a status-returning entry point on the current stream; raise RuntimeError on failure."""
     global launch_count
     launch_count += 1
+    # kernels are enqueued on the current stream of the CURRENT device: tensors living elsewhere would be touched by
+    # the wrong GPU (and per-device kernel attributes would be missing) -- fail loudly instead
+    dev = getattr(_seen, "device", None)
+    _seen.device = None
+    if dev is not None and dev != torch.cuda.current_device():
+        raise RuntimeError(f"{name}: tensors live on cuda:{dev} but the current device is cuda:{torch.cuda.current_device()}; "
+                           f"run the model under torch.cuda.device({dev}) (one process per GPU)")
     check(getattr(load(), name)(*args, stream()), name)
 
 

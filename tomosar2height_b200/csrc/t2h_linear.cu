@@ -1222,12 +1222,25 @@ __global__ void split_f16_kernel(const float* __restrict__ w, int64_t n2, const 
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+// Kernel-variant switches of the design study.  The product build fixes them at compile time -- the
+// entry points read no environment and keep no state; -DT2H_ABLATION_ENV re-enables the environment overrides.
+static inline int ablation_switch(const char* name, int product_value) {
+#ifdef T2H_ABLATION_ENV
+  const char* e = getenv(name);
+  return e ? atoi(e) : product_value;
+#else
+  (void)name;
+  return product_value;
+#endif
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// the driver entry point is looked up once (an immutable function pointer, initialised thread-safely)
 static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+  static const EncodeTiledFn fn = []() -> EncodeTiledFn {
     void* ptr = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
@@ -1285,13 +1298,10 @@ static int launch_linear_persistent(const CUtensorMap& x1, const CUtensorMap& x2
                                     cudaStream_t stream) {
   auto kern = linear_x3_persistent_kernel<F16, BLOCK_N, WSTEPS, PAIR>;
   using S = PSmem<F16, BLOCK_N, WSTEPS, PAIR>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return T2H_ERR_CUDA;
-    }
-    configured = true;
+  // per device and idempotent; set on every launch so that the entry point keeps no state
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return T2H_ERR_CUDA;
   }
   const int64_t tiles = ((args.rows + BLOCK_M - 1) / BLOCK_M) * ((args.n_out + BLOCK_N - 1) / BLOCK_N);
   unsigned grid = (unsigned)(tiles < kSMs ? tiles : kSMs);
@@ -1344,18 +1354,15 @@ static int launch_linear(const CUtensorMap& x1, const CUtensorMap& x2, const flo
   }
   {
     // T2H_LINEAR_NONPERSISTENT=1 (ablation): the one-tile-per-CTA kernels below; =2: only for the narrow tiles
-    static const int one_tile = []() { const char* e = getenv("T2H_LINEAR_NONPERSISTENT"); return e ? atoi(e) : 0; }();
+    const int one_tile = ablation_switch("T2H_LINEAR_NONPERSISTENT", 0);
     if (one_tile == 0 || (one_tile == 2 && BLOCK_N == 128))
       return launch_linear_persistent<false, BLOCK_N>(x1, x2, whi, wlo, mout, maux, args, stream);
   }
   auto kern = linear_tf32x3_kernel<BLOCK_N, A_TMEM, STAGES_>;
-  static bool configured = false;  // idempotent attribute, racing threads set the same value
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BLOCK_N, A_TMEM, STAGES_>::TOTAL) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return T2H_ERR_CUDA;
-    }
-    configured = true;
+  // per device and idempotent; set on every launch so that the entry point keeps no state
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BLOCK_N, A_TMEM, STAGES_>::TOTAL) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return T2H_ERR_CUDA;
   }
   const int64_t tiles = ((args.rows + BLOCK_M - 1) / BLOCK_M) * ((args.n_out + BLOCK_N - 1) / BLOCK_N);
   if (tiles > 0x7fffffffLL) return T2H_ERR_UNSUPPORTED_SHAPE;
@@ -1407,8 +1414,7 @@ extern "C" int t2h_linear_fwd(const float* x1, int64_t ld_x1, int k1, const floa
   a.x_absmax = a.w_absmax = nullptr; a.out_absmax = nullptr;
   const int k_total = k1 + k2;
   cudaStream_t s = (cudaStream_t)stream;
-  static const int ss_only = []() { const char* e = getenv("T2H_LINEAR_SS"); return e ? atoi(e) : 0; }();  // ablation
-  static const int deep = []() { const char* e = getenv("T2H_LINEAR_DEEP"); return e ? atoi(e) : 0; }();  // ablation
+  const int ss_only = ablation_switch("T2H_LINEAR_SS", 0), deep = ablation_switch("T2H_LINEAR_DEEP", 0);
   const bool shallow = a.k_chunks <= 2 && !deep;
   if (n_out <= 32) return shallow ? launch_linear<32, false, 1>(m1, m2, w_hi, w_lo, k_total, a, s)
                                   : launch_linear<32, false, 2>(m1, m2, w_hi, w_lo, k_total, a, s);
@@ -1511,7 +1517,7 @@ extern "C" int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const 
   if (bn == 64) return launch_linear_persistent<true, 64>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
   // CTA pairs (cta_group::2) for 128-wide tiles; T2H_LINEAR_PAIR=0 falls back to one CTA per tile (ablation).
   // The weight maps then have 64-row boxes (each CTA of a pair stages half of the weight tile).
-  static const int pair = []() { const char* e = getenv("T2H_LINEAR_PAIR"); return e ? atoi(e) : 1; }();
+  const int pair = ablation_switch("T2H_LINEAR_PAIR", 1);
   if (pair && rows >= 2 * BLOCK_M) {
     CUtensorMap whi2, wlo2;
     if (!make_map_f16(&whi2, w_hi, k_total, n_out, 64) || !make_map_f16(&wlo2, w_lo, k_total, n_out, 64)) return T2H_ERR_CUDA;
@@ -1521,7 +1527,7 @@ extern "C" int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const 
   // default -- measured: it halves the L2 -> SM tile traffic but leaves only 2 x-stages (64 KB in flight) for
   // K = 256, and the layer gets SLOWER (256 -> 512: 0.53 vs 0.44 ms), i.e. these layers are bound by the depth
   // of the load pipeline, not by the fabric; K = 128 (4 stages) is a wash (0.154 vs 0.157 ms).
-  static const int wres = []() { const char* e = getenv("T2H_LINEAR_WRES"); return e ? atoi(e) : 0; }();
+  const int wres = ablation_switch("T2H_LINEAR_WRES", 0);
   const int n_steps = (a.k_chunks + 1) / 2, n_tiles128 = (n_out + 127) / 128;
   if (wres && n_tiles128 <= kSMs) {
     if (n_steps <= 2) return launch_linear_persistent<true, 128, 2>(m1, m2, whi, wlo, mout, maux, a, (cudaStream_t)stream);
@@ -1596,7 +1602,7 @@ extern "C" int t2h_conv3x3_fwd_f16(const float* x, int B, int H, int W, int cin,
   }
   if (bn == 32) return launch_linear_persistent<true, 32>(mx, mx, whi, wlo, mout, maux, a, s);
   if (bn == 64) return launch_linear_persistent<true, 64>(mx, mx, whi, wlo, mout, maux, a, s);
-  static const int pair = []() { const char* e = getenv("T2H_LINEAR_PAIR"); return e ? atoi(e) : 1; }();
+  const int pair = ablation_switch("T2H_LINEAR_PAIR", 1);
   if (pair && a.rows >= 2 * BLOCK_M) {
     CUtensorMap whi2, wlo2;
     if (!make_map_f16(&whi2, w_hi, k_total, cout, 64) || !make_map_f16(&wlo2, w_lo, k_total, cout, 64)) return T2H_ERR_CUDA;
@@ -1627,13 +1633,10 @@ extern "C" size_t t2h_linear_wgrad_workspace_bytes(int64_t rows, int n_out, int 
 template <int BLOCK_N, bool F16 = false>
 static int launch_wgrad(const CUtensorMap& mg, const CUtensorMap& mx, WgradArgs a, int splits, cudaStream_t stream) {
   auto kern = wgrad_x3_kernel<BLOCK_N, F16>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<BLOCK_N, F16>::TOTAL) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return T2H_ERR_CUDA;
-    }
-    configured = true;
+  // per device and idempotent; set on every launch so that the entry point keeps no state
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<BLOCK_N, F16>::TOTAL) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return T2H_ERR_CUDA;
   }
   dim3 grid((unsigned)((a.n_out + BLOCK_M - 1) / BLOCK_M), (unsigned)((a.k_in + BLOCK_N - 1) / BLOCK_N), (unsigned)splits);
   kern<<<grid, WG_THREADS, WgSmem<BLOCK_N, F16>::TOTAL, stream>>>(mg, mx, a);

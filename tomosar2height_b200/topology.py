@@ -3,9 +3,14 @@
 Replaces the per-call ``coordinate2index`` + atomic scatter of the reference
 (pointnet.py:69-70, alto.py:79-80,189-190).  See include/t2h.h for the key layout.
 """
+import os
+
 import torch
 
 from . import _lib
+
+
+_CHECK_RANGE = os.environ.get("T2H_CHECK_RANGE", "0") == "1"
 
 
 def _is_pow2(v: int) -> bool:
@@ -76,9 +81,14 @@ class Topology:
       morton      bool          : Morton keys (power-of-two R) -> coarser levels share the sort
     """
 
-    def __init__(self, xyz: torch.Tensor, reso: int, offsets: torch.Tensor = None):
+    def __init__(self, xyz: torch.Tensor, reso: int, offsets: torch.Tensor = None, check_range: bool = False):
         """xyz (B, N, >=2) for a dense batch, or -- with ``offsets`` (B+1,) int64 on the device -- the flat
-        (P, >=2) cloud of a RAGGED batch whose tile b owns the points [offsets[b], offsets[b+1])."""
+        (P, >=2) cloud of a RAGGED batch whose tile b owns the points [offsets[b], offsets[b+1]).
+
+        The reference does not clamp cell coordinates: a point outside [0, 1)^2 makes torch_scatter raise on the
+        index (coordinate.py:24-26, dataset.py:278 keeps real data inside).  The kernels bin such points into the
+        border cells and raise a device flag, ``range_flag``; ``check_range=True`` (or env T2H_CHECK_RANGE=1) reads
+        it (one host sync) and raises IndexError like the reference path would."""
         _lib.require_cuda_f32(xyz, "Topology(xyz)")
         ragged = offsets is not None
         if xyz.dim() != (2 if ragged else 3) or xyz.shape[-1] < 2:
@@ -98,13 +108,19 @@ class Topology:
             self.B, self.N = offsets.numel() - 1, None
             n = xyz.shape[0]
             keys = torch.empty(n, dtype=torch.int32, device=dev)
+            self.range_flag = torch.zeros(1, dtype=torch.int32, device=dev)
             _lib.call("t2h_xy_keys_ragged", _lib.ptr(xyz), n, self.D, _lib.ptr(offsets.contiguous()), self.B, self.reso,
-                      int(self.morton), _lib.ptr(keys))
+                      int(self.morton), _lib.ptr(keys), _lib.ptr(self.range_flag))
         else:
             self.B, self.N = xyz.shape[0], xyz.shape[1]
             n = self.B * self.N
             keys = torch.empty(n, dtype=torch.int32, device=dev)
-            _lib.call("t2h_xy_keys", _lib.ptr(xyz), n, self.D, self.N, self.reso, int(self.morton), _lib.ptr(keys))
+            self.range_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.call("t2h_xy_keys", _lib.ptr(xyz), n, self.D, self.N, self.reso, int(self.morton), _lib.ptr(keys),
+                      _lib.ptr(self.range_flag))
+        if check_range or _CHECK_RANGE:
+            if int(self.range_flag.item()) != 0:
+                raise IndexError(f"Topology: a point lies outside the unit square [0, 1)^2 (cell index out of range for reso {self.reso})")
         self.n_points = n
         n_keys = self.B * self.reso * self.reso
         self.keys_sorted, self.perm, self.cell_start = sort_keys(keys, n_keys)
@@ -158,8 +174,9 @@ class Topology:
         return scatter_rows(rows, self.perm)
 
 
-def sort_keys(keys: torch.Tensor, n_keys: int):
-    """Stable sort of int32 keys -> (keys_sorted, perm, cell_start[n_keys + 1])."""
+def sort_keys(keys: torch.Tensor, n_keys: int, with_cell_start: bool = True):
+    """Stable sort of int32 keys in [0, n_keys) -> (keys_sorted, perm, cell_start[n_keys + 1]).
+    ``with_cell_start=False``: a plain stable sort (no first-position table)."""
     n = keys.numel()
     dev = keys.device
     lib = _lib.load()
@@ -167,7 +184,7 @@ def sort_keys(keys: torch.Tensor, n_keys: int):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     keys_sorted = torch.empty_like(keys)
     perm = torch.empty_like(keys)
-    cell_start = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+    cell_start = torch.empty(n_keys + 1, dtype=torch.int32, device=dev) if with_cell_start else None
     _lib.call("t2h_sort_by_cell", _lib.ptr(keys), n, n_keys, _lib.ptr(ws), ws_bytes, _lib.ptr(keys_sorted),
               _lib.ptr(perm), _lib.ptr(cell_start))
     return keys_sorted, perm, cell_start
