@@ -14,8 +14,11 @@ Parameters stay the modules' own fp32 ``weight`` / ``bias`` (checkpoints unchang
 logical (B, C, H, W) views with channels_last strides used everywhere in the model.  Shapes the
 kernels do not cover (Cin or Cout not a multiple of 32, planes narrower than 16) fall back to cuDNN.
 """
+from typing import Optional, Tuple
+
 import torch
 import torch.nn.functional as F
+from torch import Tensor
 
 from . import _lib
 from ._lib import ptr
@@ -46,47 +49,78 @@ def _launch_conv(x, split, cout, bias, relu_in, mask, out):
               None, ptr(out))
 
 
-class _Conv3x3TC(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, bias, relu_in):
-        """x: channels-last (B, H, W, Cin) contiguous; returns (B, H, W, Cout)."""
-        B, H, W, cin = x.shape
-        cout = weight.shape[0]
-        split = _cache.get_matrix(weight, "conv3x3_fwd", _fwd_matrix, f16=_linear.USE_F16)
-        out = torch.empty(B, H, W, cout, dtype=torch.float32, device=x.device)
-        _launch_conv(x, split, cout, bias, relu_in, None, out)
-        ctx.save_for_backward(x, weight)
-        ctx.relu_in = relu_in
-        ctx.has_bias = bias is not None
-        return out
+# t2h::conv3x3 / t2h::conv3x3_bwd -- the 3x3 / padding 1 convolution and its backward as torch custom ops over
+# t2h_conv3x3_fwd[_f16] / t2h_conv3x3_wgrad[_f16]
+@torch.library.custom_op("t2h::conv3x3", mutates_args=())
+def _conv3x3_op(x: Tensor, weight: Tensor, bias: Optional[Tensor], relu_in: bool) -> Tensor:
+    """x: channels-last (B, H, W, Cin) contiguous; returns (B, H, W, Cout)."""
+    x = x.contiguous()
+    B, H, W, cin = x.shape
+    cout = weight.shape[0]
+    split = _cache.get_matrix(weight, "conv3x3_fwd", _fwd_matrix, f16=_linear.USE_F16)
+    out = torch.empty(B, H, W, cout, dtype=torch.float32, device=x.device)
+    _launch_conv(x, split, cout, bias, relu_in, None, out)
+    return out
 
-    @staticmethod
-    def backward(ctx, g):
-        x, weight = ctx.saved_tensors
-        g = g.contiguous()
-        B, H, W, cin = x.shape
-        cout = weight.shape[0]
-        d_x = d_w = d_b = None
-        if ctx.needs_input_grad[0]:
-            split = _cache.get_matrix(weight, "conv3x3_dgrad", _dgrad_matrix, f16=_linear.USE_F16)
-            d_x = torch.empty_like(x)
-            _launch_conv(g, split, cin, None, False, x if ctx.relu_in else None, d_x)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            lib = _lib.load()
-            ws_bytes = int(lib.t2h_conv3x3_wgrad_workspace_bytes(B, H, W, cin, cout))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
-            d_wm = torch.empty(cout, 9 * cin, dtype=torch.float32, device=g.device)
-            if ctx.has_bias:
-                d_b = torch.empty(cout, dtype=torch.float32, device=g.device)
-            if _linear.USE_F16_WGRAD:
-                _lib.call("t2h_conv3x3_wgrad_f16", ptr(g), ptr(operand_absmax(g.view(-1, cout), owner=g)), ptr(x),
-                          ptr(operand_absmax(x.view(-1, cin), owner=x)), B, H, W, cin, cout, int(ctx.relu_in), ptr(ws),
-                          ws_bytes, ptr(d_wm), ptr(d_b))
-            else:
-                _lib.call("t2h_conv3x3_wgrad", ptr(g), ptr(x), B, H, W, cin, cout, int(ctx.relu_in), ptr(ws), ws_bytes,
-                          ptr(d_wm), ptr(d_b))
-            d_w = d_wm.view(cout, 3, 3, cin).permute(0, 3, 1, 2)
-        return d_x, d_w, d_b, None
+
+@_conv3x3_op.register_fake
+def _(x, weight, bias, relu_in):
+    return x.new_empty(x.shape[0], x.shape[1], x.shape[2], weight.shape[0])
+
+
+@torch.library.custom_op("t2h::conv3x3_bwd", mutates_args=())
+def _conv3x3_bwd_op(g: Tensor, x: Tensor, weight: Tensor, relu_in: bool, has_bias: bool, need_x: bool,
+                    need_w: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """(d_x, d_weight (Cout, Cin, 3, 3), d_bias); a gradient that is not needed comes back empty."""
+    g = g.contiguous()
+    x = x.contiguous()
+    B, H, W, cin = x.shape
+    cout = weight.shape[0]
+    d_x, d_w, d_b = (g.new_empty(0) for _ in range(3))  # distinct tensors: op outputs must not alias
+    if need_x:
+        split = _cache.get_matrix(weight, "conv3x3_dgrad", _dgrad_matrix, f16=_linear.USE_F16)
+        d_x = torch.empty_like(x)
+        _launch_conv(g, split, cin, None, False, x if relu_in else None, d_x)
+    if need_w or has_bias:
+        lib = _lib.load()
+        ws_bytes = int(lib.t2h_conv3x3_wgrad_workspace_bytes(B, H, W, cin, cout))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+        d_wm = torch.empty(cout, 9 * cin, dtype=torch.float32, device=g.device)
+        if has_bias:
+            d_b = torch.empty(cout, dtype=torch.float32, device=g.device)
+        if _linear.USE_F16_WGRAD:
+            _lib.call("t2h_conv3x3_wgrad_f16", ptr(g), ptr(operand_absmax(g.view(-1, cout), owner=g)), ptr(x),
+                      ptr(operand_absmax(x.view(-1, cin), owner=x)), B, H, W, cin, cout, int(relu_in), ptr(ws),
+                      ws_bytes, ptr(d_wm), ptr(d_b) if has_bias else None)
+        else:
+            _lib.call("t2h_conv3x3_wgrad", ptr(g), ptr(x), B, H, W, cin, cout, int(relu_in), ptr(ws), ws_bytes,
+                      ptr(d_wm), ptr(d_b) if has_bias else None)
+        d_w = d_wm.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+    return d_x, d_w, d_b
+
+
+@_conv3x3_bwd_op.register_fake
+def _(g, x, weight, relu_in, has_bias, need_x, need_w):
+    e = g.new_empty(0)
+    return (torch.empty_like(x) if need_x else e, torch.empty_like(weight) if (need_w or has_bias) else e,
+            g.new_empty(weight.shape[0]) if has_bias else e)
+
+
+def _conv3x3_setup(ctx, inputs, output):
+    x, weight, bias, relu_in = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.relu_in, ctx.has_bias = relu_in, bias is not None
+
+
+def _conv3x3_backward(ctx, g):
+    x, weight = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    d_x, d_w, d_b = torch.ops.t2h.conv3x3_bwd(g, x, weight, ctx.relu_in, ctx.has_bias and need[2], need[0], need[1])
+    pick = lambda t: t if t.numel() else None
+    return pick(d_x), (pick(d_w) if need[1] else None), pick(d_b), None
+
+
+_conv3x3_op.register_autograd(_conv3x3_backward, setup_context=_conv3x3_setup)
 
 
 def _tc_ok_3x3(x, weight):
@@ -99,7 +133,7 @@ def conv3x3(x, weight, bias=None, relu_in=False):
     """F.conv2d(relu?(x), weight, bias, padding=1) on logical (B, C, H, W) tensors."""
     if not _tc_ok_3x3(x, weight):
         return F.conv2d(F.relu(x) if relu_in else x, weight, bias, padding=1)
-    y = _Conv3x3TC.apply(x.permute(0, 2, 3, 1).contiguous(), weight, bias, bool(relu_in))
+    y = torch.ops.t2h.conv3x3(x.permute(0, 2, 3, 1).contiguous(), weight, bias, bool(relu_in))
     return y.permute(0, 3, 1, 2)
 
 

@@ -16,8 +16,11 @@ that come from elsewhere take a streaming ``t2h_absmax`` pass.
 import os
 import weakref
 
+from typing import Optional, Tuple
+
 import torch
 import torch.nn.functional as F
+from torch import Tensor
 
 from . import _lib
 from ._lib import ptr
@@ -226,50 +229,83 @@ def colsum(g):
     return out
 
 
-class _LinearTC(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x1, x2, weight, bias, residual, relu_in):
-        x1 = _rowmajor(x1)
-        x2 = None if x2 is None else _rowmajor(x2)
-        residual = None if residual is None else _rowmajor(residual)
-        n_out = weight.shape[0]
-        split = _cache.get(weight, f16=use_f16(n_out, weight.shape[1]))
-        out = torch.empty(x1.shape[0], n_out, dtype=torch.float32, device=x1.device)
-        _launch_fwd(x1, x2, split, n_out, bias, relu_in, None, residual, out)
-        ctx.save_for_backward(x1, x2, weight)
-        ctx.relu_in = relu_in
-        ctx.has_bias = bias is not None
-        return out
+# ------------------------------------------------------------------------------------------
+# t2h::linear / t2h::linear_bwd -- nn.Linear (+ ReLU-on-load, concat, residual) and its backward as torch custom ops
+# over t2h_linear_fwd[_f16] / t2h_linear_wgrad[_f16] / t2h_colsum (t2h_linear_fwd / t2h_linear_bwd)
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("t2h::linear", mutates_args=())
+def _linear_op(x1: Tensor, x2: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor],
+               relu_in: bool) -> Tensor:
+    """relu?([x1 | x2]) @ weight.T + bias + residual on 2-D row-major operands."""
+    x1 = _rowmajor(x1)
+    x2 = None if x2 is None else _rowmajor(x2)
+    residual = None if residual is None else _rowmajor(residual)
+    n_out = weight.shape[0]
+    split = _cache.get(weight, f16=use_f16(n_out, weight.shape[1]))
+    out = torch.empty(x1.shape[0], n_out, dtype=torch.float32, device=x1.device)
+    _launch_fwd(x1, x2, split, n_out, bias, relu_in, None, residual, out)
+    return out
 
-    @staticmethod
-    def backward(ctx, gy):
-        x1, x2, weight = ctx.saved_tensors
-        gy = _rowmajor(gy)
-        k1 = x1.shape[1]
-        n_out, k_total = weight.shape
-        need = ctx.needs_input_grad
-        d_x1 = d_x2 = d_w = d_b = d_res = None
-        if need[0]:
-            split = _cache.get(weight, 0, k1, transposed=True, f16=use_f16(k1, n_out))
-            d_x1 = torch.empty_like(x1)
-            _launch_fwd(gy, None, split, k1, None, False, x1 if ctx.relu_in else None, None, d_x1)
-        if x2 is not None and need[1]:
-            split = _cache.get(weight, k1, k_total, transposed=True, f16=use_f16(k_total - k1, n_out))
-            d_x2 = torch.empty_like(x2)
-            _launch_fwd(gy, None, split, k_total - k1, None, False, x2 if ctx.relu_in else None, None, d_x2)
-        want_bias = ctx.has_bias and need[3]
-        if need[2]:
-            d_w = torch.empty(n_out, k_total, dtype=torch.float32, device=gy.device)
-            if want_bias:  # the bias gradient (column sum of gy) rides along with the first wgrad launch
-                d_b = torch.empty(n_out, dtype=torch.float32, device=gy.device)
-            _launch_wgrad(gy, x1, ctx.relu_in, d_w[:, :k1], d_b)
-            if x2 is not None:
-                _launch_wgrad(gy, x2, ctx.relu_in, d_w[:, k1:])
-        elif want_bias:
-            d_b = colsum(gy)
-        if need[4]:
-            d_res = gy
-        return d_x1, d_x2, d_w, d_b, d_res, None
+
+@_linear_op.register_fake
+def _(x1, x2, weight, bias, residual, relu_in):
+    return x1.new_empty(x1.shape[0], weight.shape[0])
+
+
+@torch.library.custom_op("t2h::linear_bwd", mutates_args=())
+def _linear_bwd_op(gy: Tensor, x1: Tensor, x2: Optional[Tensor], weight: Tensor, relu_in: bool, has_bias: bool,
+                   need_x1: bool, need_x2: bool, need_w: bool, need_b: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """(d_x1, d_x2, d_weight, d_bias); a gradient that is not needed comes back as an empty tensor."""
+    gy = _rowmajor(gy)
+    x1 = _rowmajor(x1)
+    x2 = None if x2 is None else _rowmajor(x2)
+    k1 = x1.shape[1]
+    n_out, k_total = weight.shape
+    d_x1, d_x2, d_w, d_b = (gy.new_empty(0) for _ in range(4))  # distinct tensors: op outputs must not alias
+    if need_x1:
+        split = _cache.get(weight, 0, k1, transposed=True, f16=use_f16(k1, n_out))
+        d_x1 = torch.empty_like(x1)
+        _launch_fwd(gy, None, split, k1, None, False, x1 if relu_in else None, None, d_x1)
+    if x2 is not None and need_x2:
+        split = _cache.get(weight, k1, k_total, transposed=True, f16=use_f16(k_total - k1, n_out))
+        d_x2 = torch.empty_like(x2)
+        _launch_fwd(gy, None, split, k_total - k1, None, False, x2 if relu_in else None, None, d_x2)
+    want_bias = has_bias and need_b
+    if need_w:
+        d_w = torch.empty(n_out, k_total, dtype=torch.float32, device=gy.device)
+        if want_bias:  # the bias gradient (column sum of gy) rides along with the first wgrad launch
+            d_b = torch.empty(n_out, dtype=torch.float32, device=gy.device)
+        _launch_wgrad(gy, x1, relu_in, d_w[:, :k1], d_b if want_bias else None)
+        if x2 is not None:
+            _launch_wgrad(gy, x2, relu_in, d_w[:, k1:])
+    elif want_bias:
+        d_b = colsum(gy)
+    return d_x1, d_x2, d_w, d_b
+
+
+@_linear_bwd_op.register_fake
+def _(gy, x1, x2, weight, relu_in, has_bias, need_x1, need_x2, need_w, need_b):
+    e = gy.new_empty(0)
+    return (torch.empty_like(x1) if need_x1 else e, torch.empty_like(x2) if (x2 is not None and need_x2) else e,
+            torch.empty_like(weight) if need_w else e, gy.new_empty(weight.shape[0]) if (has_bias and need_b) else e)
+
+
+def _linear_setup(ctx, inputs, output):
+    x1, x2, weight, bias, residual, relu_in = inputs
+    ctx.save_for_backward(x1, x2, weight)
+    ctx.relu_in, ctx.has_bias = relu_in, bias is not None
+
+
+def _linear_backward(ctx, gy):
+    x1, x2, weight = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    d_x1, d_x2, d_w, d_b = torch.ops.t2h.linear_bwd(gy, x1, x2, weight, ctx.relu_in, ctx.has_bias, need[0],
+                                                    x2 is not None and need[1], need[2], ctx.has_bias and need[3])
+    pick = lambda t: t if t.numel() else None
+    return pick(d_x1), pick(d_x2), pick(d_w), pick(d_b), (gy if need[4] else None), None
+
+
+_linear_op.register_autograd(_linear_backward, setup_context=_linear_setup)
 
 
 def _pad_to(v, m):
@@ -304,6 +340,6 @@ def linear(x, weight, bias=None, x2=None, relu_in=False, residual=None):
     x2d = x.reshape(-1, x.shape[-1])
     x22d = None if x2 is None else x2.reshape(-1, x2.shape[-1])
     res2d = None if residual is None else residual.reshape(-1, weight.shape[0])
-    y = _LinearTC.apply(x2d, x22d, weight, bias, res2d, bool(relu_in))
+    y = torch.ops.t2h.linear(x2d, x22d, weight, bias, res2d, bool(relu_in))
     y = y.view(*lead, weight.shape[0])
     return y[..., :n_out] if pn else y
