@@ -117,6 +117,13 @@ int t2h_seg_reduce_fwd(const float* rows, int64_t n_rows, const int32_t* perm, c
 int t2h_seg_broadcast(const float* plane, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
                       const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,
                       int mean, float* rows, t2h_stream_t stream);
+/* rows[row, :] = plane[cell(row), :] (/ count) + add_rows[row, :], and *absmax_slot (nullable) = bit pattern of max |rows|:
+ * the backward of the mean-scatter fused with the accumulation of the OTHER gradient branch of the same per-point
+ * tensor (alto.py:123-130: `c` feeds generate_plane_features and the next level's fc_c), so that autograd's add pass
+ * and the operand-maximum pass of the GEMMs that consume the sum disappear */
+int t2h_seg_broadcast_add(const float* plane, const float* add_rows, int64_t n_rows, const int32_t* perm,
+                          const int32_t* row_keys, const int32_t* cell_start, int64_t n_seg, int shift, int C,
+                          int morton, int reso, int mean, float* rows, uint32_t* absmax_slot, t2h_stream_t stream);
 /* the scatter_mean pair under the names of SURVEY.md §8(b): = t2h_seg_reduce_fwd(mean = 1) / t2h_seg_broadcast(mean = 1) */
 int t2h_seg_mean_fwd(const float* rows, int64_t n_rows, const int32_t* perm, const int32_t* row_keys,
                      const int32_t* cell_start, int64_t n_seg, int shift, int C, int morton, int reso,

@@ -28,4 +28,4 @@ from .ops import (  # noqa: F401
     bilinear_sample_points,
     upsample_bilinear_align,
 )
-from .model import oracle_forward, oracle_loss, synth_state_dict, reference_param_shapes  # noqa: F401
+from .model import oracle_forward, oracle_loss, synth_state_dict, reference_param_shapes, Selections  # noqa: F401

@@ -180,6 +180,73 @@ def synth_state_dict(shapes: dict, seed: int = 0, dtype=torch.float32) -> dict:
 
 
 # --------------------------------------------------------------------------
+# discrete selections (ReLU masks, max-pool winners, scatter-max argmax)
+# --------------------------------------------------------------------------
+class Selections:
+    """Record the discrete selections of a forward pass, or replay recorded ones.
+
+    The network is piecewise linear: its parameter gradients are exact functions of the inputs GIVEN the pattern of
+    ReLU masks, max-pool winners and scatter-max argmax.  Two fp32 implementations that differ by rounding can pick
+    different winners for near-ties, which moves single gradients by O(1e-3) although every operator is accurate to
+    1e-6.  ``mode='record'`` stores the pattern of this evaluation on ``tape``; ``mode='replay'`` evaluates the
+    network with the pattern on ``tape`` (e.g. the one the CUDA path took), so that gradients can be compared at
+    the north-star tolerance without that ambiguity (tests/test_gpu_selection_flips.py)."""
+
+    def __init__(self, mode="record", tape=None):
+        assert mode in ("record", "replay")
+        self.mode, self.tape, self.pos = mode, ([] if tape is None else tape), 0
+
+    def _next(self, kind):
+        k, v = self.tape[self.pos]
+        assert k == kind, f"selection tape out of step: expected {kind}, found {k} at {self.pos}"
+        self.pos += 1
+        return v
+
+    def relu(self, x, slope=0.0):
+        if self.mode == "record":
+            mask = x > 0
+            self.tape.append(("relu", mask))
+        else:
+            mask = self._next("relu")
+            assert mask.shape == x.shape, (mask.shape, x.shape)
+        return torch.where(mask, x, x * slope)
+
+    def max_pool(self, x):
+        if self.mode == "record":
+            out, idx = F.max_pool2d(x, 2, 2, return_indices=True)
+            self.tape.append(("pool", idx))
+            return out
+        idx = self._next("pool")
+        return x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
+
+    def seg_max(self, src, index, dim_size):
+        if self.mode == "record":
+            out, arg = ops.segment_max(src, index, dim_size)
+            self.tape.append(("argmax", arg))
+            return out, arg
+        arg = self._next("argmax")
+        n = src.shape[2]
+        picked = src.gather(2, arg.clamp(max=n - 1))
+        return torch.where(arg == n, torch.zeros((), dtype=src.dtype), picked), arg
+
+
+class _Plain:
+    """default policy: the operators themselves"""
+
+    @staticmethod
+    def relu(x, slope=0.0):
+        return F.leaky_relu(x, slope) if slope else F.relu(x)
+
+    @staticmethod
+    def max_pool(x):
+        return F.max_pool2d(x, 2, 2)
+
+    @staticmethod
+    def seg_max(src, index, dim_size):
+        return ops.segment_max(src, index, dim_size)
+
+
+# --------------------------------------------------------------------------
 # layers
 # --------------------------------------------------------------------------
 def _lin(P, name, x):
@@ -194,10 +261,10 @@ def _convT(P, name, x):
     return F.conv_transpose2d(x, P[name + ".weight"], P[name + ".bias"], stride=2)
 
 
-def _resblock(P, name, x):
+def _resblock(P, name, x, sel=_Plain):
     """block/resnet.py:46-54"""
-    net = _lin(P, name + ".fc_0", F.relu(x))
-    dx = _lin(P, name + ".fc_1", F.relu(net))
+    net = _lin(P, name + ".fc_0", sel.relu(x))
+    dx = _lin(P, name + ".fc_1", sel.relu(net))
     if name + ".shortcut.weight" in P:
         return _lin(P, name + ".shortcut", x) + dx
     return x + dx
@@ -226,20 +293,20 @@ def _upsample(plane, size, aten):
     return ops.upsample_bilinear_align(plane, size)
 
 
-def _alto(P, pre, cloud, plane, c, depth, concat, aten, trace):
+def _alto(P, pre, cloud, plane, c, depth, concat, aten, trace, sel=_Plain):
     """alto.py:368-382 with DownConv :97-138 and UpConv :207-257 unrolled."""
     xy = cloud[..., :2]
     x, after, skips = plane, None, []
     for i in range(depth):
         q = f"{pre}.down_convs.{i}"
-        x = F.relu(_conv(P, q + ".conv1", x, 1))
-        x = F.relu(_conv(P, q + ".conv2", x, 1))
+        x = sel.relu(_conv(P, q + ".conv1", x, 1))
+        x = sel.relu(_conv(P, q + ".conv2", x, 1))
         if after is not None:
-            side = F.max_pool2d(after, 2, 2) if 2 <= i < depth else after
+            side = sel.max_pool(after) if 2 <= i < depth else after
             x = x + _conv(P, q + ".conv1x1", side)
         after = x
         s = _sample(x, xy, aten)
-        s = _lin(P, q + ".fc_comm.2", F.relu(_lin(P, q + ".fc_comm.0", s)))
+        s = _lin(P, q + ".fc_comm.2", sel.relu(_lin(P, q + ".fc_comm.0", s)))
         c = s if c is None else s + _lin(P, q + ".fc_c", c)
         x = _mean_plane(c, xy, x.shape[2])
         if trace is not None:
@@ -247,22 +314,22 @@ def _alto(P, pre, cloud, plane, c, depth, concat, aten, trace):
             trace[f"down{i}.plane"] = x
         skips.append(x)
         if 0 < i < depth - 1:
-            x = F.max_pool2d(x, 2, 2)
+            x = sel.max_pool(x)
     for j in range(depth - 1):
         q = f"{pre}.up_convs.{j}"
         last = j == depth - 2
         up = _conv(P, q + ".upconv_noup", x) if last else _convT(P, q + ".upconv", x)
         skip = skips[-(j + 2)]
         x = torch.cat((up, skip), 1) if concat else up + skip
-        x = F.relu(_conv(P, q + ".conv1", x, 1))
-        x = F.relu(_conv(P, q + ".conv2", x, 1))
+        x = sel.relu(_conv(P, q + ".conv1", x, 1))
+        x = sel.relu(_conv(P, q + ".conv2", x, 1))
         if after is not None:
             x = x + (_conv(P, q + ".conv1x1", after) if last else _convT(P, q + ".conv1x1", after))
         after = x
         if last:
             break
         s = _sample(x, xy, aten)
-        s = _lin(P, q + ".fc_comm.2", F.relu(_lin(P, q + ".fc_comm.0", s)))
+        s = _lin(P, q + ".fc_comm.2", sel.relu(_lin(P, q + ".fc_comm.0", s)))
         c = s if c is None else s + _lin(P, q + ".fc_c", c)
         x = _mean_plane(c, xy, x.shape[2])
         if trace is not None:
@@ -289,7 +356,7 @@ def _plain_unet(P, pre, x, depth, concat):
     return _conv(P, pre + ".conv_final", x)
 
 
-def _point_encoder(P, cfg, cloud, aten, trace):
+def _point_encoder(P, cfg, cloud, aten, trace, sel=_Plain):
     """pointnet.py:60-90"""
     ek = cfg["model"]["encoder_kwargs"]
     reso = ek["plane_resolution"]
@@ -297,20 +364,20 @@ def _point_encoder(P, cfg, cloud, aten, trace):
     idx = ops.cell_index(xy, reso)
     pe = "point_encoder"
     net = _lin(P, pe + ".fc_pos", cloud)
-    net = _resblock(P, pe + ".blocks.0", net)
+    net = _resblock(P, pe + ".blocks.0", net, sel)
     n_blocks = sum(1 for k in P if k.startswith(pe + ".blocks.") and k.endswith(".fc_0.weight"))
     use_max = _get(ek, "scatter_type", default="max") == "max"
     for i in range(1, n_blocks):
         src = net.permute(0, 2, 1)
         if use_max:
-            cells, arg = ops.segment_max(src, idx, reso * reso)
+            cells, arg = sel.seg_max(src, idx, reso * reso)
             if trace is not None:
                 trace[f"pool{i}.arg"] = arg
         else:
             cells = ops.segment_mean(src, idx, reso * reso)
         pooled = cells.gather(2, idx.expand(-1, src.shape[1], -1)).permute(0, 2, 1)
-        net = _resblock(P, f"{pe}.blocks.{i}", torch.cat([net, pooled], dim=2))
-    c = _lin(P, pe + ".fc_c", F.relu(net))
+        net = _resblock(P, f"{pe}.blocks.{i}", torch.cat([net, pooled], dim=2), sel)
+    c = _lin(P, pe + ".fc_c", sel.relu(net))
     plane = _mean_plane(c, xy, reso)
     if trace is not None:
         trace["index"] = idx
@@ -319,11 +386,11 @@ def _point_encoder(P, cfg, cloud, aten, trace):
     uk = ek["unet_kwargs"]
     concat = _get(uk, "merge_mode", default="concat") == "concat"
     if _get(ek, "unet_type", default="alto") == "alto":
-        return _alto(P, pe + ".unet", cloud, plane, c, uk["depth"], concat, aten, trace)
+        return _alto(P, pe + ".unet", cloud, plane, c, uk["depth"], concat, aten, trace, sel)
     return _plain_unet(P, pe + ".unet", plane, uk["depth"], concat)
 
 
-def _decoder(P, cfg, planes, aten, output_size):
+def _decoder(P, cfg, planes, aten, output_size, sel=_Plain):
     """pixel.py:94-125"""
     dk = cfg["model"]["decoder_pixel_kwargs"]
     c = None
@@ -334,7 +401,8 @@ def _decoder(P, cfg, planes, aten, output_size):
         c = img if c is None else c + img
     leaky = bool(dk["leaky"])
 
-    def conv_head(q, act):
+    def conv_head(q, slope):
+        act = lambda t: sel.relu(t, slope)
         x1 = act(_conv(P, q + ".conv1", c, 1))
         x2 = act(_conv(P, q + ".conv2", x1, 1))
         x3 = act(_conv(P, q + ".conv3", x2, 1))
@@ -344,14 +412,14 @@ def _decoder(P, cfg, planes, aten, output_size):
         x = c.permute(0, 2, 3, 1)
         n_fc = sum(1 for k in P if k.startswith(q + ".blocks.") and k.endswith(".fc_0.weight"))
         for i in range(n_fc):
-            x = _resblock(P, f"{q}.blocks.{i}", x)
-        return _lin(P, q + ".fc_out", F.relu(x))  # :88 quirk => act is always relu
+            x = _resblock(P, f"{q}.blocks.{i}", x, sel)
+        return _lin(P, q + ".fc_out", sel.relu(x))  # :88 quirk => act is always relu
 
     foot = None
     if dk["mode"] == "conv":
-        pa = conv_head("decoder.conv_decoder", F.leaky_relu if leaky else F.relu)
+        pa = conv_head("decoder.conv_decoder", 0.01 if leaky else 0.0)  # F.leaky_relu's default slope
         if dk["use_footprint"]:
-            foot = conv_head("decoder.conv_decoder_footprint", F.relu)
+            foot = conv_head("decoder.conv_decoder_footprint", 0.0)
     elif dk["mode"] == "fc":
         pa = fc_head("decoder.fc_decoder")
         if dk["use_footprint"]:
@@ -361,17 +429,20 @@ def _decoder(P, cfg, planes, aten, output_size):
     return pa, foot
 
 
-def oracle_forward(P, cfg, input_cloud=None, input_image=None, aten=True, trace=None):
+def oracle_forward(P, cfg, input_cloud=None, input_image=None, aten=True, trace=None, selections=None):
     """model.py:54-67.  Returns (heights (B,S,S,1) * z_scale, footprint logits or None).
 
     ``aten=True`` uses ATen's own grid_sample / interpolate (the reference's
     dependency); ``aten=False`` uses the explicit restatements in oracle/ops.py.
     ``trace`` (dict) collects intermediate tensors for op-level parity tests.
+    ``selections`` (a ``Selections``) records or replays the ReLU / max-pool / argmax pattern of the point branch
+    and the decoder (the image branch keeps the plain operators).
     """
+    sel = _Plain if selections is None else selections
     assert cfg["use_cloud"] or cfg["use_image"], "At least one input modality must be used."
     planes = {}
     if cfg["use_cloud"]:
-        planes["xy"] = _point_encoder(P, cfg, input_cloud, aten, trace)
+        planes["xy"] = _point_encoder(P, cfg, input_cloud, aten, trace, sel)
     if cfg["use_image"]:
         ik = cfg["model"]["encoder2_kwargs"]
         planes["image"] = _plain_unet(P, "image_encoder", input_image, ik["depth"],
@@ -379,7 +450,7 @@ def oracle_forward(P, cfg, input_cloud=None, input_image=None, aten=True, trace=
     if trace is not None:
         trace["planes"] = dict(planes)
     output_size = _get(cfg, "model", "decoder_pixel_kwargs", "output_size", default=512)
-    pa, pb = _decoder(P, cfg, planes, aten, output_size)
+    pa, pb = _decoder(P, cfg, planes, aten, output_size, sel)
     z_bound = cfg["dataset"]["normalize"]["z_bound"]
     return pa * (z_bound[1] - z_bound[0]), pb
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "t2h_seg_max_bwd": [_p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _sz, _p, _p],
     "t2h_seg_reduce_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _sz, _p, _p],
     "t2h_seg_broadcast": [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p],
+    "t2h_seg_broadcast_add": [_p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p],
     "t2h_seg_mean_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _sz, _p, _p],
     "t2h_seg_mean_bwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p],
     "t2h_bilinear_sample_fwd": [_p, _i32, _i32, _p, _i64, _p, _p, _i64, _i64, _p, _p],

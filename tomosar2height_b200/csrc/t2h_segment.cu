@@ -408,10 +408,13 @@ seg_max_fix_kernel(SegGeom g, int cpw, const float* __restrict__ s_val, const in
 // j once, the RPI sub-groups fetch them by shuffle.
 //   MODE 0: rows[row] = plane[cell] (* 1/count when mean)       -- S2 backward, gather-back of pool_local
 //   MODE 1: rows[row, c] = (arg[cell, c] == row) ? tot[cell, c] (+ extra[cell, c]) : 0   -- S1 backward
+//   MODE 2: rows[row] = plane[cell] (* 1/count) + extra[row], *slot = max |rows|  -- S2 backward fused with the
+//           accumulation of the second gradient branch of the same tensor (and the operand maximum of the GEMMs
+//           that consume the sum)
 template <class RS, int MODE>
 __global__ void __launch_bounds__(kSegWarps * kWarp)
 seg_rowmap_kernel(const float* __restrict__ plane, const float* __restrict__ extra, const int32_t* __restrict__ arg,
-                  SegGeom g, int mean, float* __restrict__ rows) {
+                  SegGeom g, int mean, float* __restrict__ rows, uint32_t* __restrict__ slot = nullptr) {
   constexpr int LPR = RS::LPR, CH = RS::CH, RPI = RS::RPI, C = RS::C;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -431,6 +434,7 @@ seg_rowmap_kernel(const float* __restrict__ plane, const float* __restrict__ ext
       my_inv = __fdiv_rn(1.0f, (float)n);
     }
   }
+  float vmax = 0.f;
   for (int t0 = 0; t0 < npts; t0 += RPI) {
     const int j = t0 + sub;
     const bool act = j < npts;
@@ -446,6 +450,10 @@ seg_rowmap_kernel(const float* __restrict__ plane, const float* __restrict__ ext
       float4 v = ld4(p + c * LPR * 4);
       if (MODE == 0) {
         v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      } else if (MODE == 2) {
+        const float4 e = ld4_stream(extra + (int64_t)row * C + (c * LPR + l) * 4);
+        v.x = v.x * inv + e.x; v.y = v.y * inv + e.y; v.z = v.z * inv + e.z; v.w = v.w * inv + e.w;
+        vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
       } else {
         if (extra) {
           const float4 e = ld4(extra + prow * C + (c * LPR + l) * 4);
@@ -459,6 +467,12 @@ seg_rowmap_kernel(const float* __restrict__ plane, const float* __restrict__ ext
       }
       st4_stream(dst + c * LPR * 4, v);
     }
+  }
+  if (MODE == 2 && slot) {  // bit pattern order == float order for non-negative values; integer atomicMax is exact
+    uint32_t b = __float_as_uint(vmax);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if (lane == 0 && b) atomicMax(slot, b);
   }
 }
 
@@ -591,6 +605,22 @@ extern "C" int t2h_seg_broadcast(const float* plane, int64_t n_rows, const int32
   SegGeom g{perm, nullptr, row_keys, cell_start, n_rows, n_seg, shift, morton, reso, log2_cells_of(reso)};
   T2H_DISPATCH_ROWSHAPE(C, (seg_rowmap_kernel<RS, 0><<<blocks_for(n_rows, 32), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
                                plane, nullptr, nullptr, g, mean, rows)));
+  T2H_CHECK_LAUNCH();
+  return T2H_OK;
+}
+
+extern "C" int t2h_seg_broadcast_add(const float* plane, const float* add_rows, int64_t n_rows, const int32_t* perm,
+                                     const int32_t* row_keys, const int32_t* cell_start, int64_t n_seg, int shift, int C,
+                                     int morton, int reso, int mean, float* rows, uint32_t* absmax_slot,
+                                     t2h_stream_t stream) {
+  int st = check_geom(row_keys, cell_start, n_rows, n_seg, shift, C, morton, reso);
+  if (st) return st;
+  if ((n_rows > 0 && (!rows || !add_rows)) || !plane) return T2H_ERR_INVALID_ARGUMENT;
+  if (n_seg == 0 || n_rows == 0) return T2H_OK;
+  SegGeom g{perm, nullptr, row_keys, cell_start, n_rows, n_seg, shift, morton, reso, log2_cells_of(reso)};
+  if (absmax_slot && cudaMemsetAsync(absmax_slot, 0, sizeof(uint32_t), (cudaStream_t)stream) != cudaSuccess) return T2H_ERR_CUDA;
+  T2H_DISPATCH_ROWSHAPE(C, (seg_rowmap_kernel<RS, 2><<<blocks_for(n_rows, 32), kSegWarps * kWarp, 0, (cudaStream_t)stream>>>(
+                               plane, add_rows, nullptr, g, mean, rows, absmax_slot)));
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }

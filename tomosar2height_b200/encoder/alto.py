@@ -53,9 +53,11 @@ class _Exchange:
         hidden = linear(sampled, self.fc_comm[0].weight, self.fc_comm[0].bias)
         carry = None if c_last is None else linear(c_last, self.fc_c.weight, self.fc_c.bias)
         c = linear(hidden, self.fc_comm[2].weight, self.fc_comm[2].bias, relu_in=True, residual=carry)
-        # c feeds the mean-scatter AND the next level's fc_c: sum the two gradient branches in one kernel
-        c_plane, c_next = fork2(c)
-        return self.generate_plane_features(p, c_plane, plane.shape[1], plane.shape[2]), c_next
+        # c feeds the mean-scatter AND the next level's fc_c: the gather of the plane gradient, the sum of the two
+        # gradient branches and the operand maximum of the GEMMs that consume it are one kernel in the backward
+        level = p.level(plane.shape[2])
+        scattered, c_next = T.seg_mean_carry(c, level)
+        return T.plane_to_nchw(scattered, p.B, plane.shape[2]), c_next
 
 
 class DownConv(nn.Module, _Exchange):

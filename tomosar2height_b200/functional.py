@@ -172,6 +172,52 @@ def _seg_broadcast_backward(ctx, g_rows):
 _seg_broadcast.register_autograd(_seg_broadcast_backward, setup_context=_seg_broadcast_setup)
 
 
+@torch.library.custom_op("t2h::seg_broadcast_add", mutates_args=())
+def _seg_broadcast_add(plane: Tensor, add_rows: Tensor, perm: Optional[Tensor], keys: Tensor, cell_start: Tensor, n_seg: int,
+                       shift: int, morton: int, reso: int, mean: bool) -> Tuple[Tensor, Tensor]:
+    """(rows = plane[cell] / count + add_rows, device word with the bit pattern of max |rows|)"""
+    plane = _rows(plane, "seg_broadcast_add(plane)")
+    add_rows = _rows(add_rows, "seg_broadcast_add(rows)")
+    n, C = add_rows.shape
+    rows = torch.empty_like(add_rows)
+    slot = torch.empty(1, dtype=torch.int32, device=plane.device)
+    call("t2h_seg_broadcast_add", ptr(plane), ptr(add_rows), n, ptr(perm), ptr(keys), ptr(cell_start), n_seg, shift, C, morton,
+         reso, int(mean), ptr(rows), ptr(slot))
+    return rows, slot
+
+
+@_seg_broadcast_add.register_fake
+def _(plane, add_rows, perm, keys, cell_start, n_seg, shift, morton, reso, mean):
+    return torch.empty_like(add_rows), plane.new_empty(1, dtype=torch.int32)
+
+
+class _SegMeanCarry(torch.autograd.Function):
+    """``rows -> (mean plane, rows)``: the mean-scatter of alto.py:130 together with the hand-over of the same
+    per-point tensor to the next level's fc_c (alto.py:127).  Forward = t2h::seg_reduce, the second output is the
+    input itself.  Backward: the two gradient branches meet here, so the gather of the plane gradient, their sum and
+    the operand maximum of the GEMMs that consume the sum are ONE kernel (t2h::seg_broadcast_add) instead of a
+    broadcast, autograd's add and a maximum pass."""
+
+    @staticmethod
+    def forward(ctx, rows, level):
+        ctx.level = level
+        ctx.n_rows = rows.shape[0]
+        plane = torch.ops.t2h.seg_reduce(rows, level.perm, *_lv(level), True)
+        return plane, rows.view_as(rows)
+
+    @staticmethod
+    def backward(ctx, g_plane, g_rows):
+        level = ctx.level
+        if g_plane is None:
+            return g_rows, None
+        if g_rows is None:
+            return torch.ops.t2h.seg_broadcast(g_plane.contiguous(), ctx.n_rows, level.perm, *_lv(level), True), None
+        out, slot = torch.ops.t2h.seg_broadcast_add(g_plane.contiguous(), g_rows.contiguous(), level.perm, *_lv(level), True)
+        from .linear import publish_absmax
+        publish_absmax(out, slot)
+        return out, None
+
+
 # ------------------------------------------------------------------------------------------
 # t2h::bilinear_sample -- F.grid_sample(plane, 2p-1, bilinear, border, align_corners=True): alto.py:90-95,199-205
 # ------------------------------------------------------------------------------------------
@@ -312,6 +358,13 @@ def seg_max(rows, level):
 def seg_mean(rows, level):
     """Per-cell mean -> (n_seg, C); empty cells are 0."""
     return torch.ops.t2h.seg_reduce(rows, level.perm, *_lv(level), True)
+
+
+def seg_mean_carry(rows, level):
+    """(per-cell mean (n_seg, C), rows) for a tensor that feeds the mean-scatter AND a later consumer; see _SegMeanCarry."""
+    if not (torch.is_grad_enabled() and rows.requires_grad):
+        return seg_mean(rows, level), rows
+    return _SegMeanCarry.apply(rows, level)
 
 
 def seg_sum(rows, level):

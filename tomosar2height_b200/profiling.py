@@ -34,6 +34,9 @@ def _bytes(name, a):
     if name == "t2h_seg_broadcast":   # plane, n_rows, perm, keys, cell_start, n_seg, shift, C, ...
         rows, n_seg, C = a[1], a[5], a[7]
         return 4 * rows * C + 4 * rows + 4 * n_seg * C
+    if name == "t2h_seg_broadcast_add":  # plane, add, n_rows, perm, keys, cell_start, n_seg, shift, C, ...
+        rows, n_seg, C = a[2], a[6], a[8]
+        return 8 * rows * C + 4 * rows + 4 * n_seg * C
     if name == "t2h_bilinear_sample_fwd":
         reso, C, n, n_per = a[1], a[2], a[7], a[8]
         return 4 * max(n // max(n_per, 1), 1) * reso * reso * C + 8 * n + 4 * n * C
