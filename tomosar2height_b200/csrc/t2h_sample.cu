@@ -213,30 +213,33 @@ sample_bwd_kernel(const float* __restrict__ grad_rows, int reso, const float* __
 
 constexpr int kTileWarps = 8;
 
-// ---- G2, fine levels (few rows per cell): warp-private shared-memory tiles ------------------------------
-// A CTA owns a Morton-aligned region of 8 blocks of TW x TW cells (4 blocks wide, 2 tall); warp w owns block w,
-// whose points are ONE contiguous range of the sorted order, and a private (TW+2) x (TW+2) accumulator tile
-// (taps of a point of cell cx lie in columns cx-1..cx+1, hence the one-cell halo).  Rows stream in coalesced and
-// are read exactly once.  A row of C floats is LPR = C/4 lanes x float4; the G = 32/LPR lane groups of the warp
-// all load the SAME row and each adds it into a different one of the row's four taps (G = 4: one tap each,
-// G = 1: four taps in turn), so no two lanes ever touch one accumulator at the same time and every accumulator
-// sees its contributions in sorted point order: atomic-free, deterministic, and a fat cell only costs its own
-// warp time in proportion to its rows.  The eight private tiles are then summed (fixed block order) into the
-// region's haloed tile in scratch; sample_bwd_merge_kernel adds the (<= 4) overlapping region tiles of every
-// plane cell.
+// ---- G2, fine levels (few rows per cell): row-balanced walk with warp-private shared-memory tiles --------
+// The cells of a level are grouped into Morton blocks of TW x TW cells; the points of a block are ONE contiguous
+// range of the sorted order and all their taps fall into the block's haloed (TW+2) x (TW+2) tile (taps of a point
+// of cell cx lie in columns cx-1..cx+1).  As everywhere else the work is split over the ROWS: warp w of the grid
+// owns the sorted positions [w * kRowChunk, (w + 1) * kRowChunk) and walks the blocks they belong to, one after the
+// other, accumulating each into a private tile in shared memory.  A row of C floats is LPR = C/4 lanes x float4;
+// the G = 32/LPR lane groups of the warp all load the SAME row and each adds it into a different one of the row's
+// four taps (G = 4: one tap each, G = 1: four taps in turn), so no two lanes ever touch one accumulator at the
+// same time and every accumulator sees its contributions in sorted point order: atomic-free, deterministic.
+// A block that lies inside the chunk is complete -> its tile goes to blocks[block]; a block that crosses a chunk
+// border (a facade end holds thousands of rows in a few cells) leaves a partial tile per chunk in slots[chunk][s]
+// (s = 0: the block entered from the left, s = 1: it starts here and leaves to the right).  Warps are independent
+// work items -- no CTA-wide barrier, so a fat block never holds an SM hostage.
+// sample_bwd_wtile_merge_kernel then builds every plane cell from the (<= 4) block tiles that cover it, adding the
+// chunk partials of a crossing block in chunk order.
+constexpr int kRowWarps = 4;    // warps per CTA of the tile walk; every warp is an independent work item
+constexpr int kRowChunk = 128;  // sorted positions per warp
+
 template <int C, int TW>
 struct WTile {
   static constexpr int LPR = C / 4, G = 32 / LPR, TAPS = 4 / G;
   static constexpr int TWH = TW + 2;
   static constexpr int TILE_FLOATS = TWH * TWH * C;
-  static constexpr int RW = 4 * TW, RH = 2 * TW;          // region extent in cells
-  static constexpr int RWH = RW + 2, RHH = RH + 2;        // with the halo
-  static constexpr int LOG2_REGION = (TW == 4) ? 7 : 5;   // log2(8 * TW * TW)
   static constexpr int LOG2_BLOCK = (TW == 4) ? 4 : 2;
   static constexpr int STAGE_WORDS = 32 * 9;              // per warp: 32 rows x (4 tap cells, 4 weights, row)
-  static constexpr int SMEM = (kTileWarps * TILE_FLOATS + kTileWarps * STAGE_WORDS) * 4;  // private tiles + staging
-  static constexpr int CS = (C == 64) ? 32 : C;                                          // channels per assembly pass
-  static constexpr int SMEM_REGION = SMEM + RWH * RHH * CS * 4;                           // + the region tile (light pass)
+  static constexpr int WARP_BYTES = (TILE_FLOATS + STAGE_WORDS) * 4;   // private tile + staging
+  static constexpr int SMEM = kRowWarps * WARP_BYTES;
 };
 
 // rows [r0, r1) of the sorted order (all inside the block whose haloed tile origin is (bx0 - 1, by0 - 1)) -> tile.
@@ -270,14 +273,12 @@ __device__ __forceinline__ void wtile_accumulate(float* __restrict__ tile, int* 
       st_row[lane] = perm ? __ldg(perm + i) : i;
     }
     __syncwarp();
-    float4 cur[U], nxt[U];
+    float4 buf_a[U], buf_b[U];
+    auto load = [&](float4 (&dst)[U], int j0) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) cur[u] = ld4_stream(gbase + (int64_t)st_row[min(u, nb - 1)] * C);
-    for (int j0 = 0; j0 < nb; j0 += U) {
-      if (j0 + U < nb) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) nxt[u] = ld4_stream(gbase + (int64_t)st_row[min(j0 + U + u, nb - 1)] * C);
-      }
+      for (int u = 0; u < U; ++u) dst[u] = ld4_stream(gbase + (int64_t)st_row[min(j0 + u, nb - 1)] * C);
+    };
+    auto add = [&](const float4 (&src)[U], int j0) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (j0 + u < nb) {
@@ -289,212 +290,134 @@ __device__ __forceinline__ void wtile_accumulate(float* __restrict__ tile, int* 
             if (cell >= 0) {
               float4* a = reinterpret_cast<float4*>(tile + cell + l * 4);
               float4 v = *a;
-              v.x += w * cur[u].x; v.y += w * cur[u].y; v.z += w * cur[u].z; v.w += w * cur[u].w;
+              v.x += w * src[u].x; v.y += w * src[u].y; v.z += w * src[u].z; v.w += w * src[u].w;
               *a = v;
             }
           }
         }
         __syncwarp();  // the next row may hit the accumulators another lane group just wrote
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+    };
+    load(buf_a, 0);
+    for (int j0 = 0; j0 < nb; j0 += 2 * U) {  // ping-pong: the loads of the next U rows fly while U rows are added
+      if (j0 + U < nb) load(buf_b, j0 + U);
+      add(buf_a, j0);
+      if (j0 + 2 * U < nb) load(buf_a, j0 + 2 * U);
+      if (j0 + U < nb) add(buf_b, j0 + U);
     }
     __syncwarp();      // the staging arrays are rewritten by the next batch
   }
 }
 
-// Blocks with more than kHeavyBlock rows (a facade end, thousands of points in a few cells) are not walked by
-// their one warp -- the rest of the grid would have finished long before -- but left to the row-balanced pass
-// below (sample_bwd_wtile_heavy_kernel), which adds them into the region tile afterwards.
-constexpr int kHeavyBlock = 128;
-
 template <int C, int TW>
-__global__ void __launch_bounds__(kTileWarps * kWarp)
-sample_bwd_wtile_kernel(const float* __restrict__ grad_rows, int reso, const float* __restrict__ xyz, int64_t stride,
-                        const int32_t* __restrict__ perm, const int32_t* __restrict__ cell_start, int shift,
-                        int log2_cells, float* __restrict__ scratch) {
-  using Cfg = WTile<C, TW>;
-  constexpr int TWH = Cfg::TWH;
-  extern __shared__ float wt_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* tile = wt_smem + warp * Cfg::TILE_FLOATS;
-  int* st_cell = reinterpret_cast<int*>(wt_smem + kTileWarps * Cfg::TILE_FLOATS) + warp * Cfg::STAGE_WORDS;  // [32][4]
-  float* st_w = reinterpret_cast<float*>(st_cell + 32 * 4);                                                  // [32][4]
-  int* st_row = st_cell + 32 * 8;                                                                           // [32]
-
-  // region -> image, origin; warp -> block origin
-  const int64_t region = blockIdx.x;
-  const int regions_log2 = log2_cells - Cfg::LOG2_REGION;
-  const int64_t img = region >> regions_log2;
-  const uint32_t rcode = (uint32_t)(region - (img << regions_log2)) << Cfg::LOG2_REGION;  // Morton code of the first cell
-  const int rx0 = (int)compact1by1(rcode), ry0 = (int)compact1by1(rcode >> 1);
-  const int bx = (warp & 1) | (((warp >> 2) & 1) << 1), by = (warp >> 1) & 1;
-  const int bx0 = rx0 + bx * TW, by0 = ry0 + by * TW;
-  const int64_t key0 = (img << log2_cells) + rcode + ((int64_t)warp << Cfg::LOG2_BLOCK);
-  const int p0 = __ldg(cell_start + (key0 << shift)), p1 = __ldg(cell_start + ((key0 + (1 << Cfg::LOG2_BLOCK)) << shift));
-
-  const bool mine = p1 > p0 && p1 - p0 <= kHeavyBlock;  // empty and heavy blocks contribute nothing here
-  if (mine) {
-    for (int f = lane; f < Cfg::TILE_FLOATS / 4; f += kWarp) reinterpret_cast<float4*>(tile)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
-    wtile_accumulate<C, TW>(tile, st_cell, st_w, st_row, grad_rows, reso, xyz, stride, perm, p0, p1, bx0, by0, lane);
-  }
-  // region tile = sum of the private tiles, added in four phases: the blocks of one phase (same row, columns two
-  // apart) do not overlap, so every region cell has one writer per phase and a fixed order of additions.
-  // Assembled CS channels at a time to bound the shared memory of the wide variants.
-  constexpr int CS = Cfg::CS;
-  float* rt = wt_smem + Cfg::SMEM / 4;  // [RHH][RWH][CS], behind the private tiles and the staging arrays
-  float* dst = scratch + region * (int64_t)(Cfg::RWH * Cfg::RHH * C);
-#pragma unroll 1
-  for (int cs0 = 0; cs0 < C; cs0 += CS) {
-    __syncthreads();
-    for (int f = threadIdx.x; f < Cfg::RWH * Cfg::RHH * (CS / 4); f += kTileWarps * kWarp)
-      reinterpret_cast<float4*>(rt)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-#pragma unroll 1
-    for (int phase = 0; phase < 4; ++phase) {
-      if (mine && ((bx & 1) | (by << 1)) == phase) {
-        // a tile row (TWH cells x CS channels) is contiguous in the region tile too
-#pragma unroll
-        for (int ly = 0; ly < TWH; ++ly) {
-          float* drow = rt + ((by * TW + ly) * Cfg::RWH + bx * TW) * CS;
-          const float* srow = tile + ly * TWH * C + cs0;
-          for (int f = lane; f < TWH * (CS / 4); f += kWarp) {
-            const int cellx = f / (CS / 4), c4i = f % (CS / 4);
-            float4* d = reinterpret_cast<float4*>(drow + f * 4);
-            const float4 o = *reinterpret_cast<const float4*>(srow + cellx * C + c4i * 4);
-            float4 v = *d;
-            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            *d = v;
-          }
-        }
-      }
-      __syncthreads();
-    }
-    if (CS == C) {
-      for (int f = threadIdx.x; f < Cfg::RWH * Cfg::RHH * (C / 4); f += kTileWarps * kWarp)
-        st4(dst + f * 4, reinterpret_cast<const float4*>(rt)[f]);
-    } else {
-      for (int f = threadIdx.x; f < Cfg::RWH * Cfg::RHH * (CS / 4); f += kTileWarps * kWarp) {
-        const int c4i = f % (CS / 4), cellt = f / (CS / 4);
-        st4(dst + (int64_t)cellt * C + cs0 + c4i * 4, reinterpret_cast<const float4*>(rt)[f]);
-      }
-    }
-  }
-}
-
-// Row-balanced pass over the heavy blocks: warp w of the grid owns the sorted positions [w * kHeavyBlock,
-// (w + 1) * kHeavyBlock).  A heavy block holds more rows than that, so at most two of them overlap a chunk:
-// one that entered from the left (slot 0, also when it covers the whole chunk) and one that starts inside and
-// leaves to the right (slot 1).  The overlap is accumulated into a private tile exactly as above and stored
-// to slots[chunk][slot]; chunks that only see light blocks return after reading two keys.
-template <int C, int TW>
-__global__ void __launch_bounds__(kTileWarps * kWarp)
-sample_bwd_wtile_heavy_kernel(const float* __restrict__ grad_rows, int64_t n_rows, int reso, const float* __restrict__ xyz,
-                              int64_t stride, const int32_t* __restrict__ perm, const int32_t* __restrict__ keys,
-                              const int32_t* __restrict__ cell_start, int shift, int log2_cells, float* __restrict__ slots) {
+__global__ void __launch_bounds__(kRowWarps * kWarp)
+sample_bwd_wtile_rows_kernel(const float* __restrict__ grad_rows, int64_t n_rows, int reso, const float* __restrict__ xyz,
+                             int64_t stride, const int32_t* __restrict__ perm, const int32_t* __restrict__ keys,
+                             const int32_t* __restrict__ cell_start, int shift, int log2_cells,
+                             float* __restrict__ blocks, float* __restrict__ slots) {
   using Cfg = WTile<C, TW>;
   extern __shared__ float wt_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* tile = wt_smem + warp * Cfg::TILE_FLOATS;
-  int* st_cell = reinterpret_cast<int*>(wt_smem + kTileWarps * Cfg::TILE_FLOATS) + warp * Cfg::STAGE_WORDS;
-  float* st_w = reinterpret_cast<float*>(st_cell + 32 * 4);
-  int* st_row = st_cell + 32 * 8;
-  const int64_t chunk = (int64_t)blockIdx.x * kTileWarps + warp;
-  const int64_t first = chunk * kHeavyBlock;
-  if (first >= n_rows) return;
-  const int last = (int)min(first + (int64_t)kHeavyBlock, n_rows);
+  float* tile = wt_smem + warp * (Cfg::WARP_BYTES / 4);
+  int* st_cell = reinterpret_cast<int*>(tile + Cfg::TILE_FLOATS);  // [32][4]
+  float* st_w = reinterpret_cast<float*>(st_cell + 32 * 4);        // [32][4]
+  int* st_row = st_cell + 32 * 8;                                  // [32]
+  const int64_t chunk = (int64_t)blockIdx.x * kRowWarps + warp;
+  const int64_t first64 = chunk * kRowChunk;
+  if (first64 >= n_rows) return;
+  const int first = (int)first64, last = (int)min(first64 + (int64_t)kRowChunk, n_rows);
   const int bshift = shift + Cfg::LOG2_BLOCK;  // sort key -> block of this level
-  const int blk_first = __ldg(keys + first) >> bshift, blk_last = __ldg(keys + last - 1) >> bshift;
-#pragma unroll 1
-  for (int slot = 0; slot < 2; ++slot) {
-    const int blk = slot == 0 ? blk_first : blk_last;
-    if (slot == 1 && blk_last == blk_first) break;
+  int row = first;
+  while (row < last) {
+    const int blk = __ldg(keys + row) >> bshift;
     const int64_t key0 = (int64_t)blk << Cfg::LOG2_BLOCK;  // first cell of the block (level key incl. the image)
     const int p0 = __ldg(cell_start + (key0 << shift)), p1 = __ldg(cell_start + ((key0 + (1 << Cfg::LOG2_BLOCK)) << shift));
-    if (p1 - p0 <= kHeavyBlock) continue;                       // light: done by its own warp
-    // a heavy first block that STARTS at the chunk start and leaves to the right is a slot-1 block
-    const int use_slot = (p0 < (int)first) ? 0 : 1;
+    const int r1 = min(p1, last);
     const uint32_t code = (uint32_t)(key0 & ((1ll << log2_cells) - 1));
     const int bx0 = (int)compact1by1(code), by0 = (int)compact1by1(code >> 1);
     for (int f = lane; f < Cfg::TILE_FLOATS / 4; f += kWarp) reinterpret_cast<float4*>(tile)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
-    wtile_accumulate<C, TW>(tile, st_cell, st_w, st_row, grad_rows, reso, xyz, stride, perm, max(p0, (int)first), min(p1, last),
-                            bx0, by0, lane);
-    float* dst = slots + (chunk * 2 + use_slot) * (int64_t)Cfg::TILE_FLOATS;
+    wtile_accumulate<C, TW>(tile, st_cell, st_w, st_row, grad_rows, reso, xyz, stride, perm, row, r1, bx0, by0, lane);
+    const bool complete = p0 >= first && p1 <= last;
+    float* dst = complete ? blocks + (int64_t)blk * Cfg::TILE_FLOATS
+                          : slots + (chunk * 2 + (p0 < first ? 0 : 1)) * (int64_t)Cfg::TILE_FLOATS;
     for (int f = lane; f < Cfg::TILE_FLOATS / 4; f += kWarp) st4(dst + f * 4, reinterpret_cast<const float4*>(tile)[f]);
     __syncwarp();
+    row = r1;
   }
 }
 
-// one CTA per region: the slot tiles of its heavy blocks are added, in block and then chunk order, into the
-// region tile the light pass left in scratch (a single writer per region tile -> no races, fixed order)
+// grad_plane[b, y, x, :] = sum over the (<= 4) blocks whose haloed tile covers (x, y), in block order (row, then
+// column): an empty block contributes nothing, a block inside one chunk its tile, a block that crosses chunk borders
+// the chunk partials in chunk order.
 template <int C, int TW>
-__global__ void __launch_bounds__(kTileWarps * kWarp)
-sample_bwd_wtile_fix_kernel(const int32_t* __restrict__ cell_start, int shift, const float* __restrict__ slots,
-                            float* __restrict__ scratch) {
-  using Cfg = WTile<C, TW>;
-  constexpr int TWH = Cfg::TWH;
-  const int64_t region = blockIdx.x;
-  float* rt = scratch + region * (int64_t)(Cfg::RWH * Cfg::RHH * C);
-  __shared__ int bounds[kTileWarps + 1];  // the nine block boundaries, fetched in parallel
-  if (threadIdx.x <= kTileWarps)
-    bounds[threadIdx.x] = __ldg(cell_start + (((region << Cfg::LOG2_REGION) + ((int64_t)threadIdx.x << Cfg::LOG2_BLOCK)) << shift));
-  __syncthreads();
-  for (int w = 0; w < kTileWarps; ++w) {
-    const int p0 = bounds[w], p1 = bounds[w + 1];
-    if (p1 - p0 <= kHeavyBlock) continue;  // uniform across the CTA
-    const int bx = (w & 1) | (((w >> 2) & 1) << 1), by = (w >> 1) & 1;
-    const int c0 = p0 / kHeavyBlock, c1 = (p1 - 1) / kHeavyBlock;
-    for (int idx = threadIdx.x; idx < Cfg::TILE_FLOATS / 4; idx += kTileWarps * kWarp) {
-      const int c4i = idx % (C / 4), cellt = idx / (C / 4);
-      const int ly = cellt / TWH, lx = cellt % TWH;
-      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int ck = c0; ck <= c1; ++ck) {
-        const int slot = (ck * kHeavyBlock > p0) ? 0 : 1;
-        const float4 o = ld4(slots + ((int64_t)ck * 2 + slot) * Cfg::TILE_FLOATS + idx * 4);
-        sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
-      }
-      float* d = rt + ((by * TW + ly) * Cfg::RWH + bx * TW + lx) * C + c4i * 4;
-      float4 v = *reinterpret_cast<const float4*>(d);
-      v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
-      st4(d, v);
-    }
-    __syncthreads();  // the halos of two heavy blocks of one region overlap
-  }
-}
-
-// grad_plane[b, y, x, :] = sum of the region tiles that cover (x, y): own region plus the left/upper or
-// right/lower neighbours when the cell lies on a region edge; fixed order (region row, then column).
-// Regions are RW x RH cells, enumerated in Morton order of (column, row) with the ROW bit first (the Morton
-// code of a cell continues with a y bit above a region's 2*log2(TW)+3 low bits).
-template <int TW>
 __global__ void __launch_bounds__(256)
-sample_bwd_merge_kernel(const float* __restrict__ scratch, int reso, int C, int log2_cells, int64_t n_cells,
-                        float* __restrict__ grad_plane) {
-  constexpr int RW = 4 * TW, RH = 2 * TW, RWH = RW + 2, RHH = RH + 2;
-  constexpr int LOG2_REGION = (TW == 4) ? 7 : 5;
-  const int c4 = C / 4;
+sample_bwd_wtile_merge_kernel(const float* __restrict__ blocks, const float* __restrict__ slots,
+                              const int32_t* __restrict__ cell_start, int shift, int log2_reso, int64_t n_cells,
+                              float* __restrict__ grad_plane) {
+  constexpr int TWH = TW + 2;
+  constexpr int LOG2_TW = (TW == 4) ? 2 : 1, LOG2_BLOCK = 2 * LOG2_TW;
+  constexpr int TILE = TWH * TWH * C;
+  constexpr int C4 = C / 4;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= n_cells * c4) return;
-  const int64_t cellid = gid / c4;
-  const int ch = (int)(gid - cellid * c4) * 4;
+  if (gid >= n_cells * C4) return;
+  const int64_t cellid = gid / C4;
+  const int ch = (int)(gid % C4) * 4;
+  const int log2_cells = 2 * log2_reso, reso = 1 << log2_reso;
   const int64_t img = cellid >> log2_cells;
-  const int rem = (int)(cellid - (img << log2_cells));
-  const int y = rem / reso, x = rem - y * reso;
-  const int nx = reso / RW, ny = reso / RH;
-  const int regions_log2 = log2_cells - LOG2_REGION;
-  const int qx_lo = max((x - 1 + RW) / RW - 1, 0), qx_hi = min((x + 1) / RW, nx - 1);
-  const int qy_lo = max((y - 1 + RH) / RH - 1, 0), qy_hi = min((y + 1) / RH, ny - 1);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int qy = qy_lo; qy <= qy_hi; ++qy)
-    for (int qx = qx_lo; qx <= qx_hi; ++qx) {
-      const int lx = x - qx * RW + 1, ly = y - qy * RH + 1;
-      if (lx < 0 || lx >= RWH || ly < 0 || ly >= RHH) continue;
-      const int64_t region = (img << regions_log2) + (part1by1((uint32_t)qy) | (part1by1((uint32_t)qx) << 1));
-      const float4 v = ld4(scratch + (region * (RWH * RHH) + ly * RWH + lx) * (int64_t)C + ch);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  const int rem = (int)(cellid & ((1ll << log2_cells) - 1));
+  const int y = rem >> log2_reso, x = rem & (reso - 1);
+  const int bx = x >> LOG2_TW, by = y >> LOG2_TW, ox = x & (TW - 1), oy = y & (TW - 1), nb = reso >> LOG2_TW;
+  // the own block always covers the cell; a neighbour only when the cell sits on the facing edge (one-cell halo)
+  const int qx_lo = (ox == 0 && bx > 0) ? bx - 1 : bx, qx_hi = (ox == TW - 1 && bx + 1 < nb) ? bx + 1 : bx;
+  const int qy_lo = (oy == 0 && by > 0) ? by - 1 : by, qy_hi = (oy == TW - 1 && by + 1 < nb) ? by + 1 : by;
+  // up to 2 x 2 candidate blocks in (row, column) order; their row ranges first, then their tiles, all in flight together
+  int64_t blk[4];
+  int p0[4], p1[4], off[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int qy = (k >> 1) ? qy_hi : qy_lo, qx = (k & 1) ? qx_hi : qx_lo;
+    const bool dup = ((k >> 1) && qy_hi == qy_lo) || ((k & 1) && qx_hi == qx_lo);
+    blk[k] = (img << (log2_cells - LOG2_BLOCK)) + (part1by1((uint32_t)qx) | (part1by1((uint32_t)qy) << 1));
+    off[k] = ((y - (qy << LOG2_TW) + 1) * TWH + (x - (qx << LOG2_TW) + 1)) * C + ch;
+    const int64_t key0 = blk[k] << LOG2_BLOCK;
+    p0[k] = dup ? 0 : __ldg(cell_start + (key0 << shift));
+    p1[k] = dup ? 0 : __ldg(cell_start + ((key0 + (1 << LOG2_BLOCK)) << shift));
+  }
+  float4 v[4];
+  bool crossing = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p1[k] > p0[k]) {
+      if (p0[k] / kRowChunk == (p1[k] - 1) / kRowChunk) v[k] = ld4(blocks + blk[k] * TILE + off[k]);
+      else crossing = true;
     }
+  }
+  if (crossing) {  // a block that spans several chunks: its chunk partials in chunk order
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      if (p1[k] <= p0[k]) continue;
+      const int c0 = p0[k] / kRowChunk, c1 = (p1[k] - 1) / kRowChunk;
+      if (c0 == c1) continue;
+      float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ck = c0; ck <= c1; ck += 4) {
+        float4 o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cq = min(ck + q, c1);
+          o[q] = ld4(slots + ((int64_t)cq * 2 + ((cq * kRowChunk > p0[k]) ? 0 : 1)) * TILE + off[k]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (ck + q <= c1) { part.x += o[q].x; part.y += o[q].y; part.z += o[q].z; part.w += o[q].w; }
+      }
+      v[k] = part;
+    }
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
   st4(grad_plane + cellid * C + ch, acc);
 }
 
@@ -774,7 +697,7 @@ static inline int g2_mode(int reso, int C, int morton, int64_t n_points, int64_t
   const bool nine_ok = C == 32 || C == 64 || (C % 128 == 0 && C <= 1024);
   const int64_t avg = n_points / n_seg;
   const int tw = C == 128 ? 2 : 4;
-  if ((C == 32 || C == 64 || C == 128) && avg < 32 && reso >= 4 * tw) return G2_WTILE;
+  if ((C == 32 || C == 64 || C == 128) && avg < 32 && reso >= tw) return G2_WTILE;
   return nine_ok ? G2_NINE : G2_GATHER;
 }
 static inline int nine_rows(int C) { return C >= 128 ? 256 : 128; }
@@ -784,10 +707,9 @@ extern "C" size_t t2h_bilinear_sample_bwd_workspace_bytes(int reso, int C, int64
   switch (g2_mode(reso, C, morton, n_points, n_seg)) {
     case G2_WTILE: {
       const int tw = C == 128 ? 2 : 4;
-      const int64_t regions = n_seg / (8 * tw * tw);
-      const int64_t chunks = (n_points + kHeavyBlock - 1) / kHeavyBlock;
-      return align256s((size_t)regions * (4 * tw + 2) * (2 * tw + 2) * C * sizeof(float)) +
-             (size_t)chunks * 2 * (tw + 2) * (tw + 2) * C * sizeof(float) + 256;
+      const size_t tile = (size_t)(tw + 2) * (tw + 2) * C * sizeof(float);
+      const int64_t chunks = (n_points + kRowChunk - 1) / kRowChunk;
+      return align256s((size_t)(n_seg / (tw * tw)) * tile) + (size_t)chunks * 2 * tile + 256;
     }
     case G2_NINE: {
       const int64_t chunks = (n_points + nine_rows(C) - 1) / nine_rows(C);
@@ -802,28 +724,23 @@ static int launch_wtile(const float* grad_rows, int64_t n_points, int reso, cons
                         const int32_t* perm, const int32_t* keys, const int32_t* cell_start, int64_t n_seg, int shift,
                         int log2_cells, float* scratch, float* grad_plane, cudaStream_t s) {
   using Cfg = WTile<C, TW>;
-  auto kern = sample_bwd_wtile_kernel<C, TW>;
-  auto heavy = sample_bwd_wtile_heavy_kernel<C, TW>;
+  auto kern = sample_bwd_wtile_rows_kernel<C, TW>;
   // per device and idempotent; set on every launch so that the entry point keeps no state
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_REGION) != cudaSuccess ||
-      cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
     (void)cudaGetLastError();
     return T2H_ERR_CUDA;
   }
-  const int64_t regions = n_seg >> Cfg::LOG2_REGION;
-  float* slots = (float*)((char*)scratch + align256s((size_t)regions * Cfg::RWH * Cfg::RHH * C * sizeof(float)));
-  kern<<<(unsigned)regions, kTileWarps * kWarp, Cfg::SMEM_REGION, s>>>(grad_rows, reso, xyz, stride, perm, cell_start, shift, log2_cells, scratch);
-  T2H_CHECK_LAUNCH();
-  const int64_t chunks = (n_points + kHeavyBlock - 1) / kHeavyBlock;
+  float* blocks = scratch;
+  float* slots = (float*)((char*)scratch + align256s((size_t)(n_seg >> Cfg::LOG2_BLOCK) * Cfg::TILE_FLOATS * sizeof(float)));
+  const int64_t chunks = (n_points + kRowChunk - 1) / kRowChunk;
   if (chunks > 0) {
-    heavy<<<(unsigned)((chunks + kTileWarps - 1) / kTileWarps), kTileWarps * kWarp, Cfg::SMEM, s>>>(
-        grad_rows, n_points, reso, xyz, stride, perm, keys, cell_start, shift, log2_cells, slots);
-    T2H_CHECK_LAUNCH();
-    sample_bwd_wtile_fix_kernel<C, TW><<<(unsigned)regions, kTileWarps * kWarp, 0, s>>>(cell_start, shift, slots, scratch);
+    kern<<<(unsigned)((chunks + kRowWarps - 1) / kRowWarps), kRowWarps * kWarp, Cfg::SMEM, s>>>(
+        grad_rows, n_points, reso, xyz, stride, perm, keys, cell_start, shift, log2_cells, blocks, slots);
     T2H_CHECK_LAUNCH();
   }
   const int64_t threads = n_seg * (C / 4);
-  sample_bwd_merge_kernel<TW><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(scratch, reso, C, log2_cells, n_seg, grad_plane);
+  sample_bwd_wtile_merge_kernel<C, TW><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(blocks, slots, cell_start, shift,
+                                                                                        log2_cells / 2, n_seg, grad_plane);
   T2H_CHECK_LAUNCH();
   return T2H_OK;
 }
