@@ -52,7 +52,7 @@ class _Recorder:
         import tomosar2height_b200.encoder.alto as m_alto
         import tomosar2height_b200.decoder.pixel as m_px
         import tomosar2height_b200.functional as T
-        from tomosar2height_b200.linear import linear as real_linear
+        from tomosar2height_b200.linear import linear as real_linear, relu as real_relu
         from tomosar2height_b200.conv import apply_conv as real_conv
         from tomosar2height_b200.topology import Topology as RealTopology
         rec = self
@@ -62,10 +62,10 @@ class _Recorder:
                 rec.tape.append(("relu", rec._rows_mask(x.detach(), None if x2 is None else x2.detach())))
             return real_linear(x, weight, bias, x2=x2, relu_in=relu_in, residual=residual)
 
-        def apply_conv(module, x, relu_in=False):
+        def apply_conv(module, x, relu_in=False, residual=None):
             if relu_in:
                 rec.tape.append(("relu", (x.detach() > 0).cpu()))
-            return real_conv(module, x, relu_in=relu_in)
+            return real_conv(module, x, relu_in=relu_in, residual=residual)
 
         def relu(x, *a, **k):
             rec.tape.append(("relu", (x.detach() > 0).cpu()))
@@ -96,10 +96,15 @@ class _Recorder:
         t_proxy.seg_max_pool = seg_max_pool
         for mod in (m_res, m_pn, m_alto, m_px):
             self._patch(mod, "linear", linear)
+        def relu_bounded(x, slope=0.0):
+            rec.tape.append(("relu", (x.detach() > 0).cpu()))
+            return real_relu(x, slope)
+
         for mod in (m_alto, m_px):
             self._patch(mod, "apply_conv", apply_conv)
             self._patch(mod, "F", f_proxy)
-        # ConvDecoder binds F.relu / F.leaky_relu at construction time: patched per instance in `attach`
+            self._patch(mod, "relu_bounded", relu_bounded)
+        # ConvDecoder binds its activation at construction time: patched per instance in `attach`
         self._patch(m_pn, "Topology", topology)
         self._patch(m_pn, "T", t_proxy)
         return self
@@ -114,12 +119,10 @@ class _Recorder:
 
         self._hooks = [m.register_forward_hook(pool_hook) for m in model.modules() if isinstance(m, torch.nn.MaxPool2d)]
         for m in model.modules():
-            if hasattr(m, "act") and m.act in (F.relu, F.leaky_relu):
-                leaky = m.act is F.leaky_relu
-
-                def act(x, _leaky=leaky):
+            if callable(getattr(m, "act", None)) and not isinstance(m.act, torch.nn.Module):
+                def act(x, _inner=m.act):
                     rec.tape.append(("relu", (x.detach() > 0).cpu()))
-                    return F.leaky_relu(x) if _leaky else F.relu(x)
+                    return _inner(x)
 
                 self._undo.append((m, "act", m.act))
                 m.act = act

@@ -137,11 +137,14 @@ def conv3x3(x, weight, bias=None, relu_in=False):
     return y.permute(0, 3, 1, 2)
 
 
-def conv1x1(x, weight, bias=None, relu_in=False):
-    """F.conv2d(relu?(x), weight, bias) for 1x1 kernels = a linear layer over the pixels."""
+def conv1x1(x, weight, bias=None, relu_in=False, residual=None):
+    """F.conv2d(relu?(x), weight, bias) (+ residual) for 1x1 kernels = a linear layer over the pixels; the residual
+    add (alto.py:111-114: ``x = x + conv1x1(x_after_conv)``) rides in the GEMM epilogue."""
     if USE_LIBRARY_GEMM or not x.is_cuda:
-        return F.conv2d(F.relu(x) if relu_in else x, weight, bias)
-    y = linear(x.permute(0, 2, 3, 1), weight.reshape(weight.shape[0], weight.shape[1]), bias, relu_in=relu_in)
+        y = F.conv2d(F.relu(x) if relu_in else x, weight, bias)
+        return y if residual is None else y + residual
+    y = linear(x.permute(0, 2, 3, 1), weight.reshape(weight.shape[0], weight.shape[1]), bias, relu_in=relu_in,
+               residual=None if residual is None else residual.permute(0, 2, 3, 1))
     return y.permute(0, 3, 1, 2)
 
 
@@ -158,15 +161,19 @@ def conv_transpose2x2(x, weight, bias=None):
     return y.permute(0, 3, 1, 2)
 
 
-def apply_conv(module, x, relu_in=False):
+def apply_conv(module, x, relu_in=False, residual=None):
     """Run an ``nn.Conv2d`` / ``nn.ConvTranspose2d`` module of the plane CNN through the kernels above
-    (its parameters are used as they are); anything else is called as a module."""
+    (its parameters are used as they are); anything else is called as a module.  ``residual`` is added to the
+    result -- inside the GEMM epilogue for 1x1 convolutions."""
     if isinstance(module, torch.nn.Conv2d) and module.groups == 1 and module.stride == (1, 1) and module.dilation == (1, 1):
-        if module.kernel_size == (3, 3) and module.padding == (1, 1) and module.padding_mode == 'zeros':
-            return conv3x3(x, module.weight, module.bias, relu_in=relu_in)
         if module.kernel_size == (1, 1) and module.padding == (0, 0):
-            return conv1x1(x, module.weight, module.bias, relu_in=relu_in)
+            return conv1x1(x, module.weight, module.bias, relu_in=relu_in, residual=residual)
+        if module.kernel_size == (3, 3) and module.padding == (1, 1) and module.padding_mode == 'zeros':
+            y = conv3x3(x, module.weight, module.bias, relu_in=relu_in)
+            return y if residual is None else y + residual
     if (isinstance(module, torch.nn.ConvTranspose2d) and module.kernel_size == (2, 2) and module.stride == (2, 2)
             and module.padding == (0, 0) and module.output_padding == (0, 0) and module.groups == 1 and not relu_in):
-        return conv_transpose2x2(x, module.weight, module.bias)
-    return module(F.relu(x) if relu_in else x)
+        y = conv_transpose2x2(x, module.weight, module.bias)
+        return y if residual is None else y + residual
+    y = module(F.relu(x) if relu_in else x)
+    return y if residual is None else y + residual

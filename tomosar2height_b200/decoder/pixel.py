@@ -11,7 +11,7 @@ import torch.nn.functional as F
 from .. import functional as T
 from ..conv import apply_conv
 from ..block import ResnetBlockFC
-from ..linear import linear
+from ..linear import linear, relu as relu_bounded, leaky_relu as leaky_relu_bounded
 
 
 class ConvDecoder(nn.Module):
@@ -21,7 +21,7 @@ class ConvDecoder(nn.Module):
         self.conv2 = nn.Conv2d(64, 128, kernel_size=3, padding=1)
         self.conv3 = nn.Conv2d(128, 64, kernel_size=3, padding=1)
         self.conv4 = nn.Conv2d(288, out_channels, kernel_size=1)
-        self.act = F.leaky_relu if leaky else F.relu
+        self.act = leaky_relu_bounded if leaky else relu_bounded  # F.leaky_relu / F.relu, handing the operand maximum on
 
     def forward(self, x):
         x1 = self.act(apply_conv(self.conv1, x))

@@ -19,6 +19,7 @@ from .. import functional as T
 from ..conv import apply_conv
 from ..linear import use_f16, publish_absmax, operand_absmax, fork2
 from ..linear import linear
+from ..linear import relu as relu_bounded
 from ..topology import Topology
 from .unet import conv3x3, conv1x1, upconv2x2, check_modes, xavier_normal_convs
 
@@ -76,12 +77,12 @@ class DownConv(nn.Module, _Exchange):
 
     def forward(self, p, x, x_after_conv=None, c_last=None):
         # conv3x3 -> ReLU -> conv3x3 -> ReLU; the first ReLU is applied on load by the second conv
-        plane = F.relu(apply_conv(self.conv2, apply_conv(self.conv1, x['xy']), relu_in=True))
+        plane = relu_bounded(apply_conv(self.conv2, apply_conv(self.conv1, x['xy']), relu_in=True))
         if x_after_conv is not None:
             side = x_after_conv['xy']
             if 2 <= self.downsample < self.depth:  # alto.py:108-110: levels >= 2 see a pooled residual
                 side = self.pool(side)
-            plane = plane + apply_conv(self.conv1x1, side)
+            plane = apply_conv(self.conv1x1, side, residual=plane)  # plane + conv1x1(side), added in the epilogue
         x_after_conv = {'xy': plane}
         scattered, c = self.exchange(p, plane, c_last)
         before_pool = {'xy': scattered}
@@ -110,9 +111,9 @@ class UpConv(nn.Module, _Exchange):
         last = i == self.depth - 2
         up = apply_conv(self.upconv_noup, from_up['xy']) if last else apply_conv(self.upconv, from_up['xy'])
         merged = torch.cat((up, from_down['xy']), 1) if self.merge_mode == 'concat' else up + from_down['xy']
-        plane = F.relu(apply_conv(self.conv2, apply_conv(self.conv1, merged), relu_in=True))
+        plane = relu_bounded(apply_conv(self.conv2, apply_conv(self.conv1, merged), relu_in=True))
         if x_after_conv is not None:
-            plane = plane + apply_conv(self.conv1x1, x_after_conv['xy'])
+            plane = apply_conv(self.conv1x1, x_after_conv['xy'], residual=plane)
         x_after_conv = {'xy': plane}
         if last:  # alto.py:241-242: the last block has no point exchange
             return {'xy': plane}, x_after_conv, c_last

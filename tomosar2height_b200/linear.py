@@ -88,6 +88,12 @@ def use_f16(n_out, k_total):
     return USE_F16 and n_out > 64 and k_total >= 128 and k_total % 8 == 0
 
 
+def _dense(t):
+    """the tensor covers exactly ``numel`` consecutive elements from its data pointer (row-major, or a channels-last
+    NCHW view of a row-major NHWC plane): its maximum is a property of that memory range, whatever the view"""
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+
+
 class _AbsmaxRegistry:
     """Device words holding max |t| of live tensors, so that an operand maximum is computed once.
 
@@ -114,10 +120,10 @@ class _AbsmaxRegistry:
 
     def get(self, t):
         e = self._entries.get((t.data_ptr(), t.numel()))
-        if e is None or not t.is_contiguous() or t.is_inference():
+        if e is None or not _dense(t) or t.is_inference():
             return None
         owner = e[0]()
-        if owner is None or owner._version != e[1] or t._version != e[1] or not owner.is_contiguous():
+        if owner is None or owner._version != e[1] or t._version != e[1] or not _dense(owner):
             return None
         return e[2]
 
@@ -136,14 +142,14 @@ def operand_absmax(x1, x2=None, owner=None):
     slot = torch.empty(1, dtype=torch.int32, device=x1.device)
     _lib.call("t2h_absmax", ptr(x1), x1.stride(0), x1.shape[1], ptr(x2), 0 if x2 is None else x2.stride(0),
               0 if x2 is None else x2.shape[1], x1.shape[0], ptr(slot))
-    if x2 is None and owner.is_contiguous():
+    if x2 is None and _dense(owner):
         _absmax.put(owner, slot)
     return slot
 
 
 def publish_absmax(t, slot):
-    """register ``slot`` (written by a kernel epilogue) as the maximum of the contiguous tensor ``t``."""
-    if t.is_contiguous():
+    """register ``slot`` (written by a kernel epilogue) as the maximum of the dense tensor ``t``."""
+    if _dense(t):
         _absmax.put(t, slot)
 
 
@@ -175,6 +181,21 @@ def fork2(x):
     if not (torch.is_grad_enabled() and x.requires_grad):
         return x, x
     return _Fork2.apply(x)
+
+
+def relu(x, slope=0.0):
+    """F.relu / F.leaky_relu that hands the operand maximum on: max |relu(x)| <= max |x|, so the bound a GEMM / conv
+    epilogue published for ``x`` also scales the result when it feeds the next fp16 GEMM (an upper bound is all the
+    power-of-two operand scale needs) -- no streaming maximum pass over the activation plane."""
+    out = F.leaky_relu(x, slope) if slope else F.relu(x)
+    slot = _absmax.get(x) if x.is_cuda else None
+    if slot is not None:
+        publish_absmax(out, slot)
+    return out
+
+
+def leaky_relu(x):
+    return relu(x, 0.01)  # F.leaky_relu's default slope
 
 
 def _rowmajor(t):
