@@ -336,22 +336,22 @@ def munich_scene(scale, dev, seed=0):
 def run_infer(args, ctx, scale, steps, warmup):
     import tomosar2height_b200 as t2h
     from tomosar2height_b200.generator import SceneGenerator
-    from tomosar2height_b200.parallel import shard_tiles
     dev = ctx.dev
     cfg = t2h.munich_config()
     model = build_model(cfg, dev).eval()
     pts_d, lo, hi = munich_scene(scale, dev)
     pts_h = pts_d.cpu().pin_memory()
     gen = SceneGenerator(model, lo, hi, cfg.dataset.normalize.z_bound, tiles_per_batch=args.tiles_per_batch)
-    mine = shard_tiles(len(gen.anchors), ctx.rank, ctx.world)  # contiguous block of the anchor list = a strip of the scene
-    rows = [gen.raster_window(*gen.anchors[i])[0] for i in mine] or [0]
-    r_lo, r_hi = max(min(rows), 0), min(max(rows) + 512, gen.n_rows)
-
+    # every rank takes a contiguous block of the anchor list (= a strip of the scene) with a balanced number of
+    # candidate points, derived from the bin table each rank computes anyway: no communication
     def step_resident():
-        return gen.generate(pts_d, tile_range=mine)
+        return gen.generate(pts_d, rank=ctx.rank, world=ctx.world)
 
     def step_e2e():
-        dsm, weight = gen.generate(pts_h.to(dev, non_blocking=True), tile_range=mine)
+        dsm, weight = gen.generate(pts_h.to(dev, non_blocking=True), rank=ctx.rank, world=ctx.world)
+        rows = [gen.raster_window(*gen.anchors[i])[0] for i in gen.last_tile_range] or [0]
+        r_lo, r_hi = max(min(rows), 0), min(max(rows) + 512, gen.n_rows)
+        step_e2e.d2h = 2 * (r_hi - r_lo) * gen.n_cols * 8
         return dsm[r_lo:r_hi].cpu(), weight[r_lo:r_hi].cpu()  # the rank's strip of the partial rasters
 
     for _ in range(warmup):
@@ -360,7 +360,7 @@ def run_infer(args, ctx, scale, steps, warmup):
     ms_e2e, out = ctx.timed(step_e2e, steps)
     return {"ms": ms, "ms_e2e": ms_e2e, "points": pts_d.shape[0] * steps, "px": gen.n_rows * gen.n_cols * steps,
             "tiles": len(gen.anchors), "scene_m": [hi[0] - lo[0], hi[1] - lo[1]], "scene_points": pts_d.shape[0],
-            "h2d": pts_h.numel() * 8, "d2h": 2 * (r_hi - r_lo) * gen.n_cols * 8,
+            "h2d": pts_h.numel() * 8, "d2h": getattr(step_e2e, "d2h", 0),
             "covered_fraction": float((out[1] > 0).double().mean()) if out is not None else None}
 
 

@@ -167,3 +167,35 @@ def test_ctypes_signatures_have_the_arity_of_the_header():
         assert n == len(_lib.SIGNATURES[name]), (name, n, len(_lib.SIGNATURES[name]))
         seen += 1
     assert seen == len(_lib.SIGNATURES)
+
+
+def test_custom_ops_propagate_shapes_without_a_gpu():
+    """The torch custom-op layer (t2h::*) over the C ABI: every op has a register_fake shape function, so meta / fake
+    tensors flow through it with no device (what torch.compile / export need); real CPU tensors still raise."""
+    import torch
+    import tomosar2height_b200  # noqa: F401  (registers the ops)
+    m = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device="meta")
+    n, C, M, B, r = 100, 32, 64, 1, 8
+    keys, cs = m(n, dt=torch.int32), m(M + 1, dt=torch.int32)
+    ops = torch.ops.t2h
+    assert ops.seg_reduce(m(n, C), None, keys, cs, M, 0, 1, r, True).shape == (M, C)
+    assert ops.seg_broadcast(m(M, C), n, None, keys, cs, M, 0, 1, r, True).shape == (n, C)
+    rows, slot = ops.seg_broadcast_add(m(M, C), m(n, C), None, keys, cs, M, 0, 1, r, True)
+    assert rows.shape == (n, C) and slot.shape == (1,)
+    pooled, plane, arg = ops.seg_max(m(n, C), None, None, keys, cs, M, 0, 1, r, True)
+    assert pooled.shape == (n, C) and plane.shape == (M, C) and arg.dtype == torch.int32
+    assert ops.seg_max_bwd(m(n, C), None, arg, n, None, keys, cs, M, 0, 1, r).shape == (n, C)
+    assert ops.bilinear_sample(m(B, r, r, C), m(n, 4), None, None, keys, cs, M, 0, 1, n).shape == (n, C)
+    assert ops.bilinear_sample_bwd(m(n, C), B, r, m(n, 4), None, keys, cs, M, 0, 1).shape == (B, r, r, C)
+    assert ops.upsample_bilinear(m(B, r, r, C), 16, 16).shape == (B, 16, 16, C)
+    assert ops.upsample_bilinear_bwd(m(B, 16, 16, C), r, r).shape == (B, r, r, C)
+    assert ops.cell_index(m(2, n, 2), 256).shape == (2, 1, n)
+    assert ops.gather_rows(m(n, C), m(n, dt=torch.int32)).shape == (n, C)
+    assert ops.linear(m(n, 64), m(n, 64), m(32, 128), m(32), m(n, 32), True).shape == (n, 32)
+    dx1, dx2, dw, db = ops.linear_bwd(m(n, 32), m(n, 64), m(n, 64), m(32, 128), True, True, True, True, True, True)
+    assert dx1.shape == (n, 64) and dx2.shape == (n, 64) and dw.shape == (32, 128) and db.shape == (32,)
+    assert ops.conv3x3(m(B, 16, 16, C), m(64, C, 3, 3), None, False).shape == (B, 16, 16, 64)
+    dx, dwc, dbc = ops.conv3x3_bwd(m(B, 16, 16, 64), m(B, 16, 16, C), m(64, C, 3, 3), False, True, True, True)
+    assert dx.shape == (B, 16, 16, C) and dwc.shape == (64, C, 3, 3) and dbc.shape == (64,)
+    with pytest.raises(RuntimeError):
+        ops.seg_reduce(torch.zeros(n, C), None, torch.zeros(n, dtype=torch.int32), torch.zeros(M + 1, dtype=torch.int32), M, 0, 1, r, True)

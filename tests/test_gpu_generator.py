@@ -40,6 +40,10 @@ def test_scene_generation_matches_oracle():
     # tile-sharded generation (no collective): partial sums of two ranks add up to the same raster
     from tomosar2height_b200.parallel import shard_tiles
     parts = [gen.generate(pts.cuda(), tile_range=shard_tiles(len(gen.anchors), rk, 2)) for rk in range(2)]
+    balanced = [gen.generate(pts.cuda(), rank=rk, world=3) for rk in range(3)]   # blocks balanced by candidate points
+    merged3 = gen.finalize(sum(p[0] for p in balanced), sum(p[1] for p in balanced))
+    assert torch.allclose(sum(p[1] for p in balanced).cpu(), ref_w, rtol=1e-12, atol=0)
+    assert (merged3[covered.cuda()] - dsm[covered.cuda()]).abs().max().item() <= 1e-5 * scale.item()
     merged = gen.finalize(parts[0][0] + parts[1][0], parts[0][1] + parts[1][1])
     # not bitwise: the fp16x3 GEMMs scale their operands by the maximum of the whole batch, so a tile's result
     # depends (at fp32 rounding level) on which other tiles share its batch

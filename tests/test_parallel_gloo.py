@@ -134,3 +134,18 @@ def test_trainer_accumulates_and_reduces_once_per_step():
     mp.spawn(_trainer_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert out[0][0] == out[1][0] == [2, 5]              # an optimizer step every 3 tiles per rank
     assert torch.allclose(out[0][1], out[1][1])          # replicas stay identical: gradients were summed over ranks
+
+
+def test_shard_tiles_weighted_balances_contiguous_blocks():
+    from tomosar2height_b200.parallel import shard_tiles_weighted
+    import random
+    rnd = random.Random(0)
+    for n in (1, 7, 770):
+        weights = [rnd.choice([0, 1, 5, 40, 400]) for _ in range(n)]
+        for world in (1, 2, 4, 8):
+            parts = [list(shard_tiles_weighted(weights, r, world)) for r in range(world)]
+            assert sum(parts, []) == list(range(n))                     # contiguous, complete, disjoint, in rank order
+            if n == 770:
+                loads = [sum(weights[i] for i in p) for p in parts]
+                assert max(loads) <= sum(weights) / world + 400          # within one (heaviest) tile of the ideal share
+    assert [list(shard_tiles_weighted([0, 0, 0], r, 2)) for r in range(2)] == [[0, 1], [2]]  # no weight: by count

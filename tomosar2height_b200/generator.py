@@ -104,12 +104,24 @@ class SceneGenerator:
                     items.append((t, min(1024, last - f), f & 0xFFFFFFFF, f >> 32))
         return items
 
-    def crop_tiles(self, points, todo):
+    def tile_weights(self, starts, nx, ny):
+        """candidate points of every tile of the scene (from the bin table): the work estimate for sharding"""
+        w = []
+        for (x0, y0) in self.anchors:
+            x1, y1 = x0 + self.patch, y0 + self.patch
+            cx0 = min(max(int(math.floor((x0 - self.l) / self.stride)), 0), nx - 1)
+            cx1 = min(max(int(math.floor((x1 - self.l) / self.stride)), 0), nx - 1)
+            cy0 = min(max(int(math.floor((y0 - self.b) / self.stride)), 0), ny - 1)
+            cy1 = min(max(int(math.floor((y1 - self.b) / self.stride)), 0), ny - 1)
+            w.append(sum(starts[cy * nx + cx1 + 1] - starts[cy * nx + cx0] for cy in range(cy0, cy1 + 1)))
+        return w
+
+    def crop_tiles(self, points, todo, binned=None):
         """Strict crop + normalisation of every tile in ``todo`` (a list of anchors) in two launches.
         Returns (flat (P, 4) fp32 rows (x, y, z, 0), per-tile counts as a python list)."""
         from . import _lib
         dev = points.device
-        binned, starts, nx, ny = self._bin(points.double())
+        binned, starts, nx, ny = self._bin(points.double()) if binned is None else binned
         items = self._work_items(todo, starts, nx, ny)
         n_items, n_tiles = len(items), len(todo)
         if n_items == 0:
@@ -137,14 +149,21 @@ class SceneGenerator:
         return t_row, l_col
 
     @torch.no_grad()
-    def generate(self, points, tile_range=None):
+    def generate(self, points, tile_range=None, rank=None, world=None):
         """points (P, 3) world coordinates on the device (float64 recommended for geo-coordinates).
-        Returns (dsm (n_rows, n_cols) float64, weight float64); with ``tile_range`` the un-normalised
-        partial sums of that block of tiles (sum the partials of all ranks, then ``finalize``)."""
+        Returns (dsm (n_rows, n_cols) float64, weight float64); with ``tile_range`` (or ``rank`` / ``world``: a
+        contiguous block of the tile list balanced by candidate points, identical on every rank without
+        communication) the un-normalised partial sums of that block of tiles -- sum the partials of all ranks, then
+        ``finalize``."""
         from . import _lib
+        from .parallel import shard_tiles_weighted
         dev = points.device
+        binned = self._bin(points.double())
+        if tile_range is None and world is not None:
+            tile_range = shard_tiles_weighted(self.tile_weights(*binned[1:]), rank, world)
+            self.last_tile_range = tile_range
         todo = list(self.anchors if tile_range is None else [self.anchors[i] for i in tile_range])
-        flat, counts = self.crop_tiles(points, todo)
+        flat, counts = self.crop_tiles(points, todo, binned)
         dsm = torch.zeros(self.n_rows, self.n_cols, dtype=torch.float64, device=dev)
         weight = torch.zeros_like(dsm)
         S = int(round(self.patch / self.px))

@@ -16,6 +16,24 @@ def shard_tiles(n_tiles: int, rank: int, world: int):
     return range(start, start + base + (1 if rank < rem else 0))
 
 
+def shard_tiles_weighted(weights, rank: int, world: int):
+    """Contiguous partition of the tile list with balanced total WEIGHT (e.g. candidate points per tile): rank r
+    owns the tiles whose cumulative weight midpoint falls into the r-th of `world` equal slices.  Deterministic and
+    identical on every rank (no communication); spatially adjacent tiles stay together."""
+    total = float(sum(weights))
+    if total <= 0:
+        return shard_tiles(len(weights), rank, world)
+    start, end, acc = None, None, 0.0
+    for i, w in enumerate(weights):
+        mid = acc + 0.5 * w
+        owner = min(int(mid * world / total), world - 1)
+        if owner == rank:
+            start = i if start is None else start
+            end = i + 1
+        acc += w
+    return range(start, end) if start is not None else range(0, 0)
+
+
 class FlatGradients:
     """Re-homes every parameter's ``.grad`` into one contiguous buffer so that the whole model is
     reduced by ONE collective (NCCL picks NVLS / NVSwitch on a B200 box).
