@@ -80,24 +80,52 @@ class SceneGenerator:
         self.half_blend = half_blend
 
     # -- binning: one sort of the scene cloud by stride-sized cell --------------------------------------
-    def _bin(self, pts64):
+    def _grid(self):
         nx = max(int(math.ceil((self.r - self.l) / self.stride)), 1)
         ny = max(int(math.ceil((self.t - self.b) / self.stride)), 1)
+        return nx, ny
+
+    def _tile_cells(self, x0, y0, nx, ny):
+        """bin cells (cx0..cx1, cy0..cy1) a tile overlaps"""
+        x1, y1 = x0 + self.patch, y0 + self.patch
+        cx0 = min(max(int(math.floor((x0 - self.l) / self.stride)), 0), nx - 1)
+        cx1 = min(max(int(math.floor((x1 - self.l) / self.stride)), 0), nx - 1)
+        cy0 = min(max(int(math.floor((y0 - self.b) / self.stride)), 0), ny - 1)
+        cy1 = min(max(int(math.floor((y1 - self.b) / self.stride)), 0), ny - 1)
+        return cx0, cx1, cy0, cy1
+
+    def _bin(self, pts64, rank=None, world=None):
+        """Histogram of the cloud over the stride cells (one pass), then a stable sort by cell of the points this rank
+        needs: with ``world`` ranks the tile list is split into contiguous blocks balanced by candidate points (from the
+        histogram: identical on every rank, no communication) and only the cell rows this rank's tiles overlap are sorted.
+        Returns ((binned points, bin starts (host list), nx, ny), tile_range or None)."""
+        from .parallel import shard_tiles_weighted
+        nx, ny = self._grid()
         cx = ((pts64[:, 0] - self.l) / self.stride).floor().clamp(0, nx - 1).long()
         cy = ((pts64[:, 1] - self.b) / self.stride).floor().clamp(0, ny - 1).long()
-        order = torch.argsort(cy * nx + cx, stable=True)
-        starts = torch.searchsorted((cy * nx + cx)[order], torch.arange(nx * ny + 1, device=pts64.device))
-        return pts64[order].contiguous(), starts.tolist(), nx, ny
+        cell = cy * nx + cx
+        counts = torch.bincount(cell, minlength=nx * ny)
+        tile_range = None
+        if world is not None:
+            acc = [0] + counts.cumsum(0).tolist()
+            tile_range = shard_tiles_weighted(self.tile_weights(acc, nx, ny), rank, world)
+            rows = [self._tile_cells(*self.anchors[i], nx, ny) for i in tile_range]
+            cy_lo = min((r[2] for r in rows), default=0)
+            cy_hi = max((r[3] for r in rows), default=-1)
+            keep = (cy >= cy_lo) & (cy <= cy_hi)
+            pts64, cell = pts64[keep], cell[keep]
+            inside = torch.zeros(ny, dtype=torch.bool, device=counts.device)
+            inside[cy_lo:cy_hi + 1] = True
+            counts = counts * inside.repeat_interleave(nx)
+        order = torch.argsort(cell, stable=True)
+        starts = [0] + counts.cumsum(0).tolist()
+        return (pts64[order].contiguous(), starts, nx, ny), tile_range
 
     def _work_items(self, todo, starts, nx, ny):
         """Candidate row ranges of every tile (the bin cells it overlaps), cut into <= 1024-row work items."""
         items = []
         for t, (x0, y0) in enumerate(todo):
-            x1, y1 = x0 + self.patch, y0 + self.patch
-            cx0 = min(max(int(math.floor((x0 - self.l) / self.stride)), 0), nx - 1)
-            cx1 = min(max(int(math.floor((x1 - self.l) / self.stride)), 0), nx - 1)
-            cy0 = min(max(int(math.floor((y0 - self.b) / self.stride)), 0), ny - 1)
-            cy1 = min(max(int(math.floor((y1 - self.b) / self.stride)), 0), ny - 1)
+            cx0, cx1, cy0, cy1 = self._tile_cells(x0, y0, nx, ny)
             for cy in range(cy0, cy1 + 1):
                 first, last = starts[cy * nx + cx0], starts[cy * nx + cx1 + 1]
                 for f in range(first, last, 1024):
@@ -108,11 +136,7 @@ class SceneGenerator:
         """candidate points of every tile of the scene (from the bin table): the work estimate for sharding"""
         w = []
         for (x0, y0) in self.anchors:
-            x1, y1 = x0 + self.patch, y0 + self.patch
-            cx0 = min(max(int(math.floor((x0 - self.l) / self.stride)), 0), nx - 1)
-            cx1 = min(max(int(math.floor((x1 - self.l) / self.stride)), 0), nx - 1)
-            cy0 = min(max(int(math.floor((y0 - self.b) / self.stride)), 0), ny - 1)
-            cy1 = min(max(int(math.floor((y1 - self.b) / self.stride)), 0), ny - 1)
+            cx0, cx1, cy0, cy1 = self._tile_cells(x0, y0, nx, ny)
             w.append(sum(starts[cy * nx + cx1 + 1] - starts[cy * nx + cx0] for cy in range(cy0, cy1 + 1)))
         return w
 
@@ -121,7 +145,7 @@ class SceneGenerator:
         Returns (flat (P, 4) fp32 rows (x, y, z, 0), per-tile counts as a python list)."""
         from . import _lib
         dev = points.device
-        binned, starts, nx, ny = self._bin(points.double()) if binned is None else binned
+        binned, starts, nx, ny = self._bin(points.double())[0] if binned is None else binned
         items = self._work_items(todo, starts, nx, ny)
         n_items, n_tiles = len(items), len(todo)
         if n_items == 0:
@@ -156,12 +180,12 @@ class SceneGenerator:
         communication) the un-normalised partial sums of that block of tiles -- sum the partials of all ranks, then
         ``finalize``."""
         from . import _lib
-        from .parallel import shard_tiles_weighted
         dev = points.device
-        binned = self._bin(points.double())
         if tile_range is None and world is not None:
-            tile_range = shard_tiles_weighted(self.tile_weights(*binned[1:]), rank, world)
+            binned, tile_range = self._bin(points.double(), rank, world)
             self.last_tile_range = tile_range
+        else:
+            binned, _ = self._bin(points.double())
         todo = list(self.anchors if tile_range is None else [self.anchors[i] for i in tile_range])
         flat, counts = self.crop_tiles(points, todo, binned)
         dsm = torch.zeros(self.n_rows, self.n_cols, dtype=torch.float64, device=dev)
