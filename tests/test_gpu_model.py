@@ -235,3 +235,25 @@ def test_ragged_batch_equals_per_tile_forward_backward():
         # flips a few ReLU / max-pool selections; the mean deviation stays at rounding level
         diff = (grads[n] - p.grad).abs()
         assert float(diff.max()) <= 5e-3 * denom and float(diff.mean()) <= 1e-4 * denom, n
+
+
+def test_alto_unet_tensor_arguments_carry_gradients():
+    """UNet.forward(p: Tensor, x, c) -- the reference signature (alto.py:368): the gradient reaches ``c`` through the
+    differentiable row permutation (t2h::gather_rows / scatter_rows) exactly as on the topology path."""
+    cfg, params, model = _build("berlin_small")
+    enc = model.point_encoder
+    from tomosar2height_b200.topology import Topology
+    import tomosar2height_b200.functional as T
+    cloud = synthetic_cloud(1, 2000, seed=4).cuda()
+    R, C = enc.reso_plane, enc.c_dim
+    g = torch.Generator().manual_seed(0)
+    c0 = torch.randn(1, 2000, C, generator=g).cuda()
+    topo = Topology(cloud, R)
+    plane = T.plane_to_nchw(T.seg_mean(topo.sort_rows(c0.view(-1, C)), topo.level(R)), 1, R).detach()
+    w = torch.randn(1, C, R, R, generator=g).cuda()
+    c_a = c0.clone().requires_grad_(True)
+    (enc.unet(cloud, {'xy': plane}, c_a) * w).sum().backward()
+    c_b = c0.clone().requires_grad_(True)
+    (enc.unet(topo, {'xy': plane}, topo.sort_rows(c_b.view(-1, C))) * w).sum().backward()
+    assert c_a.grad is not None and float(c_a.grad.abs().max()) > 0
+    assert torch.equal(c_a.grad, c_b.grad)

@@ -27,7 +27,18 @@ class ConvDecoder(nn.Module):
         x1 = self.act(apply_conv(self.conv1, x))
         x2 = self.act(apply_conv(self.conv2, x1))
         x3 = self.act(apply_conv(self.conv3, x2))
-        return apply_conv(self.conv4, torch.cat([x, x1, x2, x3], dim=1))
+        if not x.is_cuda:
+            return apply_conv(self.conv4, torch.cat([x, x1, x2, x3], dim=1))
+        # conv4 (1x1) over the dense-skip concatenation (pixel.py:31) = sum of its four column blocks applied to the
+        # four tensors: two GEMM launches with two K sources each, the second taking the first as residual -- the
+        # 288-channel concatenation at 512^2 (1.2 GB per 4 tiles, plus its gradient and the slicing copies in the
+        # backward) is never materialised
+        w = self.conv4.weight.reshape(self.conv4.weight.shape[0], -1)
+        c0, c1, c2 = x.shape[1], x.shape[1] + x1.shape[1], x.shape[1] + x1.shape[1] + x2.shape[1]
+        nhwc = lambda t: t.permute(0, 2, 3, 1)
+        y = linear(nhwc(x), w[:, :c1], self.conv4.bias, x2=nhwc(x1))
+        y = linear(nhwc(x2), w[:, c1:], None, x2=nhwc(x3), residual=y)
+        return y.permute(0, 3, 1, 2)
 
 
 class FCDecoder(nn.Module):

@@ -57,8 +57,12 @@ class _SplitCache:
             split = self._split(builder(weight.detach()).contiguous(), f16)
         if capture_mode:
             return split  # lives in the graph's private pool; not a cache entry
-        if len(self._store) > 4096:
-            self._store.clear()
+        if len(self._store) > 256:
+            # entries of temporaries (reshaped / padded / permuted weight views are new tensors on every call) only
+            # hold dead weak references: drop them so that their hi / lo device tensors are freed
+            self._store = {k: v for k, v in self._store.items() if v[0]() is not None}
+            if len(self._store) > 4096:
+                self._store.clear()
         self._store[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), split)
         return split
 
@@ -66,6 +70,11 @@ class _SplitCache:
         c1 = weight.shape[1] if c1 is None else c1
         return self._lookup(weight, (id(weight), c0, c1, transposed),
                             lambda w: w[:, c0:c1].t() if transposed else w[:, c0:c1], f16)
+
+    def invalidate(self):
+        """forget every derived split (call after the weights were changed behind autograd's back, e.g. by a captured
+        optimizer step or a ``.data`` write, which do not bump the version counter)"""
+        self._store.clear()
 
     def get_matrix(self, weight, tag, builder, f16=False):
         """split of ``builder(weight.detach())`` (a 2-D fp32 matrix), cached per parameter version."""
