@@ -63,7 +63,8 @@ def test_linear_epilogues_and_concat():
 
 
 @pytest.mark.parametrize("rows,K,N", [(128, 32, 32), (1000, 64, 32), (5000, 32, 64), (3000, 128, 256), (2000, 512, 1024),
-                                     (4100, 1024, 512), (130, 96, 48), (9000, 256, 128), (40, 64, 64)])
+                                     (4100, 1024, 512), (130, 96, 48), (9000, 256, 128), (40, 64, 64), (33, 256, 256),
+                                     (70000, 512, 256), (129, 256, 512)])
 @pytest.mark.parametrize("relu_in", [False, True])
 @pytest.mark.parametrize("flavour", ["f16", "tf32"])
 def test_linear_autograd_matches_fp64(rows, K, N, relu_in, flavour, monkeypatch):

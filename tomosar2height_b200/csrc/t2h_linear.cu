@@ -1050,6 +1050,199 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_d, S::TMEM_COLS);
 }
 
+// ---- weight gradient over CTA PAIRS (fp16x3, n_out and k_in multiples of 256) --------------------------
+// wgrad_x3_kernel<128, true> converts 8192 operand elements (g 32 x 128 and x 32 x 128) for every 128 x 128 x 32
+// MMA triple: ~2100 warp instructions against the 4 x 384 issue slots that the MMAs of a stage last -- it is
+// issue-bound by construction (profiles/r02_ncu_gemm_full.txt: tensor pipe 37 % active at 58 % issue utilisation).
+// Here the two CTAs of a cluster (the two SMs of a TPC) own one 256 x 256 tile of dW for a slice of the rows:
+//   A = g^T, M = 256: each CTA splits ITS 128 columns of g into its own tensor memory (lanes = rows of dW),
+//   B = x,   N = 256: each CTA converts ITS 128 columns of x into its own shared memory (tcgen05.mma.cta_group::2
+//                     reads half of the N extent from either CTA),
+//   D: 128 lanes x 256 fp32 columns in either CTA.
+// The same 8192 conversions per CTA and stage now feed 128 x 256 x 32 x 3 of MMA work per SM (768 cycles): half the
+// conversion work and half the L2 -> SM bytes per MMA cycle, and four 48 KB stages fit beside the accumulator.
+// Warps: 0 producer (own tiles, own barrier), 1 MMA issuer (leader CTA only), 2-5 g^T -> tensor memory + bias
+// gradient, 6-9 x -> fp16 hi / lo MN-major tiles; all eight drain the accumulator (32-column blocks 0-3 / 4-7).
+constexpr int WGP_STAGES = 4;
+constexpr int WGP_X_RAW = 4 * WG_GROUP_BYTES;            // this CTA's 128 columns of x: four 32-float boxes
+constexpr int WGP_X16 = WG_ROWS * 128 * 2;               // one fp16 operand tile
+constexpr int WGP_STAGE_BYTES = WG_A_BYTES + WGP_X_RAW + 2 * WGP_X16;   // g raw | x raw | x hi | x lo
+constexpr int WGP_TOTAL = WGP_STAGES * WGP_STAGE_BYTES + 256 + 1024;
+constexpr int WGP_TILE = 256;                            // dW tile edge (both ways)
+constexpr int WGP_A_COLS = 32;                           // TMEM columns of (g hi | g lo) per stage
+constexpr int WGP_TMEM_COLS = 512;                       // 256 accumulator + 4 x 32 operand columns
+static_assert(WGP_TOTAL <= 227 * 1024, "shared memory");
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, const WgradArgs p,
+                      const int tiles_k, const int n_tiles) {
+  constexpr int STAGES = WGP_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + STAGES * WGP_STAGE_BYTES;
+  auto full_tma = [&](int s) { return bars + 8u * s; };                  // this CTA's tiles have landed
+  auto full_ab = [&](int s) { return bars + 8u * (STAGES + s); };        // both CTAs' operands are converted (leader's)
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };      // the pair's MMAs have read the stage
+  const uint32_t tmem_full = bars + 8u * (3 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * WGP_STAGE_BYTES + 8 * (3 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1);
+  const int tile = pair % n_tiles, split = pair / n_tiles;
+  const int n0 = (tile / tiles_k) * WGP_TILE + (int)rank * 128;   // this CTA's columns of g = its rows of dW
+  const int kd0 = (tile % tiles_k) * WGP_TILE;                    // columns of dW held by the accumulator
+  const int kx0 = kd0 + (int)rank * 128;                          // this CTA's columns of x
+  const int64_t r_begin = (int64_t)split * p.rows_per_split;
+  const int64_t r_end = min(r_begin + p.rows_per_split, p.rows);
+  const int n_iter = r_end > r_begin ? (int)((r_end - r_begin + WG_ROWS - 1) / WG_ROWS) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_tma(s), 1);
+      mbar_init(full_ab(s), 16);   // one arrival per transform warp of both CTAs
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, WGP_TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(empty(s), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t stage = base + s * WGP_STAGE_BYTES;
+        const int r = (int)(r_begin + (int64_t)it * WG_ROWS);
+        mbar_arrive_expect_tx(full_tma(s), (uint32_t)(WG_A_BYTES + WGP_X_RAW));
+        tma_load_2d(stage, &tm_g, full_tma(s), n0, r);   // the global tail is zero-filled by TMA
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq)
+          tma_load_2d(stage + WG_A_BYTES + gq * WG_GROUP_BYTES, &tm_x, full_tma(s), kx0 + gq * 32, r);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {  // the leader's MMAs drive the tensor cores of both SMs
+      constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M, WGP_TILE, 0, 1);  // A from TMEM, B MN-major
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait_cluster(full_ab(s), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_hi0 = base + s * WGP_STAGE_BYTES + WG_A_BYTES + WGP_X_RAW;
+          const uint64_t d_hi0 = make_smem_desc(b_hi0, 4096, 1024, kLayoutSW128);
+          const uint64_t d_lo0 = make_smem_desc(b_hi0 + WGP_X16, 4096, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < WG_ROWS / 16; ++k) {
+            const uint64_t b_hi = d_hi0 + (uint64_t)(k * 128), b_lo = d_lo0 + (uint64_t)(k * 128);  // two 8-row atoms
+            const uint32_t a_hi = tmem_d + WGP_TILE + s * WGP_A_COLS + k * 8, a_lo = a_hi + 16;
+            mma_f16_ts_pair(tmem_d, a_lo, b_hi, idesc, (it | k) != 0);
+            mma_f16_ts_pair(tmem_d, a_hi, b_lo, idesc, 1);
+            mma_f16_ts_pair(tmem_d, a_hi, b_hi, idesc, 1);
+          }
+          mma_commit_pair(empty(s));
+        }
+        __syncwarp();
+      }
+      if (n_iter > 0 && elect_one()) mma_commit_pair(tmem_full);
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int t = quarter * 32 + lane;  // TMEM lane = column n0 + t of g
+    const bool a_warp = warp < 6;
+    const float sg = pow2f(f16_scale_exp(*p.g_absmax));
+    const float sx = pow2f(f16_scale_exp(*p.x_absmax));
+    float bias_acc = 0.f;
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(full_tma(s), ph);
+      if (a_warp) {
+        // column t of the [32 rows][128] tile -> TMEM lane t as 16 + 16 packed fp16 pairs (rows 2c, 2c + 1)
+        const float* gcol = reinterpret_cast<const float*>(base_ptr + s * WGP_STAGE_BYTES) + t;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int r = 0; r < WG_ROWS; r += 2) {
+          const float v0 = gcol[r * 128], v1 = gcol[(r + 1) * 128];
+          bias_acc += v0;
+          bias_acc += v1;
+          split_f16x2(v0 * sg, v1 * sg, hi[r >> 1], lo[r >> 1]);
+        }
+        const uint32_t a_dst = tmem_d + ((uint32_t)(quarter * 32) << 16) + WGP_TILE + s * WGP_A_COLS;
+        tmem_st_32x16(a_dst, hi);
+        tmem_st_32x16(a_dst + 16, lo);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        // fp32 [4 boxes][32 rows][32 floats] -> fp16 hi / lo, MN-major SWIZZLE_128B (two 64-wide groups 4096 B apart);
+        // 16 consecutive lanes take one row of a box pair: 128 contiguous bytes in, one swizzled 128-byte row out
+        const int tb = threadIdx.x - 192;
+        const float4* raw = reinterpret_cast<const float4*>(base_ptr + s * WGP_STAGE_BYTES + WG_A_BYTES);
+        uint8_t* bhi = base_ptr + s * WGP_STAGE_BYTES + WG_A_BYTES + WGP_X_RAW;
+        uint8_t* blo = bhi + WGP_X16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int unit = (tb >> 4) + 8 * i, r = unit & 31, j = tb & 15;
+          const int box = 2 * (unit >> 5) + (j >> 3), q = j & 7;
+          float4 v = raw[box * 256 + r * 8 + q];
+          if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          uint2 h, l;
+          split_f16x2(v.x * sx, v.y * sx, h.x, l.x);
+          split_f16x2(v.z * sx, v.w * sx, h.y, l.y);
+          const int chunk = ((box & 1) << 2) | (q >> 1);  // 16-byte chunk of the 128-byte row (64 fp16 along k_in)
+          const int off = (box >> 1) * 4096 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4) + ((q & 1) << 3);
+          *reinterpret_cast<uint2*>(bhi + off) = h;
+          *reinterpret_cast<uint2*>(blo + off) = l;
+        }
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) {  // one (possibly remote) arrival per warp
+        if (rank != 0) mbar_arrive_remote(full_ab(s), 0);
+        else mbar_arrive(full_ab(s));
+      }
+    }
+    const int n = n0 + t;
+    if (a_warp && p.partial_bias && kd0 == 0) p.partial_bias[(int64_t)split * p.n_out + n] = bias_acc;
+    float* dst = p.partial + ((int64_t)split * p.n_out + n) * p.k_in + kd0;
+    if (n_iter > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    const float inv = pow2f(-(f16_scale_exp(*p.g_absmax) + f16_scale_exp(*p.x_absmax)));
+#pragma unroll 1
+    for (int c0 = a_warp ? 0 : 128; c0 < (a_warp ? 128 : 256); c0 += 32) {
+      float v[32];
+      if (n_iter > 0) {
+        __syncwarp();
+        tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+#pragma unroll
+      for (int gq = 0; gq < 8; ++gq)
+        st4(dst + c0 + gq * 4, make_float4(v[gq * 4] * inv, v[gq * 4 + 1] * inv, v[gq * 4 + 2] * inv, v[gq * 4 + 3] * inv));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer's shared and tensor memory are not read by the pair's MMAs any more
+  if (warp == 1) tmem_dealloc_pair(tmem_d, WGP_TMEM_COLS);
+}
+
 // dst[n, k] (ld) = sum over splits of partial[s, n, k]; TPO threads share one float4 of the output
 // (narrow layers have few outputs but hundreds of row splits), fixed strided order + xor tree
 template <int TPO>
@@ -1703,6 +1896,41 @@ extern "C" int t2h_linear_wgrad_f16(const float* grad_out, int64_t ld_g, const u
   a.conv = 0; a.tiles_x = a.units_per_img = a.cin = 0;
   a.g_absmax = g_absmax; a.x_absmax = x_absmax;
   a.a_cols = n_out >= BLOCK_M ? BLOCK_M : ((n_out + 31) / 32) * 32;
+  if (rows > 0 && n_out % WGP_TILE == 0 && k_in % WGP_TILE == 0 && ablation_switch("T2H_WGRAD_PAIR", 1)) {
+    // wide layers: CTA pairs on 256 x 256 tiles, one wave of pairs (never more splits than the workspace holds)
+    const int tiles_k = k_in / WGP_TILE, n_tiles = (n_out / WGP_TILE) * tiles_k;
+    int64_t want = (kSMs / 2) / n_tiles;
+    if (want < 1) want = 1;
+    if (want > splits) want = splits;
+    per = (rows + want - 1) / want;
+    a.rows_per_split = ((per + WG_ROWS - 1) / WG_ROWS) * WG_ROWS;
+    const int psplits = (int)((rows + a.rows_per_split - 1) / a.rows_per_split);  // every split holds rows
+    a.partial_bias = grad_b ? a.partial + (size_t)psplits * n_out * k_in : nullptr;
+    CUtensorMap mg, mx;
+    if (!make_map(&mg, grad_out, n_out, rows, ld_g, 128, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
+    if (!make_map(&mx, x, k_in, rows, ld_x, 32, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
+    if (cudaFuncSetAttribute(wgrad_f16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGP_TOTAL) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return T2H_ERR_CUDA;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * n_tiles * psplits));
+    cfg.blockDim = dim3(WG_THREADS);
+    cfg.dynamicSmemBytes = WGP_TOTAL;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, wgrad_f16_pair_kernel, mg, mx, a, tiles_k, n_tiles) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return T2H_ERR_CUDA;
+    }
+    launch_wgrad_reduce(a.partial, a.partial_bias, psplits, n_out, k_in, grad_w, ld_w, grad_b, s);
+    T2H_CHECK_LAUNCH();
+    return T2H_OK;
+  }
   if (rows > 0) {
     CUtensorMap mg, mx;
     if (!make_map(&mg, grad_out, n_out, rows, ld_g, a.a_cols, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) return T2H_ERR_CUDA;
