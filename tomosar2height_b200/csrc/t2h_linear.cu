@@ -324,21 +324,27 @@ constexpr int P_THREADS = 448;  // producer, MMA, 4 transform warps, 2 x 4 epilo
 // HALF of the weight tile (64 of the 128 output columns; the MMA reads both halves) and drains its own
 // accumulator.  48 KB instead of 64 KB per step and SM, so four stages fit: fewer bytes per MMA cycle and a
 // deeper load pipeline, which is what bounds the single-CTA kernel.
-template <bool F16, int BLOCK_N, int WSTEPS = 0, bool PAIR = false>
+// DS (CTA pairs): TWO epilogue staging slots per group and three load stages.  With one slot a group's blocks run
+// strictly one after the other -- wait until the previous store has been read out of the slot, load the mask /
+// residual block into it (a full memory latency), post-process, store -- which bounds the layers with K <= 512
+// (a tile's MMAs last 2-4 stages).  With two slots both mask / residual loads of a tile are issued before the
+// accumulator is waited for, and a store drains while the next block is processed.
+template <bool F16, int BLOCK_N, int WSTEPS = 0, bool PAIR = false, bool DS = false>
 struct PSmem {
   static constexpr bool WRES = WSTEPS > 0;
-  static constexpr int STAGES = PAIR ? 4 : (WRES ? (WSTEPS <= 2 ? 4 : 2) : (F16 ? (BLOCK_N == 128 ? 3 : 4) : (BLOCK_N == 128 ? 4 : 6)));
+  static constexpr int STAGES = PAIR ? (DS ? 3 : 4) : (WRES ? (WSTEPS <= 2 ? 4 : 2) : (F16 ? (BLOCK_N == 128 ? 3 : 4) : (BLOCK_N == 128 ? 4 : 6)));
   static constexpr int X_BYTES = (F16 ? 2 : 1) * A_BYTES;
   static constexpr int W_BYTES = (F16 ? BLOCK_N * 64 * 2 : BLOCK_N * BLOCK_K * 4) / (PAIR ? 2 : 1);
   static constexpr int STAGE_BYTES = WRES ? X_BYTES : X_BYTES + 2 * W_BYTES;   // x raw (| w hi | w lo)
   static constexpr int WREGION_BYTES = WSTEPS * 2 * W_BYTES;       // resident weight: per k-step (w hi | w lo)
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + WREGION_BYTES;
-  static constexpr int STAGING_BYTES = 2 * A_BYTES;                // epilogue staging: two 32-column blocks at a time
+  static constexpr int STAGING_BYTES = (DS ? 4 : 2) * A_BYTES;     // epilogue staging: 32-column blocks, one (DS: two) per group
   static constexpr int TOTAL = STAGING_OFF + STAGING_BYTES + 256 + 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int A_COL0 = 2 * BLOCK_N;
   static_assert(!WRES || (F16 && BLOCK_N == 128), "weight-resident: fp16, 128-wide tiles");
   static_assert(!PAIR || (F16 && BLOCK_N == 128 && !WRES), "CTA pairs: fp16, 128-wide tiles");
+  static_assert(!DS || PAIR, "double staging slots: CTA pairs");
   static_assert(A_COL0 + STAGES * 64 <= 512, "tensor memory: two accumulators + the split x stages");
   static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
@@ -353,13 +359,13 @@ __device__ __forceinline__ int f16_scale_exp(uint32_t absmax_bits) {
 }
 __device__ __forceinline__ float pow2f(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
 
-template <bool F16, int BLOCK_N, int WSTEPS, bool PAIR>
+template <bool F16, int BLOCK_N, int WSTEPS, bool PAIR, bool DS>
 __global__ void __launch_bounds__(P_THREADS, 1)
 linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                                 const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
                                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_aux,
                                 const LinearArgs p, const int64_t n_tiles_total) {
-  using S = PSmem<F16, BLOCK_N, WSTEPS, PAIR>;
+  using S = PSmem<F16, BLOCK_N, WSTEPS, PAIR, DS>;
   // PAIR: rank of this CTA in its pair; the pair (not the CTA) walks the list of 256-row tiles
   const uint32_t rank = PAIR ? cluster_ctarank() : 0;
   const int64_t vblock = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
@@ -383,6 +389,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
   auto aux_bar = [&](int g) { return bars + 8u * (3 * STAGES + 4 + g); };
   const uint32_t w_full = bars + 8u * (3 * STAGES + 7);
   auto w_pair = [&](int s) { return bars + 8u * (3 * STAGES + 8 + s); };  // PAIR: both weight halves landed (leader's)
+  auto aux_bar2 = [&](int g, int j) { return bars + 8u * (4 * STAGES + 8 + 2 * g + j); };  // DS: per group and slot
   const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 6);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(staging_ptr + S::STAGING_BYTES + 8 * (3 * STAGES + 6));
   // epilogue threads that hand an accumulator back per tile: both groups, or (32-wide tiles) the one that owns the tile
@@ -402,6 +409,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
       mbar_init(acc_full(a), 1);
       mbar_init(acc_empty(a), PAIR ? 2 * EPI_ARRIVALS : EPI_ARRIVALS);  // PAIR: both CTAs' epilogues, on the leader's
       mbar_init(aux_bar(a), 1);
+      if (DS) { mbar_init(aux_bar2(a, 0), 1); mbar_init(aux_bar2(a, 1), 1); }
     }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -613,12 +621,13 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
     const int eh = (warp - 6) >> 2;
     const int t = quarter * 32 + lane;
     const bool leader = ((warp - 6) & 3) == 0 && lane == 0;
-    const uint32_t my_staging = staging + eh * A_BYTES;
-    float* srow = reinterpret_cast<float*>(staging_ptr + eh * A_BYTES + t * 128);
+    const uint32_t group_staging = staging + eh * (DS ? 2 : 1) * A_BYTES;
+    float* group_srow = reinterpret_cast<float*>(staging_ptr + eh * (DS ? 2 : 1) * A_BYTES + t * 128);
     // fp16 mode: undo the two power-of-two operand scales (|exponent| <= 63 each, so the product is a float)
     const float inv = F16 ? pow2f(-(f16_scale_exp(*p.x_absmax) + f16_scale_exp(*p.w_absmax))) : 1.f;
     const int epi_mode = (p.mask && p.residual) || (p.aux_kind == 0 && (p.mask || p.residual)) ? 3 : p.aux_kind;
     uint32_t aux_phase = 0;
+    bool prev_two = false;  // DS: the group's latest store came from slot 1
     float out_max = 0.f;
     int64_t local = 0;
     for (int64_t tile = vblock; tile < n_tiles_total; tile += vgrid, ++local) {
@@ -632,19 +641,45 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
       const bool row_ok = row < p.rows;
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
       bool have_acc = false;
+      const bool two = DS && eh + 2 < n_blocks;  // DS: the group has a second block in this tile (slot 1)
+      if (DS && p.aux_kind && leader && eh < n_blocks) {
+        // both mask / residual blocks of the tile go out before the accumulator is waited for; a slot is free
+        // once the store that last used it has been read (slot 0: all but the latest store, if that was slot 1's)
+        if (prev_two) tma_store_wait_read_but_one(); else tma_store_wait_read();
+        mbar_arrive_expect_tx(aux_bar2(eh, 0), A_BYTES);
+        if (p.conv) tma_load_4d(group_staging, &tm_aux, aux_bar2(eh, 0), n0 + eh * 32, px0, py0, img);
+        else tma_load_2d(group_staging, &tm_aux, aux_bar2(eh, 0), n0 + eh * 32, m0);
+        if (two) {
+          tma_store_wait_read();
+          mbar_arrive_expect_tx(aux_bar2(eh, 1), A_BYTES);
+          if (p.conv) tma_load_4d(group_staging + A_BYTES, &tm_aux, aux_bar2(eh, 1), n0 + (eh + 2) * 32, px0, py0, img);
+          else tma_load_2d(group_staging + A_BYTES, &tm_aux, aux_bar2(eh, 1), n0 + (eh + 2) * 32, m0);
+        }
+      }
 #pragma unroll 1
       for (int cb = (BLOCK_N == 32 ? 0 : eh); cb < n_blocks; cb += 2) {
-        // the slot is free once the group's previous store has been read
-        if (leader) tma_store_wait_read();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + eh) : "memory");
-        if (p.aux_kind) {
+        const int slot = DS ? (cb - eh) >> 1 : 0;
+        const uint32_t my_staging = group_staging + slot * A_BYTES;
+        float* srow = group_srow + slot * (A_BYTES / 4);
+        if (DS && p.aux_kind) {
+          mbar_wait(aux_bar2(eh, slot), (aux_phase >> slot) & 1u);
+          aux_phase ^= 1u << slot;
+        } else {
+          // the slot is free once the store that last used it has been read
           if (leader) {
-            mbar_arrive_expect_tx(aux_bar(eh), A_BYTES);
-            if (p.conv) tma_load_4d(my_staging, &tm_aux, aux_bar(eh), n0 + cb * 32, px0, py0, img);
-            else tma_load_2d(my_staging, &tm_aux, aux_bar(eh), n0 + cb * 32, m0);
+            if (DS && (slot == 1 || prev_two)) tma_store_wait_read_but_one();
+            else tma_store_wait_read();
           }
-          mbar_wait(aux_bar(eh), aux_phase);
-          aux_phase ^= 1;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eh) : "memory");
+          if (p.aux_kind) {
+            if (leader) {
+              mbar_arrive_expect_tx(aux_bar(eh), A_BYTES);
+              if (p.conv) tma_load_4d(my_staging, &tm_aux, aux_bar(eh), n0 + cb * 32, px0, py0, img);
+              else tma_load_2d(my_staging, &tm_aux, aux_bar(eh), n0 + cb * 32, m0);
+            }
+            mbar_wait(aux_bar(eh), aux_phase);
+            aux_phase ^= 1;
+          }
         }
         if (!have_acc) {
           mbar_wait(acc_full(acc), acc_ph);
@@ -725,6 +760,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           tma_store_commit();
         }
       }
+      if (DS && eh < n_blocks) prev_two = two;
       if (BLOCK_N != 32 && !have_acc) {
         // a group without a block in this (narrow last) tile still takes part in the accumulator hand-over, in step
         mbar_wait(acc_full(acc), acc_ph);
@@ -1485,12 +1521,12 @@ static bool make_map_4d(CUtensorMap* map, const float* ptr, uint64_t C, uint64_t
 
 struct PlaneGeom { int B, H, W; };  // conv mode only
 
-template <bool F16, int BLOCK_N, int WSTEPS = 0, bool PAIR = false>
+template <bool F16, int BLOCK_N, int WSTEPS = 0, bool PAIR = false, bool DS = false>
 static int launch_linear_persistent(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& whi, const CUtensorMap& wlo,
                                     const CUtensorMap& mout, const CUtensorMap& maux, const LinearArgs& args,
                                     cudaStream_t stream) {
-  auto kern = linear_x3_persistent_kernel<F16, BLOCK_N, WSTEPS, PAIR>;
-  using S = PSmem<F16, BLOCK_N, WSTEPS, PAIR>;
+  auto kern = linear_x3_persistent_kernel<F16, BLOCK_N, WSTEPS, PAIR, DS>;
+  using S = PSmem<F16, BLOCK_N, WSTEPS, PAIR, DS>;
   // per device and idempotent; set on every launch so that the entry point keeps no state
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
     (void)cudaGetLastError();
@@ -1714,6 +1750,13 @@ extern "C" int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const 
   if (pair && rows >= 2 * BLOCK_M) {
     CUtensorMap whi2, wlo2;
     if (!make_map_f16(&whi2, w_hi, k_total, n_out, 64) || !make_map_f16(&wlo2, w_lo, k_total, n_out, 64)) return T2H_ERR_CUDA;
+    // Two staging slots per epilogue group (and three load stages) where a mask / residual block is read per output
+    // block and a tile's MMAs are short (K <= 256): measured on 2^20 rows, K = 256 -> N = 512 with a mask 1.26 ->
+    // 1.07 ms, K = 128 -> N = 256 0.73 -> 0.55 ms; with K >= 512 the fourth load stage is worth more (K = 512 ->
+    // N = 256: 0.82 vs 0.97 ms), and without a mask / residual it is a wash.  T2H_LINEAR_DS = 0 never, 2 always.
+    const int ds = ablation_switch("T2H_LINEAR_DS", 1);
+    if (ds == 2 || (ds == 1 && a.aux_kind && a.k_chunks <= 8))
+      return launch_linear_persistent<true, 128, 0, true, true>(m1, m2, whi2, wlo2, mout, maux, a, (cudaStream_t)stream);
     return launch_linear_persistent<true, 128, 0, true>(m1, m2, whi2, wlo2, mout, maux, a, (cudaStream_t)stream);
   }
   // K <= 256: the weight tile of a CTA's N-tile can stay resident in shared memory (T2H_LINEAR_WRES=1).  OFF by

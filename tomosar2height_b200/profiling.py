@@ -175,8 +175,8 @@ def _shape(name, a):
         return (a[1] * a[2] * a[3], 9 * a[4], a[9])
     if name == "t2h_conv3x3_wgrad_f16":
         return (a[4] * a[5] * a[6], 9 * a[7], a[8])
-    if name == "t2h_linear_fwd_f16":
-        return (a[6], a[2] + a[5], a[11])
+    if name == "t2h_linear_fwd_f16":  # + epilogue operand: mask (input gradient), residual, none
+        return (a[6], a[2] + a[5], a[11], "mask" if a[14] else ("res" if a[16] else ""))
     if name == "t2h_linear_wgrad_f16":
         return (a[6], a[8], a[7])
     if name == "t2h_conv3x3_fwd":

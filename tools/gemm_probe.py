@@ -62,7 +62,7 @@ for K, N in [(256, 512), (512, 256), (128, 256), (256, 128), (512, 1024), (1024,
     print(line)
     g = torch.randn(rows, N, device=dev)
     gs = slot_of(g)
-    n_ws = int(_lib.lib.t2h_linear_wgrad_workspace_bytes(rows, N, K))
+    n_ws = int(_lib.load().t2h_linear_wgrad_workspace_bytes(rows, N, K))
     wsb = torch.empty(n_ws, dtype=torch.uint8, device=dev)
     dw, db = torch.empty(N, K, device=dev), torch.empty(N, device=dev)
     ms = timeit(lambda: _lib.call("t2h_linear_wgrad_f16", ptr(g), g.stride(0), ptr(gs), ptr(x), x.stride(0), ptr(xs_), rows, N, K,

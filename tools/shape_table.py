@@ -21,4 +21,4 @@ tab = shape_table(kt)
 tot = sum(r[3] for r in tab)
 print(f"GEMM/conv kernel time {tot:.1f} ms per micro-batch of {mb} tiles")
 for name, shp, n, ms, tf in tab[:40]:
-    print(f"{ms:8.3f} ms {ms/tot*100:5.1f}%  n={n:3d} {tf:7.1f} TF/s  {name[4:]:16s} rows={shp[0]:8d} K={shp[1]:5d} N={shp[2]:5d}")
+    print(f"{ms:8.3f} ms {ms/tot*100:5.1f}%  n={n:3d} {tf:7.1f} TF/s  {name[4:]:16s} rows={shp[0]:8d} K={shp[1]:5d} N={shp[2]:5d} {shp[3] if len(shp) > 3 else ''}")
