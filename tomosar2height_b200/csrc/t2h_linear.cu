@@ -332,7 +332,13 @@ constexpr int P_THREADS = 448;  // producer, MMA, 4 transform warps, 2 x 4 epilo
 template <bool F16, int BLOCK_N, int WSTEPS = 0, bool PAIR = false, bool DS = false>
 struct PSmem {
   static constexpr bool WRES = WSTEPS > 0;
-  static constexpr int STAGES = PAIR ? (DS ? 3 : 4) : (WRES ? (WSTEPS <= 2 ? 4 : 2) : (F16 ? (BLOCK_N == 128 ? 3 : 4) : (BLOCK_N == 128 ? 4 : 6)));
+  // WIDE (CTA pairs, 256-wide tiles): a 256 x 256 tile per pair.  Both accumulators (2 x 256 columns) fill the
+  // tensor memory, so the split x operand stays in SHARED memory: the transform warps overwrite each 128-byte fp32
+  // row of an x box (32 k) with [hi: 32 fp16 | lo: 32 fp16] in place -- still a K-major SWIZZLE_128B tile, whose
+  // k-steps 0,1 are the hi and 2,3 the lo halves -- and the MMAs read A through shared-memory descriptors.  One
+  // conversion and one L2 -> SM transfer of x now serves 256 output columns instead of 128.
+  static constexpr bool WIDE = PAIR && BLOCK_N == 256;
+  static constexpr int STAGES = WIDE ? (DS ? 2 : 3) : PAIR ? (DS ? 3 : 4) : (WRES ? (WSTEPS <= 2 ? 4 : 2) : (F16 ? (BLOCK_N == 128 ? 3 : 4) : (BLOCK_N == 128 ? 4 : 6)));
   static constexpr int X_BYTES = (F16 ? 2 : 1) * A_BYTES;
   static constexpr int W_BYTES = (F16 ? BLOCK_N * 64 * 2 : BLOCK_N * BLOCK_K * 4) / (PAIR ? 2 : 1);
   static constexpr int STAGE_BYTES = WRES ? X_BYTES : X_BYTES + 2 * W_BYTES;   // x raw (| w hi | w lo)
@@ -343,9 +349,9 @@ struct PSmem {
   static constexpr int TMEM_COLS = 512;
   static constexpr int A_COL0 = 2 * BLOCK_N;
   static_assert(!WRES || (F16 && BLOCK_N == 128), "weight-resident: fp16, 128-wide tiles");
-  static_assert(!PAIR || (F16 && BLOCK_N == 128 && !WRES), "CTA pairs: fp16, 128-wide tiles");
+  static_assert(!PAIR || (F16 && (BLOCK_N == 128 || BLOCK_N == 256) && !WRES), "CTA pairs: fp16, 128- or 256-wide tiles");
   static_assert(!DS || PAIR, "double staging slots: CTA pairs");
-  static_assert(A_COL0 + STAGES * 64 <= 512, "tensor memory: two accumulators + the split x stages");
+  static_assert(WIDE ? A_COL0 == 512 : A_COL0 + STAGES * 64 <= 512, "tensor memory: two accumulators (+ the split x stages)");
   static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
 
@@ -536,7 +542,14 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           for (int k = 0; k < 4; ++k) {
             const uint64_t b_hi = b_hi0 + (uint64_t)(k * 2), b_lo = b_lo0 + (uint64_t)(k * 2);  // +32 bytes (>> 4)
             const uint32_t a_hi = a_hi0 + k * 8, a_lo = a_hi + 32;
-            if (PAIR) {
+            if constexpr (S::WIDE) {
+              // A from shared memory: box k / 2 of the stage, (hi | lo) halves of its 128-byte rows, 32 bytes per k-step
+              const uint64_t sa_hi = make_smem_desc(base + s * S::STAGE_BYTES + (k >> 1) * A_BYTES + (k & 1) * 32, 16, 1024);
+              const uint64_t sa_lo = sa_hi + 4;  // + 64 bytes (>> 4)
+              mma_f16_ss_pair(tmem_d, sa_lo, b_hi, idesc, (kc | k) != 0);
+              mma_f16_ss_pair(tmem_d, sa_hi, b_lo, idesc, 1);
+              mma_f16_ss_pair(tmem_d, sa_hi, b_hi, idesc, 1);
+            } else if (PAIR) {
               mma_f16_ts_pair(tmem_d, a_lo, b_hi, idesc, (kc | k) != 0);
               mma_f16_ts_pair(tmem_d, a_hi, b_lo, idesc, 1);
               mma_f16_ts_pair(tmem_d, a_hi, b_hi, idesc, 1);
@@ -573,7 +586,34 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
         const uint32_t ph = (uint32_t)((it / STAGES) & 1);
         mbar_wait(full_tma(s), ph);
         const uint32_t a_dst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + S::A_COL0 + s * 64;
-        if (F16) {
+        if constexpr (S::WIDE) {
+#pragma unroll
+          for (int box = 0; box < 2; ++box) {
+            uint8_t* row = base_ptr + s * S::STAGE_BYTES + box * A_BYTES + t * 128;
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j] = *reinterpret_cast<const float4*>(row + ((j ^ (t & 7)) << 4));
+              if (p.relu_in) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); v[j].z = fmaxf(v[j].z, 0.f); v[j].w = fmaxf(v[j].w, 0.f); }
+              v[j].x *= sx; v[j].y *= sx; v[j].z *= sx; v[j].w *= sx;
+            }
+            uint4 h[4], l[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              split_f16x2(v[2 * c].x, v[2 * c].y, h[c].x, l[c].x);
+              split_f16x2(v[2 * c].z, v[2 * c].w, h[c].y, l[c].y);
+              split_f16x2(v[2 * c + 1].x, v[2 * c + 1].y, h[c].z, l[c].z);
+              split_f16x2(v[2 * c + 1].z, v[2 * c + 1].w, h[c].w, l[c].w);
+            }
+            // the whole fp32 row is in registers: overwrite it with 16-byte chunks 0-3 = hi, 4-7 = lo (same swizzle)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              *reinterpret_cast<uint4*>(row + ((c ^ (t & 7)) << 4)) = h[c];
+              *reinterpret_cast<uint4*>(row + (((4 + c) ^ (t & 7)) << 4)) = l[c];
+            }
+          }
+          fence_proxy_async_smem();
+        } else if (F16) {
 #pragma unroll
           for (int box = 0; box < 2; ++box) {
             const float* x_row = reinterpret_cast<const float*>(base_ptr + s * S::STAGE_BYTES + box * A_BYTES + t * 128);
@@ -627,7 +667,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
     const float inv = F16 ? pow2f(-(f16_scale_exp(*p.x_absmax) + f16_scale_exp(*p.w_absmax))) : 1.f;
     const int epi_mode = (p.mask && p.residual) || (p.aux_kind == 0 && (p.mask || p.residual)) ? 3 : p.aux_kind;
     uint32_t aux_phase = 0;
-    bool prev_two = false;  // DS: the group's latest store came from slot 1
+    bool prev_even = false;  // DS: the group's latest store came from slot 1 (an even number of blocks in its last tile)
     float out_max = 0.f;
     int64_t local = 0;
     for (int64_t tile = vblock; tile < n_tiles_total; tile += vgrid, ++local) {
@@ -641,24 +681,28 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
       const bool row_ok = row < p.rows;
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
       bool have_acc = false;
-      const bool two = DS && eh + 2 < n_blocks;  // DS: the group has a second block in this tile (slot 1)
-      if (DS && p.aux_kind && leader && eh < n_blocks) {
-        // both mask / residual blocks of the tile go out before the accumulator is waited for; a slot is free
-        // once the store that last used it has been read (slot 0: all but the latest store, if that was slot 1's)
-        if (prev_two) tma_store_wait_read_but_one(); else tma_store_wait_read();
-        mbar_arrive_expect_tx(aux_bar2(eh, 0), A_BYTES);
-        if (p.conv) tma_load_4d(group_staging, &tm_aux, aux_bar2(eh, 0), n0 + eh * 32, px0, py0, img);
-        else tma_load_2d(group_staging, &tm_aux, aux_bar2(eh, 0), n0 + eh * 32, m0);
-        if (two) {
+      // DS: the group's blocks of this tile (2 of a 128-wide, 4 of a 256-wide tile) alternate between its two slots
+      const int nb_grp = DS && n_blocks > eh ? (n_blocks - eh + 1) >> 1 : 0;
+      auto load_aux = [&](int b) {  // (leader) mask / residual block b of the group -> slot b & 1
+        const uint32_t dst = group_staging + (b & 1) * A_BYTES, bar = aux_bar2(eh, b & 1);
+        mbar_arrive_expect_tx(bar, A_BYTES);
+        if (p.conv) tma_load_4d(dst, &tm_aux, bar, n0 + (eh + 2 * b) * 32, px0, py0, img);
+        else tma_load_2d(dst, &tm_aux, bar, n0 + (eh + 2 * b) * 32, m0);
+      };
+      if (DS && p.aux_kind && leader && nb_grp > 0) {
+        // the first two mask / residual blocks of the tile go out before the accumulator is waited for; a slot is
+        // free once the store that last used it has been read (slot 0: all but the latest store, if that was slot 1's)
+        if (prev_even) tma_store_wait_read_but_one(); else tma_store_wait_read();
+        load_aux(0);
+        if (nb_grp > 1) {
           tma_store_wait_read();
-          mbar_arrive_expect_tx(aux_bar2(eh, 1), A_BYTES);
-          if (p.conv) tma_load_4d(group_staging + A_BYTES, &tm_aux, aux_bar2(eh, 1), n0 + (eh + 2) * 32, px0, py0, img);
-          else tma_load_2d(group_staging + A_BYTES, &tm_aux, aux_bar2(eh, 1), n0 + (eh + 2) * 32, m0);
+          load_aux(1);
         }
       }
 #pragma unroll 1
       for (int cb = (BLOCK_N == 32 ? 0 : eh); cb < n_blocks; cb += 2) {
-        const int slot = DS ? (cb - eh) >> 1 : 0;
+        const int blk = (cb - eh) >> 1;  // (DS) index of the block within the group's share of the tile
+        const int slot = DS ? blk & 1 : 0;
         const uint32_t my_staging = group_staging + slot * A_BYTES;
         float* srow = group_srow + slot * (A_BYTES / 4);
         if (DS && p.aux_kind) {
@@ -667,7 +711,7 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
         } else {
           // the slot is free once the store that last used it has been read
           if (leader) {
-            if (DS && (slot == 1 || prev_two)) tma_store_wait_read_but_one();
+            if (DS && (blk > 0 || prev_even)) tma_store_wait_read_but_one();
             else tma_store_wait_read();
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + eh) : "memory");
@@ -758,9 +802,13 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
           if (p.conv) tma_store_4d(&tm_out, my_staging, n0 + cb * 32, px0, py0, img);
           else tma_store_2d(&tm_out, my_staging, n0 + cb * 32, m0);
           tma_store_commit();
+          if (DS && p.aux_kind && blk + 2 < nb_grp) {  // 256-wide tiles: the slot's next mask / residual block
+            tma_store_wait_read();
+            load_aux(blk + 2);
+          }
         }
       }
-      if (DS && eh < n_blocks) prev_two = two;
+      if (DS && nb_grp > 0) prev_even = (nb_grp & 1) == 0;
       if (BLOCK_N != 32 && !have_acc) {
         // a group without a block in this (narrow last) tile still takes part in the accumulator hand-over, in step
         mbar_wait(acc_full(acc), acc_ph);
@@ -1749,14 +1797,25 @@ extern "C" int t2h_linear_fwd_f16(const float* x1, int64_t ld_x1, int k1, const 
   const int pair = ablation_switch("T2H_LINEAR_PAIR", 1);
   if (pair && rows >= 2 * BLOCK_M) {
     CUtensorMap whi2, wlo2;
+    // Tile and epilogue flavour (measured on 2^20 rows, profiles/r02_gemm_probe_tiles.txt):
+    //   256 x 256 tiles per pair (each CTA stages 128 weight rows) where n_out is a multiple of 256 and K > 128 --
+    //   one conversion and one L2 -> SM transfer of x per 256 output columns (K = 1024 -> N = 512: 2.70 -> 2.34 ms;
+    //   K = 128 -> N = 256 is bound by its epilogue and gets slower, 0.37 -> 0.43 ms);
+    //   two staging slots per epilogue group where a mask / residual block is read per output block and a tile's
+    //   MMAs are short (K <= 256: K = 256 -> N = 512 with a mask 1.26 -> 1.02 ms, K = 128 -> N = 256 0.73 -> 0.55 ms;
+    //   with K >= 512 the deeper load ring is worth more than the second slot).
+    int wide = n_out % 256 == 0 && a.k_chunks > 4;
+    int ds = a.aux_kind != 0 && a.k_chunks <= 8;
+    const int force_wide = ablation_switch("T2H_LINEAR_WIDE", -1), force_ds = ablation_switch("T2H_LINEAR_DS", -1);
+    if (force_wide >= 0) wide = force_wide && n_out % 256 == 0;
+    if (force_ds >= 0) ds = force_ds;
+    if (wide) {
+      if (!make_map_f16(&whi2, w_hi, k_total, n_out, 128) || !make_map_f16(&wlo2, w_lo, k_total, n_out, 128)) return T2H_ERR_CUDA;
+      if (ds) return launch_linear_persistent<true, 256, 0, true, true>(m1, m2, whi2, wlo2, mout, maux, a, (cudaStream_t)stream);
+      return launch_linear_persistent<true, 256, 0, true>(m1, m2, whi2, wlo2, mout, maux, a, (cudaStream_t)stream);
+    }
     if (!make_map_f16(&whi2, w_hi, k_total, n_out, 64) || !make_map_f16(&wlo2, w_lo, k_total, n_out, 64)) return T2H_ERR_CUDA;
-    // Two staging slots per epilogue group (and three load stages) where a mask / residual block is read per output
-    // block and a tile's MMAs are short (K <= 256): measured on 2^20 rows, K = 256 -> N = 512 with a mask 1.26 ->
-    // 1.07 ms, K = 128 -> N = 256 0.73 -> 0.55 ms; with K >= 512 the fourth load stage is worth more (K = 512 ->
-    // N = 256: 0.82 vs 0.97 ms), and without a mask / residual it is a wash.  T2H_LINEAR_DS = 0 never, 2 always.
-    const int ds = ablation_switch("T2H_LINEAR_DS", 1);
-    if (ds == 2 || (ds == 1 && a.aux_kind && a.k_chunks <= 8))
-      return launch_linear_persistent<true, 128, 0, true, true>(m1, m2, whi2, wlo2, mout, maux, a, (cudaStream_t)stream);
+    if (ds) return launch_linear_persistent<true, 128, 0, true, true>(m1, m2, whi2, wlo2, mout, maux, a, (cudaStream_t)stream);
     return launch_linear_persistent<true, 128, 0, true>(m1, m2, whi2, wlo2, mout, maux, a, (cudaStream_t)stream);
   }
   // K <= 256: the weight tile of a CTA's N-tile can stay resident in shared memory (T2H_LINEAR_WRES=1).  OFF by

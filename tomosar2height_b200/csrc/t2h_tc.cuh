@@ -144,6 +144,16 @@ __device__ __forceinline__ void mma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_a
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z)
       : "memory");
 }
+// same with A read through a shared-memory descriptor (this CTA's 128 rows, K-major) in each CTA
+__device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
 // completion of the pair's MMAs -> the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
   const uint16_t mask = 3;
