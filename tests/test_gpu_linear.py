@@ -226,15 +226,16 @@ def test_linear_f16_rows_of_very_different_magnitude():
     assert ((y.cpu().double() - ref).abs() / row_scale).max().item() < 1e-4
 
 
-def test_linear_f16_epilogues_concat_and_ragged_k():
+@pytest.mark.parametrize("n_out", [200, 256, 512])  # 128-wide tiles (ragged last tile) / 256 x 256 pair tiles
+def test_linear_f16_epilogues_concat_and_ragged_k(n_out):
     g = torch.Generator().manual_seed(1)
     rows = 1500
     a = torch.randn(rows, 96, generator=g).cuda()    # 3 chunks + 2 chunks = odd number of 32-wide chunks
     b2 = torch.randn(rows, 64, generator=g).cuda()
-    w = (torch.randn(200, 160, generator=g) / 12).cuda()
-    bias = torch.randn(200, generator=g).cuda()
-    res = torch.randn(rows, 200, generator=g).cuda()
-    mask = torch.randn(rows, 200, generator=g).cuda()
+    w = (torch.randn(n_out, 160, generator=g) / 12).cuda()
+    bias = torch.randn(n_out, generator=g).cuda()
+    res = torch.randn(rows, n_out, generator=g).cuda()
+    mask = torch.randn(rows, n_out, generator=g).cuda()
     x = torch.cat([a, b2], 1).double().relu()
     full = x @ w.double().t() + bias.double()
     y, slot = _linear_f16_raw(a, w, bias, x2=b2, relu_in=True, mask=mask)
@@ -250,7 +251,7 @@ def test_linear_f16_epilogues_concat_and_ragged_k():
     assert (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
     # K = 136 (multiple of 8, not of 32): the last chunk is zero-filled by TMA
     xs = torch.randn(rows, 136, generator=g).cuda()
-    ws = (torch.randn(96, 136, generator=g) / 11).cuda()
+    ws = (torch.randn(96 if n_out == 200 else n_out, 136, generator=g) / 11).cuda()
     y, _ = _linear_f16_raw(xs, ws)
     ref = xs.double() @ ws.double().t()
     assert (y.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
@@ -300,3 +301,25 @@ def test_fork2_sums_gradient_branches_and_publishes_their_maximum():
     with torch.no_grad():
         p, q = L.fork2(h)
     assert p is h and q is h
+
+
+@pytest.mark.parametrize("rows,K,N", [(70000, 512, 256), (40000, 1024, 512), (50000, 256, 512), (300, 288, 256)])
+def test_linear_f16_wide_tiles_with_mask_and_residual(rows, K, N):
+    """256 x 256 pair tiles: four output blocks per epilogue group and tile, mask / residual blocks through one
+    (K >= 512) or two (K <= 256) staging slots per group, many tiles per CTA pair."""
+    g = torch.Generator().manual_seed(rows + K)
+    x = torch.randn(rows, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    aux = torch.randn(rows, N, generator=g).cuda()
+    full = x.double() @ w.double().t() + bias.double()
+    tol = 2e-6 * max(1.0, K / 256)
+    y, _ = _linear_f16_raw(x, w, bias, mask=aux)
+    assert (y.double() - full * (aux > 0).double()).abs().max().item() < tol * full.abs().max().item()
+    y, slot = _linear_f16_raw(x, w, bias, residual=aux)
+    ref = full + aux.double()
+    assert (y.double() - ref).abs().max().item() < tol * ref.abs().max().item()
+    assert slot.view(torch.float32).item() == y.abs().max().item()
+    y, _ = _linear_f16_raw(x, w, bias, relu_in=True)
+    ref = x.double().relu() @ w.double().t() + bias.double()
+    assert (y.double() - ref).abs().max().item() < tol * ref.abs().max().item()

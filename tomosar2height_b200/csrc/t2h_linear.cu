@@ -1147,14 +1147,21 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
 // conversion work and half the L2 -> SM bytes per MMA cycle, and four 48 KB stages fit beside the accumulator.
 // Warps: 0 producer (own tiles, own barrier), 1 MMA issuer (leader CTA only), 2-5 g^T -> tensor memory + bias
 // gradient, 6-9 x -> fp16 hi / lo MN-major tiles; all eight drain the accumulator (32-column blocks 0-3 / 4-7).
-constexpr int WGP_STAGES = 4;
+#ifndef T2H_WGP_STAGES
+#define T2H_WGP_STAGES 6   // measured: 3 -> 4 stages 3-13 % faster (the life of a stage is a memory latency + conversion + MMAs)
+#endif
+constexpr int WGP_STAGES = T2H_WGP_STAGES;
 constexpr int WGP_X_RAW = 4 * WG_GROUP_BYTES;            // this CTA's 128 columns of x: four 32-float boxes
 constexpr int WGP_X16 = WG_ROWS * 128 * 2;               // one fp16 operand tile
-constexpr int WGP_STAGE_BYTES = WG_A_BYTES + WGP_X_RAW + 2 * WGP_X16;   // g raw | x raw | x hi | x lo
+// g raw | x: the fp32 tile is converted IN PLACE to (x hi | x lo) -- same 16 KB; the four converting warps hold the
+// whole tile in registers across a named barrier before the first of them writes
+constexpr int WGP_STAGE_BYTES = WG_A_BYTES + WGP_X_RAW;
+static_assert(2 * WGP_X16 == WGP_X_RAW, "in-place conversion: fp16 hi + lo fill the fp32 tile");
 constexpr int WGP_TOTAL = WGP_STAGES * WGP_STAGE_BYTES + 256 + 1024;
 constexpr int WGP_TILE = 256;                            // dW tile edge (both ways)
 constexpr int WGP_A_COLS = 32;                           // TMEM columns of (g hi | g lo) per stage
-constexpr int WGP_TMEM_COLS = 512;                       // 256 accumulator + 4 x 32 operand columns
+constexpr int WGP_TMEM_COLS = 512;                       // 256 accumulator + stages x 32 operand columns
+static_assert(WGP_TILE + WGP_STAGES * WGP_A_COLS <= WGP_TMEM_COLS, "tensor memory");
 static_assert(WGP_TOTAL <= 227 * 1024, "shared memory");
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -1225,7 +1232,7 @@ wgrad_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
         mbar_wait_cluster(full_ab(s), ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t b_hi0 = base + s * WGP_STAGE_BYTES + WG_A_BYTES + WGP_X_RAW;
+          const uint32_t b_hi0 = base + s * WGP_STAGE_BYTES + WG_A_BYTES;
           const uint64_t d_hi0 = make_smem_desc(b_hi0, 4096, 1024, kLayoutSW128);
           const uint64_t d_lo0 = make_smem_desc(b_hi0 + WGP_X16, 4096, 1024, kLayoutSW128);
 #pragma unroll
@@ -1275,17 +1282,24 @@ wgrad_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
         // 16 consecutive lanes take one row of a box pair: 128 contiguous bytes in, one swizzled 128-byte row out
         const int tb = threadIdx.x - 192;
         const float4* raw = reinterpret_cast<const float4*>(base_ptr + s * WGP_STAGE_BYTES + WG_A_BYTES);
-        uint8_t* bhi = base_ptr + s * WGP_STAGE_BYTES + WG_A_BYTES + WGP_X_RAW;
+        uint8_t* bhi = base_ptr + s * WGP_STAGE_BYTES + WG_A_BYTES;
         uint8_t* blo = bhi + WGP_X16;
+        float4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int unit = (tb >> 4) + 8 * i, r = unit & 31, j = tb & 15;
           const int box = 2 * (unit >> 5) + (j >> 3), q = j & 7;
-          float4 v = raw[box * 256 + r * 8 + q];
-          if (p.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          v[i] = raw[box * 256 + r * 8 + q];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four x warps: the fp32 tile is in registers
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int unit = (tb >> 4) + 8 * i, r = unit & 31, j = tb & 15;
+          const int box = 2 * (unit >> 5) + (j >> 3), q = j & 7;
+          if (p.relu_in) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
           uint2 h, l;
-          split_f16x2(v.x * sx, v.y * sx, h.x, l.x);
-          split_f16x2(v.z * sx, v.w * sx, h.y, l.y);
+          split_f16x2(v[i].x * sx, v[i].y * sx, h.x, l.x);
+          split_f16x2(v[i].z * sx, v[i].w * sx, h.y, l.y);
           const int chunk = ((box & 1) << 2) | (q >> 1);  // 16-byte chunk of the 128-byte row (64 fp16 along k_in)
           const int off = (box >> 1) * 4096 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4) + ((q & 1) << 3);
           *reinterpret_cast<uint2*>(bhi + off) = h;
