@@ -264,6 +264,50 @@ size_t t2h_colsum_workspace_bytes(int64_t rows, int n);
 int t2h_colsum(const float* g, int64_t ld_g, int64_t rows, int n, void* workspace,
                size_t workspace_bytes, float* out, t2h_stream_t stream);
 
+/* ---- one-call point-MLP blocks (t2h_resblock_fwd/bwd, t2h_comm_mlp_fwd/bwd) ----------
+ * COMPOSITIONS of the GEMM entry points above, enqueued on `stream` in the order the Python mirror issues them
+ * (not single fused kernels): ReLU-on-load, the concat halves as two K sources, bias, the
+ * shortcut / fc_c result as the residual of the last GEMM and the ReLU mask of the input gradients are fused into
+ * the launches.  Weights are plain fp32 row-major [n_out][k_in]; the operand splits (3xTF32, or 3xFP16 for
+ * n_out > 64 and K >= 128), the transposed weights of the input gradients and the row-split partials of the
+ * weight gradients live in `workspace` (>= the matching *_workspace_bytes, which covers forward and backward).
+ * Every dimension is a multiple of 4; with two sources k1 is a multiple of 32.
+ *
+ * ResnetBlockFC, block/resnet.py:46-54 (instances pointnet.py:37-39,73-79), x = [x1 | x2] (x2 nullable):
+ *   net = fc_0(relu(x)),  out = shortcut(x) + fc_1(relu(net));  w_shortcut NULL = identity (k2 = 0, k1 = n_out).
+ *   `net` (rows x n_h, the PRE-activation input of fc_1) is an output of the forward and an input of the backward.
+ * backward: d_w1 = g^T relu(net), d_b1 = sum g;  g_net = (g w1) * (net > 0);  d_w0 = g_net^T relu(x), d_b0 = sum g_net;
+ *   d_w_shortcut = g^T x;  d_x = (g_net w0) * (x > 0) + g w_shortcut (identity: + g).  d_x1 / d_x2 / d_b0 / d_b1 nullable. */
+size_t t2h_resblock_workspace_bytes(int64_t rows, int k1, int k2, int n_h, int n_out, int has_shortcut);
+int t2h_resblock_fwd(const float* x1, int64_t ld_x1, int k1, const float* x2, int64_t ld_x2, int k2,
+                     int64_t rows, const float* w0, const float* b0, int n_h, const float* w1,
+                     const float* b1, const float* w_shortcut, int n_out, void* workspace,
+                     size_t workspace_bytes, float* net, int64_t ld_net, float* out, int64_t ld_out,
+                     t2h_stream_t stream);
+int t2h_resblock_bwd(const float* grad_out, int64_t ld_g, const float* x1, int64_t ld_x1, int k1,
+                     const float* x2, int64_t ld_x2, int k2, const float* net, int64_t ld_net,
+                     int64_t rows, const float* w0, int n_h, const float* w1, const float* w_shortcut,
+                     int n_out, void* workspace, size_t workspace_bytes, float* d_x1, int64_t ld_dx1,
+                     float* d_x2, int64_t ld_dx2, float* d_w0, float* d_b0, float* d_w1, float* d_b1,
+                     float* d_w_shortcut, t2h_stream_t stream);
+
+/* fc_comm + fc_c, encoder/alto.py:63-69,123-128 (and 164-170, 248-253):
+ *   hidden = c w0^T + b0 (rows x 2C, pre-activation, an output),  out = relu(hidden) w2^T + b2 (+ c_last wc^T + bc);
+ *   c_last NULL on the first level (C_prev ignored).
+ * backward: d_w2 = g^T relu(hidden), d_b2 = sum g;  g_h = (g w2) * (hidden > 0);  d_w0 = g_h^T c, d_b0 = sum g_h;
+ *   d_c = g_h w0;  d_wc = g^T c_last, d_bc = sum g, d_c_last = g wc.  d_c / d_c_last / bias gradients nullable. */
+size_t t2h_comm_mlp_workspace_bytes(int64_t rows, int C, int C_prev);
+int t2h_comm_mlp_fwd(const float* c, int64_t ld_c, int C, const float* c_last, int64_t ld_cl, int C_prev,
+                     int64_t rows, const float* w0, const float* b0, const float* w2, const float* b2,
+                     const float* wc, const float* bc, void* workspace, size_t workspace_bytes,
+                     float* hidden, int64_t ld_hidden, float* out, int64_t ld_out, t2h_stream_t stream);
+int t2h_comm_mlp_bwd(const float* grad_out, int64_t ld_g, const float* c, int64_t ld_c, int C,
+                     const float* c_last, int64_t ld_cl, int C_prev, const float* hidden,
+                     int64_t ld_hidden, int64_t rows, const float* w0, const float* w2, const float* wc,
+                     void* workspace, size_t workspace_bytes, float* d_c, int64_t ld_dc, float* d_c_last,
+                     int64_t ld_dcl, float* d_w0, float* d_b0, float* d_w2, float* d_b2, float* d_wc,
+                     float* d_bc, t2h_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,21 @@ def test_argument_validation_without_gpu(lib):
     assert lib.t2h_xy_keys(None, 0, 3, 1, 100, 1, None, None, None) == 1
 
 
+def test_block_workspace_queries_plan_without_a_gpu(lib):
+    """t2h_resblock / t2h_comm_mlp: the workspace query runs the launch plan dry (host only)"""
+    small = lib.t2h_resblock_workspace_bytes(1000, 32, 32, 32, 32, 1)
+    large = lib.t2h_resblock_workspace_bytes(100000, 32, 32, 32, 32, 1)
+    assert 256 < small < large                        # g_net scratch grows with the rows
+    assert lib.t2h_resblock_workspace_bytes(1000, 30, 0, 32, 32, 1) == 256     # unsupported width: nothing to plan
+    assert lib.t2h_resblock_workspace_bytes(1000, 64, 0, 32, 32, 0) == 256     # identity shortcut needs size_in == size_out
+    first = lib.t2h_comm_mlp_workspace_bytes(1000, 128, 0)
+    later = lib.t2h_comm_mlp_workspace_bytes(1000, 128, 64)
+    assert 256 < first < later                        # fc_c adds a weight gradient and a transposed weight
+    # bad arguments are refused before anything is launched
+    assert lib.t2h_resblock_fwd(None, 0, 32, None, 0, 0, 10, None, None, 32, None, None, None, 32, None, 0, None, 0, None, 0, None) == 1
+    assert lib.t2h_comm_mlp_fwd(None, 0, 32, None, 0, 0, 10, None, None, None, None, None, None, None, 0, None, 0, None, 0, None) == 1
+
+
 @pytest.mark.parametrize("name", list(CASES) + ["berlin_full", "berlin_image_full", "munich_full", "munich_image_full"])
 def test_state_dict_matches_reference(golden_dir, name):
     with open(os.path.join(golden_dir, f"state_dict_{name}.json")) as fh:

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libt2h.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["t2h_topology.cu", "t2h_segment.cu", "t2h_sample.cu", "t2h_scene.cu", "t2h_linear.cu"]
+SOURCES = ["t2h_topology.cu", "t2h_segment.cu", "t2h_sample.cu", "t2h_scene.cu", "t2h_linear.cu", "t2h_blocks.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -56,6 +56,14 @@ SIGNATURES = {
     "t2h_conv3x3_wgrad": [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _sz, _p, _p, _p],
     "t2h_colsum_workspace_bytes": [_i64, _i32],
     "t2h_colsum": [_p, _i64, _i64, _i32, _p, _sz, _p, _p],
+    "t2h_resblock_workspace_bytes": [_i64, _i32, _i32, _i32, _i32, _i32],
+    "t2h_resblock_fwd": [_p, _i64, _i32, _p, _i64, _i32, _i64, _p, _p, _i32, _p, _p, _p, _i32, _p, _sz, _p, _i64, _p, _i64, _p],
+    "t2h_resblock_bwd": [_p, _i64, _p, _i64, _i32, _p, _i64, _i32, _p, _i64, _i64, _p, _i32, _p, _p, _i32, _p, _sz,
+                         _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p],
+    "t2h_comm_mlp_workspace_bytes": [_i64, _i32, _i32],
+    "t2h_comm_mlp_fwd": [_p, _i64, _i32, _p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _i64, _p, _i64, _p],
+    "t2h_comm_mlp_bwd": [_p, _i64, _p, _i64, _i32, _p, _i64, _i32, _p, _i64, _i64, _p, _p, _p, _p, _sz,
+                         _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p],
     "t2h_linear_fwd": [_p, _i64, _i32, _p, _i64, _i32, _i64, _p, _p, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p],
     "t2h_linear_wgrad_f16": [_p, _i64, _p, _p, _i64, _p, _i64, _i32, _i32, _i32, _p, _sz, _p, _i64, _p, _p],
     "t2h_conv3x3_fwd_f16": [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _p],
@@ -69,7 +77,8 @@ SIGNATURES = {
 _RESTYPE = {"t2h_status_string": ctypes.c_char_p, "t2h_sort_workspace_bytes": _sz,
             "t2h_linear_wgrad_workspace_bytes": _sz, "t2h_colsum_workspace_bytes": _sz,
             "t2h_conv3x3_wgrad_workspace_bytes": _sz, "t2h_bilinear_sample_bwd_workspace_bytes": _sz,
-            "t2h_seg_workspace_bytes": _sz}
+            "t2h_seg_workspace_bytes": _sz, "t2h_resblock_workspace_bytes": _sz,
+            "t2h_comm_mlp_workspace_bytes": _sz}
 
 _lib = None
 _lock = threading.Lock()
