@@ -36,27 +36,56 @@ class _SplitCache:
         self._store = {}
 
     @staticmethod
-    def _split(w, f16):
+    def _buffers(shape, device, f16):
         if not f16:
-            hi, lo = torch.empty_like(w), torch.empty_like(w)
-            _lib.call("t2h_split_tf32", ptr(w), w.numel(), ptr(hi), ptr(lo))
-            return hi, lo
-        slot = torch.empty(1, dtype=torch.int32, device=w.device)
-        hi = torch.empty(w.shape, dtype=torch.float16, device=w.device)
-        lo = torch.empty_like(hi)
-        _lib.call("t2h_absmax", ptr(w), w.shape[1], w.shape[1], None, 0, 0, w.shape[0], ptr(slot))
-        _lib.call("t2h_split_f16", ptr(w), w.numel(), ptr(slot), ptr(hi), ptr(lo))
-        return hi, lo, slot
+            return torch.empty(shape, dtype=torch.float32, device=device), torch.empty(shape, dtype=torch.float32, device=device)
+        return (torch.empty(shape, dtype=torch.float16, device=device), torch.empty(shape, dtype=torch.float16, device=device),
+                torch.empty(1, dtype=torch.int32, device=device))
+
+    @staticmethod
+    def _split_into(w, f16, bufs):
+        """split of the dense 2-D fp32 matrix ``w`` into existing buffers (``_buffers``)"""
+        if not f16:
+            _lib.call("t2h_split_tf32", ptr(w), w.numel(), ptr(bufs[0]), ptr(bufs[1]))
+        else:
+            _lib.call("t2h_absmax", ptr(w), w.shape[1], w.shape[1], None, 0, 0, w.shape[0], ptr(bufs[2]))
+            _lib.call("t2h_split_f16", ptr(w), w.numel(), ptr(bufs[2]), ptr(bufs[0]), ptr(bufs[1]))
+        return bufs
+
+    @classmethod
+    def _split(cls, w, f16):
+        return cls._split_into(w, f16, cls._buffers(w.shape, w.device, f16))
 
     def _lookup(self, weight, key, builder, f16):
         key = key + (f16,)
-        hit = None if capture_mode else self._store.get(key)
+        if static_params is not None:
+            # graph.py, eager warm-up before a capture and the capture itself.  A split of a PARAMETER does not belong
+            # into the graph (it would be recomputed by every replay although the weights only change once per
+            # optimizer step): the warm-up gives it persistent buffers -- allocated OUTSIDE the graph's memory pool,
+            # whose blocks are recycled between the captured kernels -- and a recipe; the capture only hands the
+            # buffers out, and GraphedTrainStep rewrites them eagerly whenever a parameter's version has moved.
+            param = static_params.get(weight.data_ptr())
+            if param is not None and param.shape == weight.shape:
+                skey = (id(param),) + key[1:]
+                rec = static_recipes.get(skey)
+                if rec is None and not capture_mode:
+                    with torch.no_grad():
+                        shape = builder(param.detach()).shape
+                    rec = static_recipes[skey] = (param, builder, f16, self._buffers(shape, param.device, f16))
+                if rec is not None:
+                    if not capture_mode:
+                        with torch.no_grad():
+                            self._split_into(builder(param.detach()).contiguous(), f16, rec[3])
+                    return rec[3]
+        if capture_mode:
+            # splits of temporaries (padded / sliced weights, produced by captured kernels) stay inside the graph
+            with torch.no_grad():
+                return self._split(builder(weight.detach()).contiguous(), f16)  # lives in the graph's private pool
+        hit = self._store.get(key)
         if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
             return hit[3]
         with torch.no_grad():
             split = self._split(builder(weight.detach()).contiguous(), f16)
-        if capture_mode:
-            return split  # lives in the graph's private pool; not a cache entry
         if len(self._store) > 256:
             # entries of temporaries (reshaped / padded / permuted weight views are new tensors on every call) only
             # hold dead weak references: drop them so that their hi / lo device tensors are freed
@@ -82,9 +111,19 @@ class _SplitCache:
 
 
 _cache = _SplitCache()
-# True while a CUDA graph is being captured (graph.py): splits are recomputed inside the graph, because the
-# weights change between replays
+# True while a CUDA graph is being captured (graph.py).  The weights change between replays: splits of parameters
+# live in persistent buffers that graph.py refreshes (static_params: data_ptr -> Parameter, static_recipes: the
+# recipes collected during the capture); any other split is recomputed inside the graph
 capture_mode = False
+static_params = None
+static_recipes = None
+
+
+def refresh_static_splits(recipes):
+    """recompute every hoisted parameter split into its persistent buffers (eager launches on the current stream)"""
+    with torch.no_grad():
+        for param, builder, f16, bufs in recipes.values():
+            _SplitCache._split_into(builder(param.detach()).contiguous(), f16, bufs)
 # ablation switch for benchmarks / debugging only: run the point MLPs as plain cuBLAS fp32 GEMMs
 USE_LIBRARY_GEMM = os.environ.get("T2H_LINEAR", "") == "cublas"
 # wide layers run the 3xFP16 flavour (twice the tensor-core rate of 3xTF32, same fp32-grade accuracy);
