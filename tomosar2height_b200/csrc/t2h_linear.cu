@@ -32,6 +32,10 @@ constexpr int BLOCK_K = 32;   // fp32 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 8;     // tf32
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
 constexpr int kThreads = 192;
+// every kernel keeps its mbarriers in a 256-byte block (at most 26 of 32 words used); the word that receives the
+// tensor-memory base address from tcgen05.alloc sits at its end, 16-byte aligned and away from the barriers that
+// thread 0 initialises at the same time (keeps compute-sanitizer's racecheck quiet about that pair of accesses)
+constexpr uint32_t kTmemSlotOffset = 240;
 
 struct LinearArgs {
   int64_t rows;
@@ -98,8 +102,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_con
   auto full_ab = [&](int s) { return bars + 8u * (STAGES + s); };
   auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   const uint32_t tmem_full = bars + 8u * (3 * STAGES);
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * S::STAGE_BYTES + 8 * (3 * STAGES + 1));
+  const uint32_t tmem_slot = bars + kTmemSlotOffset;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * S::STAGE_BYTES + kTmemSlotOffset);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1-D grid, N-tile fastest: the CTAs that share an x tile are co-scheduled, so the tile is fetched
@@ -396,8 +400,8 @@ linear_x3_persistent_kernel(const __grid_constant__ CUtensorMap tm_x1, const __g
   const uint32_t w_full = bars + 8u * (3 * STAGES + 7);
   auto w_pair = [&](int s) { return bars + 8u * (3 * STAGES + 8 + s); };  // PAIR: both weight halves landed (leader's)
   auto aux_bar2 = [&](int g, int j) { return bars + 8u * (4 * STAGES + 8 + 2 * g + j); };  // DS: per group and slot
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 6);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(staging_ptr + S::STAGING_BYTES + 8 * (3 * STAGES + 6));
+  const uint32_t tmem_slot = bars + kTmemSlotOffset;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(staging_ptr + S::STAGING_BYTES + kTmemSlotOffset);
   // epilogue threads that hand an accumulator back per tile: both groups, or (32-wide tiles) the one that owns the tile
   constexpr uint32_t EPI_ARRIVALS = BLOCK_N == 32 ? 4 : 8;  // one arrival per epilogue warp
 
@@ -906,8 +910,8 @@ wgrad_x3_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
   auto full_ab = [&](int s) { return bars + 8u * (STAGES + s); };
   auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   const uint32_t tmem_full = bars + 8u * (3 * STAGES);
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * S::STAGE_BYTES + 8 * (3 * STAGES + 1));
+  const uint32_t tmem_slot = bars + kTmemSlotOffset;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * S::STAGE_BYTES + kTmemSlotOffset);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_M;   // rows of dW
@@ -1176,8 +1180,8 @@ wgrad_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
   auto full_ab = [&](int s) { return bars + 8u * (STAGES + s); };        // both CTAs' operands are converted (leader's)
   auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };      // the pair's MMAs have read the stage
   const uint32_t tmem_full = bars + 8u * (3 * STAGES);
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * WGP_STAGE_BYTES + 8 * (3 * STAGES + 1));
+  const uint32_t tmem_slot = bars + kTmemSlotOffset;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * WGP_STAGE_BYTES + kTmemSlotOffset);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
